@@ -1,0 +1,128 @@
+// sf_gemm.cu — host launcher + C-ABI for the tcgen05 GEMM (see sf_gemm.cuh).
+#include "sf_gemm.cuh"
+#include "sf_host.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace sf {
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with row stride `ld` elements,
+// box = [box_rows, box_cols], 128-byte swizzle (box_cols * 2 must be 128).
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                      int box_rows, int box_cols) {
+    auto fn = get_encode_fn();
+    if (!fn) return set_error(-38, "cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8) != 0)
+        return set_error(-22, "TMA operand must be 16-byte aligned with a leading dim multiple of 8 (got ld=%lld)",
+                         (long long)ld);
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(-22, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int G, int AM, int BM, int BN>
+static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
+    using Cfg = GemmCfg<G, AM, BM, BN>;
+    CUtensorMap ta, tb;
+    int rc;
+    if (AM == MAJOR_K) rc = make_tmap_2d_bf16(&ta, g.A, g.M, g.K, g.lda, Cfg::BLOCK_M, 64);
+    else               rc = make_tmap_2d_bf16(&ta, g.A, g.K, g.M, g.lda, 64, 64);
+    if (rc) return rc;
+    if (BM == MAJOR_K) rc = make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, Cfg::B_ROWS, 64);
+    else               rc = make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.ldb, 64, 64);
+    if (rc) return rc;
+
+    GemmParams p;
+    p.D = g.D; p.R = reinterpret_cast<const __nv_bfloat16*>(g.R);
+    p.M = g.M; p.N = g.N; p.K = g.K; p.ldd = (int)g.ldd; p.ldr = (int)g.ldr; p.epi = g.epi;
+    p.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+    p.num_n_blocks = (g.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    int clusters = num_sms() / G;
+    if (tiles < clusters) clusters = tiles;
+
+    auto kern = gemm_kernel<G, AM, BM, BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(-22, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * G);
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) return set_error(-5, "gemm launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+int gemm(const GemmDesc& g, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(-22, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
+    if (g.epi < 0 || g.epi > 3) return set_error(-22, "gemm: bad epilogue %d", g.epi);
+    if (g.epi == EPI_BF16_RESID && !g.R) return set_error(-22, "gemm: residual epilogue without R");
+    const int elt = (g.epi >= EPI_F32) ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(g.D) & 15) || (g.ldd * elt) % 16)
+        return set_error(-22, "gemm: D must be 16-byte aligned with 16-byte aligned rows");
+    if (g.epi == EPI_BF16_RESID && ((reinterpret_cast<uintptr_t>(g.R) & 15) || (g.ldr % 8)))
+        return set_error(-22, "gemm: R must be 16-byte aligned with ld multiple of 8");
+    int G = g.cta_group;
+    if (G == 0) G = (g.M > 128) ? 2 : 1;
+    const int key = (G == 2 ? 4 : 0) | (g.a_major ? 2 : 0) | (g.b_major ? 1 : 0);
+    switch (key) {
+        case 0: return launch_cfg<1, MAJOR_K, MAJOR_K, 256>(g, stream);
+        case 1: return launch_cfg<1, MAJOR_K, MAJOR_MN, 256>(g, stream);
+        case 3: return launch_cfg<1, MAJOR_MN, MAJOR_MN, 256>(g, stream);
+        case 4: return launch_cfg<2, MAJOR_K, MAJOR_K, 256>(g, stream);
+        case 5: return launch_cfg<2, MAJOR_K, MAJOR_MN, 256>(g, stream);
+        case 7: return launch_cfg<2, MAJOR_MN, MAJOR_MN, 256>(g, stream);
+        default: return set_error(-22, "gemm: unsupported operand majors a=%d b=%d", g.a_major, g.b_major);
+    }
+}
+
+}  // namespace sf
+
+extern "C" int sf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major,
+                            void* D, int64_t ldd, const void* R, int64_t ldr, int M, int N, int K, int epi,
+                            int cta_group, void* stream) {
+    sf::GemmDesc g;
+    g.A = A; g.lda = lda; g.a_major = a_major; g.B = B; g.ldb = ldb; g.b_major = b_major;
+    g.D = D; g.ldd = ldd; g.R = R; g.ldr = ldr; g.M = M; g.N = N; g.K = K; g.epi = epi; g.cta_group = cta_group;
+    return sf::gemm(g, reinterpret_cast<cudaStream_t>(stream));
+}

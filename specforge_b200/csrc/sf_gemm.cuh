@@ -1,0 +1,310 @@
+// sf_gemm.cuh — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[m, n] = sum_k A(m, k) * B(n, k)        (bf16 inputs, fp32 accumulation in TMEM)
+//
+// Each operand may be stored K-major (row-major [rows, K], the contraction dim contiguous) or
+// MN-major (row-major [K, rows], the contraction dim is the slow one).  That covers, on plain
+// row-major tensors and without any transposed copies:
+//   forward  Y = X W^T          A = X  (K-major)    B = W  (K-major)
+//   dgrad    dX = dY W          A = dY (K-major)    B = W  (MN-major)
+//   wgrad    dW = dY^T X        A = dY (MN-major)   B = X  (MN-major)
+// (reference ops replaced: every nn.Linear on the EAGLE3 draft path —
+//  specforge/modeling/draft/llama3_eagle.py:555-563,1513-1515,1668-1693 — and their autograd.)
+//
+// Structure: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (TMEM -> registers -> global).  kStages-deep smem ring between TMA and
+// MMA, two TMEM accumulator stages between MMA and epilogue, static persistent tile schedule.
+// kCtaGroup == 2 pairs two CTAs (one cluster) on a 256 x BLOCK_N tile with cta_group::2 MMAs.
+#pragma once
+#include "sf_ptx.cuh"
+#include <cuda.h>
+
+namespace sf {
+
+enum : int { MAJOR_K = 0, MAJOR_MN = 1 };
+enum : int {
+    EPI_BF16 = 0,        // D(bf16) = acc
+    EPI_BF16_RESID = 1,  // D(bf16) = bf16(acc) + R   (R bf16; sum rounded once more to bf16)
+    EPI_F32 = 2,         // D(f32)  = acc
+    EPI_F32_ACCUM = 3,   // D(f32) += acc
+};
+
+struct GemmParams {
+    void* D;
+    const __nv_bfloat16* R;
+    int M, N, K;
+    int ldd, ldr;
+    int epi;
+    int num_m_blocks, num_n_blocks;
+};
+
+template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN>
+struct GemmCfg {
+    static constexpr int BLOCK_M = 128;  // rows per CTA
+    static constexpr int TILE_M = 128 * kCtaGroup;
+    static constexpr int BLOCK_N = kBlockN;
+    static constexpr int BLOCK_K = 64;
+    static constexpr int UMMA_K = 16;
+    static constexpr int B_ROWS = kBlockN / kCtaGroup;  // B rows staged by each CTA
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int kStages = (192 * 1024) / STAGE_BYTES;
+    static constexpr int kAccStages = 2;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr int kThreads = 256;
+    static_assert(kBlockN * kAccStages <= 512, "TMEM overflow");
+    static_assert(kBlockN % 64 == 0 && kBlockN <= 256, "bad BLOCK_N");
+};
+
+template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const GemmParams p) {
+    using Cfg = GemmCfg<kCtaGroup, kAMajor, kBMajor, kBlockN>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int BLOCK_K = Cfg::BLOCK_K;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    uint32_t* tmem_slot_ptr =
+        reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+    const bool is_leader = (cta_rank == 0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4 * kCtaGroup);  // one arrive per epilogue warp per CTA
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<kCtaGroup>(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int cluster_id = blockIdx.x / kCtaGroup;
+    const int num_clusters = gridDim.x / kCtaGroup;
+    constexpr int kGroupM = 8;
+
+    auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+        const int per_group = kGroupM * p.num_n_blocks;
+        const int group = tile / per_group;
+        const int first_m = group * kGroupM;
+        const int gsz = min(kGroupM, p.num_m_blocks - first_m);
+        const int in_group = tile - group * per_group;
+        m_blk = first_m + in_group % gsz;
+        n_blk = in_group / gsz;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
+            const int m0 = m_blk * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M;
+            const int n0 = n_blk * Cfg::BLOCK_N + (int)cta_rank * Cfg::B_ROWS;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+                const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                const uint32_t sb = sa + Cfg::A_BYTES;
+                const int k0 = kb * BLOCK_K;
+                uint32_t bar;
+                if constexpr (kCtaGroup == 2) {
+                    if (is_leader) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * 2);
+                    bar = mapa(full_bar(stage), 0);
+                } else {
+                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    bar = full_bar(stage);
+                }
+                auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1) {
+                    if constexpr (kCtaGroup == 2) tma_load_2d_pair(dst, tm, bar, c0, c1);
+                    else tma_load_2d(dst, tm, bar, c0, c1);
+                };
+                if constexpr (kAMajor == MAJOR_K) {
+                    load(sa, &tmap_a, k0, m0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < Cfg::BLOCK_M / 64; ++j)
+                        load(sa + j * (BLOCK_K * 128), &tmap_a, m0 + 64 * j, k0);
+                }
+                if constexpr (kBMajor == MAJOR_K) {
+                    load(sb, &tmap_b, k0, n0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < Cfg::B_ROWS / 64; ++j)
+                        load(sb + j * (BLOCK_K * 128), &tmap_b, n0 + 64 * j, k0);
+                }
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && is_leader) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc =
+            make_idesc_bf16(Cfg::TILE_M, Cfg::BLOCK_N, kAMajor == MAJOR_MN, kBMajor == MAJOR_MN);
+        // K-major SW128: 8-row groups are 1024 B apart (SBO); one UMMA_K step = 32 B inside the atom.
+        // MN-major SW128: 64-element MN chunks are BLOCK_K*128 B apart (LBO), 8-k-row groups 1024 B
+        // apart (SBO); one UMMA_K step = 16 k-rows = 2048 B.
+        constexpr uint32_t a_lbo = (kAMajor == MAJOR_K) ? 0u : (uint32_t)(BLOCK_K * 128);
+        constexpr uint32_t b_lbo = (kBMajor == MAJOR_K) ? 0u : (uint32_t)(BLOCK_K * 128);
+        constexpr uint32_t a_kstep = (kAMajor == MAJOR_K) ? 32u : 2048u;
+        constexpr uint32_t b_kstep = (kBMajor == MAJOR_K) ? 32u : 2048u;
+        int stage = 0;
+        uint32_t phase = 0;
+        int astage = 0;
+        uint32_t aphase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            mbar_wait(tempty_bar(astage), aphase ^ 1u, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + astage * Cfg::BLOCK_N;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(full_bar(stage), phase, 3);
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                const uint32_t sb = sa + Cfg::A_BYTES;
+                const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / Cfg::UMMA_K; ++k) {
+                    umma_bf16<kCtaGroup>(d_tmem, adesc + ((k * a_kstep) >> 4),
+                                         bdesc + ((k * b_kstep) >> 4), idesc,
+                                         (kb | k) != 0 ? 1u : 0u);
+                }
+                if constexpr (kCtaGroup == 2) umma_commit_pair(empty_bar(stage), 0b11);
+                else umma_commit(empty_bar(stage));
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            if constexpr (kCtaGroup == 2) umma_commit_pair(tfull_bar(astage), 0b11);
+            else umma_commit(tfull_bar(astage));
+            if (++astage == 2) { astage = 0; aphase ^= 1u; }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int wq = warp & 3;  // TMEM lane quadrant this warp may read
+        int astage = 0;
+        uint32_t aphase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
+            const int row = m_blk * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M + wq * 32 + lane;
+            const int n0 = n_blk * Cfg::BLOCK_N;
+            mbar_wait(tfull_bar(astage), aphase, 4);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + astage * Cfg::BLOCK_N;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_row + c * 32, v);
+                tmem_ld_wait();
+                const int col = n0 + c * 32;
+                if (!row_ok || col >= p.N) continue;
+                const bool full = (col + 32 <= p.N);
+                if (p.epi == EPI_BF16 || p.epi == EPI_BF16_RESID) {
+                    __nv_bfloat16* dst =
+                        reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col;
+                    if (full) {
+                        uint32_t o[16];
+                        if (p.epi == EPI_BF16_RESID) {
+                            const uint4* rp =
+                                reinterpret_cast<const uint4*>(p.R + (size_t)row * p.ldr + col);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 r4 = __ldg(rp + q);
+                                const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
+                                    // match the reference's two roundings: linear output -> bf16, then add
+                                    float a0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[q * 8 + e * 2])));
+                                    float a1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[q * 8 + e * 2 + 1])));
+                                    o[q * 4 + e] = pack_bf16x2(a0 + __bfloat162float(rb.x),
+                                                               a1 + __bfloat162float(rb.y));
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                        }
+                        uint4* dp = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            dp[q] = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                    } else {
+                        for (int e = 0; e < 32 && col + e < p.N; ++e) {
+                            float a = __uint_as_float(v[e]);
+                            if (p.epi == EPI_BF16_RESID)
+                                a = __bfloat162float(__float2bfloat16_rn(a)) +
+                                    __bfloat162float(p.R[(size_t)row * p.ldr + col + e]);
+                            dst[e] = __float2bfloat16_rn(a);
+                        }
+                    }
+                } else {
+                    float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col;
+                    if (full) {
+                        float4* dp = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                   __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                            if (p.epi == EPI_F32_ACCUM) {
+                                float4 old = dp[q];
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            dp[q] = o;
+                        }
+                    } else {
+                        for (int e = 0; e < 32 && col + e < p.N; ++e) {
+                            float a = __uint_as_float(v[e]);
+                            if (p.epi == EPI_F32_ACCUM) a += dst[e];
+                            dst[e] = a;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (kCtaGroup == 2) mbar_arrive_cluster(tempty_bar(astage), 0);
+                else mbar_arrive(tempty_bar(astage));
+            }
+            if (++astage == 2) { astage = 0; aphase ^= 1u; }
+        }
+    }
+
+    // ===================== teardown =====================
+    __syncwarp();  // single-lane roles rejoin their warp before the aligned block/cluster barrier
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<kCtaGroup>(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace sf
