@@ -1,0 +1,135 @@
+/* specforge_b200.h — C ABI of libspecforge_b200.so: the B200 (sm_100a) EAGLE3 draft-head training step.
+ *
+ * The reference (sgl-project/SpecForge @ a6b6b02) has no FFI for this path — its seams are Python protocols
+ * (SURVEY.md §8b).  This header is the boundary a binding sits on: plain pointers and sizes, no torch types.
+ * All data pointers are DEVICE pointers owned by the caller (PyTorch), `stream` is a cudaStream_t passed as
+ * void*.  Every function returns 0 on success or a negative errno-style code; sf_last_error() holds the
+ * message (thread-local).  Nothing allocates: the caller provides a workspace sized by
+ * sf_eagle3_workspace_bytes().  Re-entrant per device; a workspace must not be shared by concurrent steps.
+ *
+ * Reference interfaces replaced (file:line in the reference tree):
+ *   sf_eagle3_forward   Eagle3TrainStrategy.forward_loss      specforge/training/strategies/base.py:237-304
+ *                       TargetHead.preprocess/forward         specforge/modeling/target/target_head.py:100-108
+ *                       _compute_target_p(_padded)            specforge/algorithms/eagle3/model.py:445-501
+ *                       OnlineEagle3Model.forward (TTT loop)  specforge/algorithms/eagle3/model.py:244-442
+ *                       LlamaForCausalLMEagle3 fc/backbone/compute_logits
+ *                                                             specforge/modeling/draft/llama3_eagle.py:1625-1798
+ *                       LogSoftmaxLoss / acceptance / top-1   specforge/core/loss.py:15-228, core/lk_loss.py:43-80
+ *   sf_eagle3_backward  torch.autograd of the above (backend.backward)   specforge/training/backend.py:310-320
+ *   sf_optimizer_step   BF16Optimizer.step                    specforge/optimizer.py:95-168
+ *   sf_gemm_bf16 ...    the individual ops, exported for kernel-level parity tests
+ */
+#ifndef SPECFORGE_B200_H
+#define SPECFORGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ---- */
+const char* sf_version(void);
+const char* sf_last_error(void);
+long long sf_launch_count(void);      /* kernels launched by this library since the last reset */
+void sf_launch_count_reset(void);
+
+/* ---- model / step description ---- */
+typedef struct sf_eagle3_config {
+    int32_t batch;            /* B  sequences per micro-batch on this GPU */
+    int32_t seq_len;          /* S  */
+    int32_t ttt_length;       /* T  (<= 9) */
+    int32_t hidden_size;      /* H  draft hidden */
+    int32_t target_hidden;    /* H_t target hidden (fc input is 3*H_t) */
+    int32_t intermediate;     /* I  */
+    int32_t num_heads;        /* nh */
+    int32_t num_kv_heads;     /* nkv */
+    int32_t head_dim;         /* d  (64 or 128) */
+    int32_t vocab;            /* V  target vocab */
+    int32_t draft_vocab;      /* DV */
+    int32_t fc_norm;          /* EAGLE3.1 per-third RMSNorm before fc (llama3_eagle.py:1679-1687) */
+    int32_t norm_output;      /* final norm before lm_head (default 1) */
+    int32_t rope_rows;        /* rows in the cos/sin tables (>= S + T) */
+    float rms_eps;
+    float ploss_decay;        /* 0.8 */
+} sf_eagle3_config;
+
+/* Offsets (in elements) of each trainable parameter inside the flat bf16 parameter buffer; the fp32 gradient
+ * buffer uses the same layout.  q/k/v and gate/up are adjacent so that they form the fused [q;k;v] and
+ * [gate;up] matrices the kernels read.  Parameter shapes are the reference state-dict shapes. */
+enum {
+    SF_P_FC = 0, SF_P_Q, SF_P_K, SF_P_V, SF_P_O, SF_P_GATE, SF_P_UP, SF_P_DOWN,
+    SF_P_HIDDEN_NORM, SF_P_INPUT_NORM, SF_P_POST_NORM, SF_P_NORM, SF_P_LM_HEAD,
+    SF_P_FC_NORM0, SF_P_FC_NORM1, SF_P_FC_NORM2, SF_P_COUNT
+};
+int sf_eagle3_param_layout(const sf_eagle3_config* cfg, int64_t offsets[SF_P_COUNT], int64_t sizes[SF_P_COUNT],
+                           int64_t* total_elems);
+
+typedef struct sf_eagle3_frozen {     /* not trained */
+    const void* embed_tokens;         /* bf16 [V, H]   (frozen target embedding) */
+    const void* target_head;          /* bf16 [V, H_t] (TargetHead.fc.weight)    */
+    const void* rope_cos;             /* bf16 [rope_rows, d] */
+    const void* rope_sin;             /* bf16 [rope_rows, d] */
+    const uint8_t* t2d;               /* [V]  1 if the target token is in the draft vocab */
+    const int64_t* d2t;               /* [DV] target id = draft id + d2t[draft id] */
+} sf_eagle3_frozen;
+
+typedef struct sf_eagle3_batch {      /* one collated micro-batch, already on the device */
+    const int64_t* input_ids;         /* [B, S] */
+    const int64_t* attention_mask;    /* [B, S] 1 = real token (key padding mask) */
+    const int64_t* loss_mask;         /* [B, S] */
+    const void* hidden_state;         /* bf16 [B, S, 3*H_t] aux hidden states */
+    const void* target;               /* bf16 [B, S, H_t]  target last hidden state (unshifted) */
+} sf_eagle3_batch;
+
+size_t sf_eagle3_workspace_bytes(const sf_eagle3_config* cfg);
+
+/* Teacher + TTT-unrolled forward + loss/metrics.  metrics: device float [T][8] =
+ * {ploss, acc_correct, acc_denom, acceptance_rate, accept_num, accept_den, loss_denom, 0};
+ * loss: device float scalar = sum_j decay^j * ploss_j.  need_grad != 0 also leaves d(loss)/d(logits) and the
+ * activations in the workspace for sf_eagle3_backward. */
+int sf_eagle3_forward(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,
+                      const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float* metrics,
+                      float* loss, int need_grad, void* stream);
+
+/* Full backward of the step just run by sf_eagle3_forward(need_grad=1) on the same workspace.
+ * grads_flat_f32 (+)= loss_scale * dLoss/dParams  (accumulate != 0 adds into the buffer). */
+int sf_eagle3_backward(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,
+                       const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float loss_scale,
+                       float* grads_flat_f32, int accumulate, void* stream);
+
+/* grads_bf16[i] = bf16(grads_f32[i])  — the bf16 gradient buffer DDP all-reduces (backend.py:233-253). */
+int sf_grads_to_bf16(const float* grads_f32, void* grads_bf16, int64_t n, void* stream);
+
+/* BF16Optimizer.step (optimizer.py:140-168) fused: ||g|| over bf16(g * grad_scale), clip coefficient
+ * min(1, max_norm/(||g||+1e-6)), AdamW on fp32 masters, bf16 write-back.  step is 1-based.
+ * grad_norm_out: device float (the pre-clip norm); scratch: device float[1024]. */
+int sf_optimizer_step(const void* grads_bf16, float* master, float* exp_avg, float* exp_avg_sq, void* params_bf16,
+                      int64_t n, float grad_scale, float max_grad_norm, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int32_t step, float* grad_norm_out, float* scratch, void* stream);
+
+/* ---- individual ops (kernel-level parity tests) ---- */
+/* D[m,n] = sum_k A(m,k) B(n,k); *_major: 0 = K-major ([rows,K] row-major), 1 = MN-major ([K,rows] row-major);
+ * epi: 0 bf16, 1 bf16 + residual R, 2 fp32, 3 fp32 accumulate; cta_group: 0 auto, 1, 2. */
+int sf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D, int64_t ldd,
+                 const void* R, int64_t ldr, int M, int N, int K, int epi, int cta_group, void* stream);
+int sf_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* out, int64_t ldo, int64_t M, int H, float eps,
+                   void* stream);
+int sf_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const void* dy, int64_t lddy, const void* add, void* dx,
+                   float* dw, int64_t M, int H, float eps, void* stream);
+/* TTT attention at step J over the fused per-step qkv buffers qkv[i] = [B*S, (nh+2nkv)*d] (RoPE already applied). */
+int sf_ttt_attention_fwd(const void* const* qkv, int J, void* out, float* lse, float* sd_ws, const uint8_t* key_mask,
+                         int B, int S, int nh, int nkv, int head_dim, void* stream);
+int sf_ttt_attention_bwd(const void* const* qkv, int J, const void* out, const void* dout, const float* lse,
+                         float* sd_ws, const uint8_t* key_mask, float* const* dk_acc, float* const* dv_acc, void* dq,
+                         float* delta_ws, float* dq_diag_ws, int B, int S, int nh, int nkv, int head_dim, void* stream);
+int sf_swiglu_fwd(const void* gu, void* act, int64_t M, int I, void* stream);
+int sf_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t M, int I, void* stream);
+int sf_rope(void* x, int64_t ld, int n_heads, int head_dim, const void* cos_t, const void* sin_t, int S, int pos_offset,
+            int64_t M, int inverse, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECFORGE_B200_H */

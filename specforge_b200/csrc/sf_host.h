@@ -21,6 +21,47 @@ struct GemmDesc {
 };
 int gemm(const GemmDesc& g, cudaStream_t stream);
 
+// TTT attention at step j = J (J diagonal blocks).  k[i]/v[i]: [B*S, nkv*D] views of block i (row stride ldkv).
+struct AttnDesc {
+    const void* q; int64_t ldq;
+    const void* k[9]; const void* v[9]; int64_t ldkv;
+    void* out; int64_t ldo;
+    float* lse;                 // [B, nh, S]
+    float* sd_ws;               // [B, nh, S, J] workspace (diagonal scores)
+    const uint8_t* key_mask;    // [B, S] or null
+    int B, S, nh, nkv, head_dim, J;
+    // backward only
+    const void* dout; int64_t lddo;
+    float* delta_ws;            // [B, nh, S]
+    float* dk_acc[9]; float* dv_acc[9]; int64_t ldacc;   // fp32 accumulators per block, [B*S, nkv*D]
+    void* dq; int64_t lddq;     // bf16 out
+    float* dq_diag_ws;          // [B*S, nh*D] fp32 workspace
+};
+int attn_fwd(const AttnDesc& a, cudaStream_t st);
+int attn_bwd(const AttnDesc& a, cudaStream_t st);
+
+int rmsnorm_fwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift, const void* w, void* out, int64_t ldo,
+                int64_t M, int H, float eps, float* rstd, cudaStream_t st);
+int rmsnorm_bwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift, const void* w, const void* dy,
+                int64_t lddy, const void* add1, const void* add2, void* dx, float* dw, int64_t M, int H, float eps,
+                cudaStream_t st);
+int rope(void* x, const float* src32, int64_t ld, int64_t ld32, int n_heads, int head_dim, const void* cos_t,
+         const void* sin_t, int S, int pos_offset, int64_t M, int inverse, cudaStream_t st);
+int cvt_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t M, int cols, float scale, cudaStream_t st);
+int swiglu_fwd(const void* gu, void* act, int64_t M, int I, cudaStream_t st);
+int swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t M, int I, cudaStream_t st);
+int shift_left(const void* src, void* dst, int64_t B, int S, int H, cudaStream_t st);
+
+int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, const int* loss_mask, float* target_p,
+            float* pod, int64_t* ids, int* position_mask, int B, int S, int T, int V, int DV, cudaStream_t st);
+int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod, const int64_t* tgt_ids,
+              const int* position_mask, const int* loss_mask, const int64_t* d2t, int B, int S, int T, int DV, int step,
+              float grad_coef, int write_grad, float* row_ws, float* metrics, cudaStream_t st);
+int grad_norm(const void* g, int64_t n, float gscale, float* partials_ws, float* out, cudaStream_t st);
+int adamw(const void* g, float* master, float* m1, float* m2, void* param, int64_t n, const float* gnorm, float max_norm,
+          float gscale, float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st);
+int cvt_flat_f32_bf16(const float* src, void* dst, int64_t n, int accumulate, cudaStream_t st);
+
 #define SF_CUDA_CHECK_LAUNCH(what)                                                            \
     do {                                                                                      \
         cudaError_t e__ = cudaGetLastError();                                                 \

@@ -1,0 +1,402 @@
+// sf_loss.cu — teacher distribution, fused soft-label CE / acceptance / top-1 loss (+ in-place gradient),
+// metric reduction, and the fused clip + AdamW optimizer step.  All HBM-bound row kernels.
+#include "sf_host.h"
+#include "sf_ptx.cuh"
+
+namespace sf {
+
+struct MaxIdx { float v; int i; };
+__device__ __forceinline__ MaxIdx better(MaxIdx a, MaxIdx b) {
+    // first index wins ties (torch.argmax semantics)
+    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ MaxIdx warp_argmax(MaxIdx a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MaxIdx b{__shfl_xor_sync(0xffffffffu, a.v, o), __shfl_xor_sync(0xffffffffu, a.i, o)};
+        a = better(a, b);
+    }
+    return a;
+}
+__device__ __forceinline__ MaxIdx block_argmax(MaxIdx a, float* redv, int* redi) {
+    a = warp_argmax(a);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) { redv[w] = a.v; redi[w] = a.i; }
+    __syncthreads();
+    MaxIdx t{(l < nw) ? redv[l] : -INFINITY, (l < nw) ? redi[l] : 0x7fffffff};
+    return warp_argmax(t);
+}
+__device__ __forceinline__ float block_sum_f(float v, float* red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < nw) ? red[l] : 0.f;
+    return warp_sum(t);
+}
+__device__ __forceinline__ float block_max_f(float v, float* red) {
+    v = warp_max(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < nw) ? red[l] : -INFINITY;
+    return warp_max(t);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+        f[2 * i] = __bfloat162float(b.x);
+        f[2 * i + 1] = __bfloat162float(b.y);
+    }
+}
+
+// ------------------------------------------------------------------ teacher
+// Reference: algorithms/eagle3/model.py:487-501 (_compute_target_p) + :445-484 (padding).
+// One block per (b, s): argmax / logsumexp over the full target vocab, gather of the draft-vocab logits,
+// softmax over the draft vocab.  Output rows live in the [B, S+T, DV] padded layout so that TTT step j
+// reads row (b, s + j) without the reference's per-step `.contiguous()` copies.
+__global__ void __launch_bounds__(512)
+teacher_kernel(const __nv_bfloat16* __restrict__ tl, int64_t ld, const int* __restrict__ d2t_idx,
+               const uint8_t* __restrict__ t2d, const int* __restrict__ loss_mask, float* __restrict__ target_p,
+               float* __restrict__ pod, int64_t* __restrict__ ids, int* __restrict__ position_mask, int S, int T, int V,
+               int DV) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // gathered draft logits (bf16: lossless)
+    __shared__ float redv[32];
+    __shared__ int redi[32];
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / S), s = (int)(r % S);
+    const __nv_bfloat16* row = tl + r * ld;
+    // pass 1: max / argmax, then sum exp
+    MaxIdx mi{-INFINITY, 0x7fffffff};
+    const int nch = V / 8;
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(row) + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (f[e] > mi.v) { mi.v = f[e]; mi.i = c * 8 + e; }
+    }
+    for (int e = nch * 8 + threadIdx.x; e < V; e += blockDim.x) {
+        const float f = __bfloat162float(row[e]);
+        if (f > mi.v) { mi.v = f; mi.i = e; }
+    }
+    mi = block_argmax(mi, redv, redi);
+    const float m = mi.v;
+    float d = 0.f;
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(row) + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d += __expf(f[e] - m);
+    }
+    for (int e = nch * 8 + threadIdx.x; e < V; e += blockDim.x) d += __expf(__bfloat162float(row[e]) - m);
+    d = block_sum_f(d, redv);
+    const float lse = m + logf(d);
+    // pass 2: gather the draft-vocab logits
+    float md = -INFINITY;
+    for (int i = threadIdx.x; i < DV; i += blockDim.x) {
+        const __nv_bfloat16 x = row[d2t_idx[i]];
+        xs[i] = x;
+        md = fmaxf(md, __bfloat162float(x));
+    }
+    md = block_max_f(md, redv);
+    float dd = 0.f;
+    for (int i = threadIdx.x; i < DV; i += blockDim.x) dd += __expf(__bfloat162float(xs[i]) - md);
+    dd = block_sum_f(dd, redv);
+    const float inv = 1.f / dd;
+    const int64_t orow = (int64_t)b * (S + T) + s;
+    float* tp = target_p + orow * DV;
+    float* pp = pod + orow * DV;
+    for (int i = threadIdx.x; i < DV; i += blockDim.x) {
+        const float x = __bfloat162float(xs[i]);
+        tp[i] = __expf(x - md) * inv;
+        pp[i] = __expf(x - lse);
+    }
+    if (threadIdx.x == 0) {
+        ids[orow] = mi.i;
+        position_mask[r] = (t2d[mi.i] ? 1 : 0) * loss_mask[r];
+    }
+}
+// padded tail rows: target_p = 1/DV, p_on_draft = 0, ids = 0   (eagle3/model.py:459-477)
+__global__ void __launch_bounds__(256)
+teacher_pad_kernel(float* __restrict__ target_p, float* __restrict__ pod, int64_t* __restrict__ ids, int B, int S, int T,
+                   int DV) {
+    const int64_t total = (int64_t)B * T * DV;
+    const float u = 1.0f / (float)DV;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pr = i / DV;
+        const int c = (int)(i % DV);
+        const int b = (int)(pr / T), t = (int)(pr % T);
+        const int64_t orow = (int64_t)b * (S + T) + S + t;
+        target_p[orow * DV + c] = u;
+        pod[orow * DV + c] = 0.f;
+        if (c == 0) ids[orow] = 0;
+    }
+}
+
+// ------------------------------------------------------------------ fused loss / metrics / gradient
+// Reference: core/loss.py:15-21,49-170 (soft-label CE, mean over ALL rows, in-place backward),
+// core/lk_loss.py:43-80 (acceptance = sum_v min(p_on_draft, softmax)), eagle3/model.py:161-173 (top-1).
+// One block per row; the bf16 logits row is staged in smem once, the gradient overwrites it in HBM.
+struct LossParams {
+    __nv_bfloat16* logits; int64_t ld;
+    const float* target_p; const float* pod; const int64_t* tgt_ids;  // padded [B, S+T, ...]
+    const int* position_mask; const int* loss_mask;                  // [B, S] (step-0 masks)
+    const int64_t* d2t;
+    int S, T, DV, step;
+    float grad_coef;      // ploss_decay^step * upstream / M
+    int write_grad;
+    int use_smem;
+    float* row_loss; float* row_accept; float* row_correct;  // [M]
+};
+
+__global__ void __launch_bounds__(512) loss_kernel(LossParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ float redv[32];
+    __shared__ int redi[32];
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / p.S), s = (int)(r % p.S);
+    const bool in_range = s + p.step < p.S;
+    const int pm = in_range ? p.position_mask[(int64_t)b * p.S + s + p.step] : 0;
+    const int lm = in_range ? p.loss_mask[(int64_t)b * p.S + s + p.step] : 0;
+    __nv_bfloat16* grow = p.logits + r * p.ld;
+    const int nch = p.DV / 8;
+    const uint4* xrow = p.use_smem ? reinterpret_cast<const uint4*>(smem_raw) : reinterpret_cast<const uint4*>(grow);
+
+    if (pm == 0 && lm == 0) {  // nothing to measure: zero gradient row and leave
+        if (p.write_grad)
+            for (int c = threadIdx.x; c < nch; c += blockDim.x) reinterpret_cast<uint4*>(grow)[c] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x == 0) { p.row_loss[r] = 0.f; p.row_accept[r] = 0.f; p.row_correct[r] = 0.f; }
+        return;
+    }
+    // pass 1: stage the row, max / argmax
+    MaxIdx mi{-INFINITY, 0x7fffffff};
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        const uint4 u = reinterpret_cast<const uint4*>(grow)[c];
+        if (p.use_smem) reinterpret_cast<uint4*>(smem_raw)[c] = u;
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (f[e] > mi.v) { mi.v = f[e]; mi.i = c * 8 + e; }
+    }
+    mi = block_argmax(mi, redv, redi);  // contains __syncthreads: smem row is visible afterwards
+    const float m = mi.v;
+    float d = 0.f;
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        float f[8];
+        unpack8(xrow[c], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d += __expf(f[e] - m);
+    }
+    d = block_sum_f(d, redv);
+    const float inv_d = 1.f / d;
+    const int64_t trow = (int64_t)b * (p.S + p.T) + s + p.step;
+    float sum_p = 0.f, sum_px = 0.f, sum_min = 0.f;
+    if (pm) {
+        const float4* tp = reinterpret_cast<const float4*>(p.target_p + trow * p.DV);
+        const float4* pp = reinterpret_cast<const float4*>(p.pod + trow * p.DV);
+        for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+            float f[8];
+            unpack8(xrow[c], f);
+            const float4 t0 = __ldg(tp + 2 * c), t1 = __ldg(tp + 2 * c + 1);
+            const float4 q0 = __ldg(pp + 2 * c), q1 = __ldg(pp + 2 * c + 1);
+            const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                sum_p += tv[e];
+                sum_px += tv[e] * f[e];
+                sum_min += fminf(qv[e], __expf(f[e] - m) * inv_d);
+            }
+        }
+        sum_p = block_sum_f(sum_p, redv);
+        sum_px = block_sum_f(sum_px, redv);
+        sum_min = block_sum_f(sum_min, redv);
+    }
+    if (threadIdx.x == 0) {
+        p.row_loss[r] = pm ? -(sum_px - (m + logf(d)) * sum_p) : 0.f;
+        p.row_accept[r] = pm ? sum_min : 0.f;
+        const int64_t pred = mi.i;
+        p.row_correct[r] = (lm && (pred + p.d2t[pred] == p.tgt_ids[trow])) ? (float)lm : 0.f;
+    }
+    if (p.write_grad) {
+        if (pm) {
+            const float4* tp = reinterpret_cast<const float4*>(p.target_p + trow * p.DV);
+            const float a = sum_p * inv_d * p.grad_coef;
+            for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+                float f[8];
+                unpack8(xrow[c], f);
+                const float4 t0 = __ldg(tp + 2 * c), t1 = __ldg(tp + 2 * c + 1);
+                const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                uint4 o;
+                o.x = pack_bf16x2(__expf(f[0] - m) * a - tv[0] * p.grad_coef, __expf(f[1] - m) * a - tv[1] * p.grad_coef);
+                o.y = pack_bf16x2(__expf(f[2] - m) * a - tv[2] * p.grad_coef, __expf(f[3] - m) * a - tv[3] * p.grad_coef);
+                o.z = pack_bf16x2(__expf(f[4] - m) * a - tv[4] * p.grad_coef, __expf(f[5] - m) * a - tv[5] * p.grad_coef);
+                o.w = pack_bf16x2(__expf(f[6] - m) * a - tv[6] * p.grad_coef, __expf(f[7] - m) * a - tv[7] * p.grad_coef);
+                reinterpret_cast<uint4*>(grow)[c] = o;
+            }
+        } else {
+            for (int c = threadIdx.x; c < nch; c += blockDim.x) reinterpret_cast<uint4*>(grow)[c] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+// Deterministic reduction of the per-row values into the step's metric slots.
+// metrics[step][0..7] = {ploss, acc_correct, acc_denom, acceptance_rate, accept_num, accept_den, loss_denom, 0}
+__global__ void __launch_bounds__(1024)
+metrics_reduce_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_accept,
+                      const float* __restrict__ row_correct, const int* __restrict__ position_mask,
+                      const int* __restrict__ loss_mask, int B, int S, int step, float* __restrict__ metrics) {
+    __shared__ float red[32];
+    const int64_t M = (int64_t)B * S;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    for (int64_t r = threadIdx.x; r < M; r += blockDim.x) {
+        const int s = (int)(r % S);
+        a0 += row_loss[r];
+        a1 += row_accept[r];
+        a2 += row_correct[r];
+        if (s + step < S) { a3 += (float)position_mask[r + step]; a4 += (float)loss_mask[r + step]; }
+    }
+    a0 = block_sum_f(a0, red); a1 = block_sum_f(a1, red); a2 = block_sum_f(a2, red);
+    a3 = block_sum_f(a3, red); a4 = block_sum_f(a4, red);
+    if (threadIdx.x == 0) {
+        float* o = metrics + step * 8;
+        o[0] = a0 / (float)M;
+        o[1] = a2;
+        o[2] = fmaxf(a4, 1e-6f);
+        o[3] = a1 / fmaxf(a3, 1e-8f);
+        o[4] = a1;
+        o[5] = fmaxf(a3, 1e-8f);
+        o[6] = (float)M;
+        o[7] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------ optimizer (optimizer.py:95-168)
+// ||g||^2 over the flat bf16 gradient buffer (fp32 accumulation), two deterministic stages.
+__global__ void __launch_bounds__(512)
+sqnorm_partial_kernel(const __nv_bfloat16* __restrict__ g, int64_t n, float gscale, float* __restrict__ partials) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    const int64_t nch = n / 8;
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nch; c += (int64_t)gridDim.x * blockDim.x) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(g) + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float x = __bfloat162float(__float2bfloat16_rn(f[e] * gscale)); acc += x * x; }
+    }
+    if (blockIdx.x == 0)
+        for (int64_t e = nch * 8 + threadIdx.x; e < n; e += blockDim.x) {
+            const float x = __bfloat162float(__float2bfloat16_rn(__bfloat162float(g[e]) * gscale));
+            acc += x * x;
+        }
+    acc = block_sum_f(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(1024) sqnorm_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+    acc = block_sum_f(acc, red);
+    if (threadIdx.x == 0) out[0] = sqrtf(acc);
+}
+// clip coefficient min(1, max_norm / (||g|| + 1e-6)) read on the device (no host sync), then torch.optim.AdamW
+// on the fp32 masters and a bf16 write-back.  gscale = 1/world (DDP averages gradients, backend.py:233-253).
+__global__ void __launch_bounds__(256)
+adamw_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ master, float* __restrict__ m1, float* __restrict__ m2,
+             __nv_bfloat16* __restrict__ param, int64_t n, const float* __restrict__ gnorm, float max_norm, float gscale,
+             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
+    const float clip = (max_norm > 0.f) ? fminf(1.0f, max_norm / (gnorm[0] + 1e-6f)) : 1.0f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gr = __bfloat162float(__float2bfloat16_rn(__bfloat162float(g[i]) * gscale)) * clip;
+        float w = master[i];
+        w *= (1.f - lr * wd);
+        const float a = m1[i] + (gr - m1[i]) * (1.f - beta1);       // lerp_
+        const float v = m2[i] * beta2 + (1.f - beta2) * gr * gr;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        w -= (lr / bc1) * (a / denom);
+        m1[i] = a; m2[i] = v; master[i] = w;
+        param[i] = __float2bfloat16_rn(w);
+    }
+}
+__global__ void __launch_bounds__(256) cvt_flat_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                               int64_t n, int accumulate) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = src[i];
+        if (accumulate) v += __bfloat162float(dst[i]);
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------ host wrappers
+int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, const int* loss_mask, float* target_p,
+            float* pod, int64_t* ids, int* position_mask, int B, int S, int T, int V, int DV, cudaStream_t st) {
+    if (V % 8) return set_error(-22, "teacher: target vocab %d must be a multiple of 8", V);
+    const int smem = DV * 2;
+    if (smem > 200 * 1024) return set_error(-22, "teacher: draft vocab %d too large for the smem-staged path", DV);
+    static int smem_set = 0;
+    if (smem > smem_set) { cudaFuncSetAttribute(teacher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
+    teacher_kernel<<<(unsigned)((int64_t)B * S), 512, smem, st>>>((const __nv_bfloat16*)tl, ld, d2t_idx, t2d, loss_mask,
+                                                                 target_p, pod, ids, position_mask, S, T, V, DV);
+    SF_CUDA_CHECK_LAUNCH("teacher");
+    if (T > 0) {
+        teacher_pad_kernel<<<148 * 4, 256, 0, st>>>(target_p, pod, ids, B, S, T, DV);
+        SF_CUDA_CHECK_LAUNCH("teacher_pad");
+    }
+    return 0;
+}
+
+int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod, const int64_t* tgt_ids,
+              const int* position_mask, const int* loss_mask, const int64_t* d2t, int B, int S, int T, int DV, int step,
+              float grad_coef, int write_grad, float* row_ws, float* metrics, cudaStream_t st) {
+    if (DV % 8 || ld % 8) return set_error(-22, "loss: draft vocab %d / ld must be multiples of 8", DV);
+    LossParams p;
+    p.logits = (__nv_bfloat16*)logits; p.ld = ld; p.target_p = target_p; p.pod = pod; p.tgt_ids = tgt_ids;
+    p.position_mask = position_mask; p.loss_mask = loss_mask; p.d2t = d2t; p.S = S; p.T = T; p.DV = DV; p.step = step;
+    p.grad_coef = grad_coef; p.write_grad = write_grad;
+    const int64_t M = (int64_t)B * S;
+    p.row_loss = row_ws; p.row_accept = row_ws + M; p.row_correct = row_ws + 2 * M;
+    int smem = DV * 2;
+    p.use_smem = smem <= 100 * 1024;
+    if (!p.use_smem) smem = 0;
+    static int smem_set = 0;
+    if (smem > smem_set) { cudaFuncSetAttribute(loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
+    loss_kernel<<<(unsigned)M, 512, smem, st>>>(p);
+    SF_CUDA_CHECK_LAUNCH("loss");
+    metrics_reduce_kernel<<<1, 1024, 0, st>>>(p.row_loss, p.row_accept, p.row_correct, position_mask, loss_mask, B, S, step,
+                                             metrics);
+    SF_CUDA_CHECK_LAUNCH("metrics_reduce");
+    return 0;
+}
+
+int grad_norm(const void* g, int64_t n, float gscale, float* partials_ws, float* out, cudaStream_t st) {
+    const int blocks = 148 * 4;
+    sqnorm_partial_kernel<<<blocks, 512, 0, st>>>((const __nv_bfloat16*)g, n, gscale, partials_ws);
+    SF_CUDA_CHECK_LAUNCH("sqnorm_partial");
+    sqnorm_final_kernel<<<1, 1024, 0, st>>>(partials_ws, blocks, out);
+    SF_CUDA_CHECK_LAUNCH("sqnorm_final");
+    return 0;
+}
+int adamw(const void* g, float* master, float* m1, float* m2, void* param, int64_t n, const float* gnorm, float max_norm,
+          float gscale, float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st) {
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2 = 1.f - powf(beta2, (float)step);
+    adamw_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)g, master, m1, m2, (__nv_bfloat16*)param, n, gnorm, max_norm,
+                                         gscale, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2));
+    SF_CUDA_CHECK_LAUNCH("adamw");
+    return 0;
+}
+int cvt_flat_f32_bf16(const float* src, void* dst, int64_t n, int accumulate, cudaStream_t st) {
+    cvt_flat_f32_bf16_kernel<<<148 * 8, 256, 0, st>>>(src, (__nv_bfloat16*)dst, n, accumulate);
+    SF_CUDA_CHECK_LAUNCH("cvt_flat");
+    return 0;
+}
+
+}  // namespace sf

@@ -1,0 +1,294 @@
+"""Host-side driver of the C-ABI EAGLE3 step (device memory + streams come from PyTorch; compute is libspecforge_b200).
+
+`Eagle3Engine` owns, for one draft head on one GPU:
+  * the flat bf16 parameter buffer (the nn.Parameters of the draft module are views into it, so q/k/v and
+    gate/up are physically adjacent and the reference state-dict names/shapes are preserved),
+  * the flat fp32 gradient accumulator and the flat bf16 gradient buffer that is all-reduced,
+  * fp32 AdamW state (masters, exp_avg, exp_avg_sq),
+  * the step workspace (activations of all TTT steps; sized by sf_eagle3_workspace_bytes).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from ctypes import POINTER, Structure, c_float, c_int32, c_int64, c_size_t, c_uint8, c_void_p
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from ._lib import check, lib
+
+P_NAMES = [
+    "fc.weight",
+    "midlayer.self_attn.q_proj.weight",
+    "midlayer.self_attn.k_proj.weight",
+    "midlayer.self_attn.v_proj.weight",
+    "midlayer.self_attn.o_proj.weight",
+    "midlayer.mlp.gate_proj.weight",
+    "midlayer.mlp.up_proj.weight",
+    "midlayer.mlp.down_proj.weight",
+    "midlayer.hidden_norm.weight",
+    "midlayer.input_layernorm.weight",
+    "midlayer.post_attention_layernorm.weight",
+    "norm.weight",
+    "lm_head.weight",
+    "fc_norm.0.weight",
+    "fc_norm.1.weight",
+    "fc_norm.2.weight",
+]
+P_COUNT = 16
+
+
+class SfConfig(Structure):
+    _fields_ = [
+        ("batch", c_int32), ("seq_len", c_int32), ("ttt_length", c_int32), ("hidden_size", c_int32),
+        ("target_hidden", c_int32), ("intermediate", c_int32), ("num_heads", c_int32), ("num_kv_heads", c_int32),
+        ("head_dim", c_int32), ("vocab", c_int32), ("draft_vocab", c_int32), ("fc_norm", c_int32),
+        ("norm_output", c_int32), ("rope_rows", c_int32), ("rms_eps", c_float), ("ploss_decay", c_float),
+    ]
+
+
+class SfFrozen(Structure):
+    _fields_ = [("embed_tokens", c_void_p), ("target_head", c_void_p), ("rope_cos", c_void_p), ("rope_sin", c_void_p),
+                ("t2d", c_void_p), ("d2t", c_void_p)]
+
+
+class SfBatch(Structure):
+    _fields_ = [("input_ids", c_void_p), ("attention_mask", c_void_p), ("loss_mask", c_void_p),
+                ("hidden_state", c_void_p), ("target", c_void_p)]
+
+
+_declared = False
+
+
+def _declare():
+    global _declared
+    if _declared:
+        return
+    l = lib()
+    l.sf_eagle3_param_layout.restype = ctypes.c_int
+    l.sf_eagle3_param_layout.argtypes = [POINTER(SfConfig), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
+    l.sf_eagle3_workspace_bytes.restype = c_size_t
+    l.sf_eagle3_workspace_bytes.argtypes = [POINTER(SfConfig)]
+    l.sf_eagle3_forward.restype = ctypes.c_int
+    l.sf_eagle3_forward.argtypes = [POINTER(SfConfig), c_void_p, POINTER(SfFrozen), POINTER(SfBatch), c_void_p, c_size_t,
+                                    c_void_p, c_void_p, ctypes.c_int, c_void_p]
+    l.sf_eagle3_backward.restype = ctypes.c_int
+    l.sf_eagle3_backward.argtypes = [POINTER(SfConfig), c_void_p, POINTER(SfFrozen), POINTER(SfBatch), c_void_p, c_size_t,
+                                     c_float, c_void_p, ctypes.c_int, c_void_p]
+    l.sf_grads_to_bf16.restype = ctypes.c_int
+    l.sf_grads_to_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    l.sf_optimizer_step.restype = ctypes.c_int
+    l.sf_optimizer_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
+                                    c_float, c_float, c_float, c_float, c_int32, c_void_p, c_void_p, c_void_p]
+    _declared = True
+
+
+@dataclass
+class DraftDims:
+    """Shape-defining fields of the draft config (configs/*-eagle3.json in the reference)."""
+    hidden_size: int
+    intermediate_size: int
+    num_heads: int
+    num_kv_heads: int
+    head_dim: int
+    vocab_size: int
+    draft_vocab_size: int
+    target_hidden_size: Optional[int] = None
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 10000.0
+    max_position_embeddings: int = 2048
+    fc_norm: bool = False
+    norm_output: bool = True
+
+    def __post_init__(self):
+        if self.target_hidden_size is None:
+            self.target_hidden_size = self.hidden_size
+
+
+def rope_tables(dims: DraftDims, rows: int, device) -> tuple:
+    """cos/sin tables exactly as LlamaRotaryEmbedding builds them (llama3_eagle.py:218-301): fp32 math, then the
+    module-wide .to(bfloat16) (algorithms/model_providers.py:112).  `rows` >= S + T."""
+    d = dims.head_dim
+    inv_freq = 1.0 / (dims.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    t = torch.arange(rows, dtype=torch.float32)
+    freqs = torch.einsum("i,j->ij", t, inv_freq)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().to(torch.bfloat16).to(device).contiguous(), emb.sin().to(torch.bfloat16).to(device).contiguous()
+
+
+class Eagle3Engine:
+    def __init__(self, dims: DraftDims, *, batch: int, seq_len: int, ttt_length: int = 7, ploss_decay: float = 0.8,
+                 device: Optional[torch.device] = None):
+        _declare()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if device.type != "cuda":
+            raise RuntimeError("specforge_b200 has no CPU path: a CUDA (sm_100a) device is required")
+        self.dims, self.device = dims, device
+        self.B, self.S, self.T = batch, seq_len, ttt_length
+        self.ploss_decay = ploss_decay
+        rope_rows = max(dims.max_position_embeddings + 20, seq_len + ttt_length)
+        self.cfg = SfConfig(batch, seq_len, ttt_length, dims.hidden_size, dims.target_hidden_size, dims.intermediate_size,
+                            dims.num_heads, dims.num_kv_heads, dims.head_dim, dims.vocab_size, dims.draft_vocab_size,
+                            int(dims.fc_norm), int(dims.norm_output), rope_rows, dims.rms_norm_eps, ploss_decay)
+        offs = (c_int64 * P_COUNT)()
+        sizes = (c_int64 * P_COUNT)()
+        total = c_int64()
+        check(lib().sf_eagle3_param_layout(self.cfg, offs, sizes, ctypes.byref(total)), "sf_eagle3_param_layout")
+        self.offsets = {P_NAMES[i]: int(offs[i]) for i in range(P_COUNT) if sizes[i] > 0}
+        self.sizes = {P_NAMES[i]: int(sizes[i]) for i in range(P_COUNT) if sizes[i] > 0}
+        self.n_params = int(total.value)
+        self.params = torch.zeros(self.n_params, dtype=torch.bfloat16, device=device)
+        self.grads_f32 = torch.zeros(self.n_params, dtype=torch.float32, device=device)
+        self.grads_bf16 = torch.zeros(self.n_params, dtype=torch.bfloat16, device=device)
+        self.master = None
+        self.exp_avg = None
+        self.exp_avg_sq = None
+        self.opt_step = 0
+        self._scratch = torch.zeros(1024, dtype=torch.float32, device=device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=device)
+        self.rope_cos, self.rope_sin = rope_tables(dims, rope_rows, device)
+        ws_bytes = lib().sf_eagle3_workspace_bytes(self.cfg)
+        if ws_bytes == 0:
+            check(-22, "sf_eagle3_workspace_bytes")
+        self.workspace_bytes = int(ws_bytes)
+        self.workspace = torch.empty(self.workspace_bytes + 1024, dtype=torch.uint8, device=device)
+        self._ws_ptr = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+        self.metrics = torch.zeros(ttt_length, 8, dtype=torch.float32, device=device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=device)
+        self.frozen_tensors: Dict[str, torch.Tensor] = {}
+        self._frozen = None
+        self._batch = None
+        self._batch_keep = None
+        self._grads_dirty = False
+
+    # ------------------------------------------------------------------ parameters
+    def shape_of(self, name: str):
+        d = self.dims
+        H, I, hd = d.hidden_size, d.intermediate_size, d.head_dim
+        return {
+            "fc.weight": (H, 3 * d.target_hidden_size),
+            "midlayer.self_attn.q_proj.weight": (d.num_heads * hd, 2 * H),
+            "midlayer.self_attn.k_proj.weight": (d.num_kv_heads * hd, 2 * H),
+            "midlayer.self_attn.v_proj.weight": (d.num_kv_heads * hd, 2 * H),
+            "midlayer.self_attn.o_proj.weight": (H, d.num_heads * hd),
+            "midlayer.mlp.gate_proj.weight": (I, H),
+            "midlayer.mlp.up_proj.weight": (I, H),
+            "midlayer.mlp.down_proj.weight": (H, I),
+            "midlayer.hidden_norm.weight": (H,),
+            "midlayer.input_layernorm.weight": (H,),
+            "midlayer.post_attention_layernorm.weight": (H,),
+            "norm.weight": (H,),
+            "lm_head.weight": (d.draft_vocab_size, H),
+            "fc_norm.0.weight": (d.target_hidden_size,),
+            "fc_norm.1.weight": (d.target_hidden_size,),
+            "fc_norm.2.weight": (d.target_hidden_size,),
+        }[name]
+
+    def param_view(self, name: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        buf = self.params if buf is None else buf
+        o, n = self.offsets[name], self.sizes[name]
+        return buf[o:o + n].view(self.shape_of(name))
+
+    def load_params(self, state: Dict[str, torch.Tensor]) -> None:
+        for name in self.offsets:
+            self.param_view(name).copy_(state[name].to(self.device, torch.bfloat16))
+        self.master = None
+
+    def set_frozen(self, *, embed_tokens: torch.Tensor, target_head: torch.Tensor, t2d: torch.Tensor, d2t: torch.Tensor) -> None:
+        dev = self.device
+        ft = {
+            "embed_tokens": embed_tokens.to(dev, torch.bfloat16).contiguous(),
+            "target_head": target_head.to(dev, torch.bfloat16).contiguous(),
+            "t2d": t2d.to(dev).to(torch.uint8).contiguous(),
+            "d2t": d2t.to(dev, torch.int64).contiguous(),
+        }
+        d = self.dims
+        assert ft["embed_tokens"].shape == (d.vocab_size, d.hidden_size), ft["embed_tokens"].shape
+        assert ft["target_head"].shape == (d.vocab_size, d.target_hidden_size), ft["target_head"].shape
+        assert ft["t2d"].shape == (d.vocab_size,) and ft["d2t"].shape == (d.draft_vocab_size,)
+        if int(ft["t2d"].sum().item()) != d.draft_vocab_size:
+            raise ValueError("t2d must select exactly draft_vocab_size target tokens")
+        self.frozen_tensors = ft
+        self._frozen = SfFrozen(ft["embed_tokens"].data_ptr(), ft["target_head"].data_ptr(), self.rope_cos.data_ptr(),
+                                self.rope_sin.data_ptr(), ft["t2d"].data_ptr(), ft["d2t"].data_ptr())
+
+    # ------------------------------------------------------------------ step
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _bind_batch(self, batch: Dict[str, torch.Tensor]) -> None:
+        B, S, d = self.B, self.S, self.dims
+        dev = self.device
+        t = {
+            "input_ids": batch["input_ids"].to(dev, torch.int64, non_blocking=True).contiguous(),
+            "loss_mask": batch["loss_mask"].to(dev, torch.int64, non_blocking=True).contiguous(),
+            "hidden_state": batch["hidden_state"].to(dev, torch.bfloat16, non_blocking=True).contiguous(),
+            "target": batch["target"].to(dev, torch.bfloat16, non_blocking=True).contiguous(),
+        }
+        am = batch.get("attention_mask")
+        t["attention_mask"] = None if am is None else am.to(dev, torch.int64, non_blocking=True).contiguous()
+        if t["input_ids"].shape != (B, S):
+            raise ValueError(f"input_ids must be [{B}, {S}], got {tuple(t['input_ids'].shape)}")
+        if t["loss_mask"].numel() != B * S:
+            raise ValueError(f"loss_mask must have {B * S} elements, got {tuple(t['loss_mask'].shape)}")
+        if t["hidden_state"].shape != (B, S, 3 * d.target_hidden_size):
+            raise ValueError(f"hidden_state must be [{B}, {S}, {3 * d.target_hidden_size}], got {tuple(t['hidden_state'].shape)}")
+        if t["target"].shape != (B, S, d.target_hidden_size):
+            raise ValueError(f"target must be [{B}, {S}, {d.target_hidden_size}], got {tuple(t['target'].shape)}")
+        self._batch_keep = t
+        self._batch = SfBatch(t["input_ids"].data_ptr(), 0 if t["attention_mask"] is None else t["attention_mask"].data_ptr(),
+                              t["loss_mask"].data_ptr(), t["hidden_state"].data_ptr(), t["target"].data_ptr())
+
+    def forward(self, batch: Dict[str, torch.Tensor], need_grad: bool = True):
+        """Teacher + TTT forward + loss.  Returns (loss[1], metrics[T, 8]) device tensors (no host sync)."""
+        if self._frozen is None:
+            raise RuntimeError("set_frozen() must be called before forward()")
+        self._bind_batch(batch)
+        check(lib().sf_eagle3_forward(self.cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
+                                      self.workspace_bytes, self.metrics.data_ptr(), self.loss.data_ptr(), int(need_grad),
+                                      self._stream()), "sf_eagle3_forward")
+        return self.loss, self.metrics
+
+    def backward(self, loss_scale: float = 1.0, accumulate: bool = False) -> None:
+        if self._batch is None:
+            raise RuntimeError("backward() without a preceding forward(need_grad=True)")
+        check(lib().sf_eagle3_backward(self.cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
+                                       self.workspace_bytes, loss_scale, self.grads_f32.data_ptr(), int(accumulate),
+                                       self._stream()), "sf_eagle3_backward")
+        self._grads_dirty = True
+
+    def grads_to_bf16(self) -> torch.Tensor:
+        check(lib().sf_grads_to_bf16(self.grads_f32.data_ptr(), self.grads_bf16.data_ptr(), self.n_params, self._stream()),
+              "sf_grads_to_bf16")
+        return self.grads_bf16
+
+    def optimizer_step(self, lr: float, *, grad_scale: float = 1.0, max_grad_norm: float = 0.5, betas=(0.9, 0.999),
+                       eps: float = 1e-8, weight_decay: float = 0.0) -> torch.Tensor:
+        if self.master is None:
+            self.master = self.params.float()
+            self.exp_avg = torch.zeros_like(self.master)
+            self.exp_avg_sq = torch.zeros_like(self.master)
+        self.opt_step += 1
+        check(lib().sf_optimizer_step(self.grads_bf16.data_ptr(), self.master.data_ptr(), self.exp_avg.data_ptr(),
+                                      self.exp_avg_sq.data_ptr(), self.params.data_ptr(), self.n_params, grad_scale,
+                                      max_grad_norm, lr, betas[0], betas[1], eps, weight_decay, self.opt_step,
+                                      self.grad_norm.data_ptr(), self._scratch.data_ptr(), self._stream()),
+              "sf_optimizer_step")
+        return self.grad_norm
+
+    # ------------------------------------------------------------------ FLOP model
+    def flops_per_step(self) -> float:
+        d = self.dims
+        M = self.B * self.S
+        H, I, Ht = d.hidden_size, d.intermediate_size, d.target_hidden_size
+        A, KV = d.num_heads * d.head_dim, d.num_kv_heads * d.head_dim
+        per_tok_step = 2 * (2 * H) * (A + 2 * KV) + 2 * A * H + 3 * 2 * H * I + 2 * H * d.draft_vocab_size
+        attn = 4 * (self.S / 2) * d.num_heads * d.head_dim
+        fwd = self.T * (per_tok_step + attn) + 2 * 3 * Ht * H
+        train = 3 * self.T * (per_tok_step + attn) + 2 * (2 * 3 * Ht * H)
+        teacher = 2 * Ht * d.vocab_size
+        _ = fwd
+        return float(M) * (train + teacher)

@@ -32,3 +32,106 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major=MAJOR_K, b_major=MAJOR_K, 
                              0 if residual is None else residual.stride(0), M, N, K, epi, cta_group, _stream()),
           "sf_gemm_bf16")
     return out
+
+
+def _declare_ops():
+    import ctypes
+    from ctypes import POINTER, c_float, c_int, c_int64, c_void_p
+    l = lib()
+    if getattr(l, "_sf_ops_declared", False):
+        return l
+    l.sf_rmsnorm_fwd.restype = c_int
+    l.sf_rmsnorm_fwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p]
+    l.sf_rmsnorm_bwd.restype = c_int
+    l.sf_rmsnorm_bwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                 c_int, c_float, c_void_p]
+    l.sf_swiglu_fwd.restype = c_int
+    l.sf_swiglu_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p]
+    l.sf_swiglu_bwd.restype = c_int
+    l.sf_swiglu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
+    l.sf_rope.restype = c_int
+    l.sf_rope.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]
+    l.sf_ttt_attention_fwd.restype = c_int
+    l.sf_ttt_attention_fwd.argtypes = [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_int, c_void_p]
+    l.sf_ttt_attention_bwd.restype = c_int
+    l.sf_ttt_attention_bwd.argtypes = [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                       c_int, c_int, c_int, c_void_p]
+    l._sf_ops_declared = True
+    return l
+
+
+def rmsnorm_fwd(x, w, eps):
+    l = _declare_ops()
+    out = torch.empty_like(x)
+    check(l.sf_rmsnorm_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1],
+                           eps, _stream()), "sf_rmsnorm_fwd")
+    return out
+
+
+def rmsnorm_bwd(x, w, dy, eps, add=None):
+    l = _declare_ops()
+    dx = torch.empty_like(x)
+    dw = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
+    check(l.sf_rmsnorm_bwd(x.data_ptr(), x.stride(0), w.data_ptr(), dy.data_ptr(), dy.stride(0), _ptr(add), dx.data_ptr(),
+                           dw.data_ptr(), x.shape[0], x.shape[1], eps, _stream()), "sf_rmsnorm_bwd")
+    return dx, dw
+
+
+def swiglu_fwd(gu):
+    l = _declare_ops()
+    M, I2 = gu.shape
+    act = torch.empty(M, I2 // 2, dtype=gu.dtype, device=gu.device)
+    check(l.sf_swiglu_fwd(gu.data_ptr(), act.data_ptr(), M, I2 // 2, _stream()), "sf_swiglu_fwd")
+    return act
+
+
+def swiglu_bwd(gu, dact):
+    l = _declare_ops()
+    dgu = torch.empty_like(gu)
+    check(l.sf_swiglu_bwd(gu.data_ptr(), dact.data_ptr(), dgu.data_ptr(), gu.shape[0], gu.shape[1] // 2, _stream()),
+          "sf_swiglu_bwd")
+    return dgu
+
+
+def rope_(x, n_heads, head_dim, cos, sin, S, pos_offset, inverse=False):
+    l = _declare_ops()
+    check(l.sf_rope(x.data_ptr(), x.stride(0), n_heads, head_dim, cos.data_ptr(), sin.data_ptr(), S, pos_offset, x.shape[0],
+                    int(inverse), _stream()), "sf_rope")
+    return x
+
+
+def _ptr_array(tensors):
+    import ctypes
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def ttt_attention_fwd(qkv_list, B, S, nh, nkv, hd, key_mask=None):
+    """qkv_list[i]: [B*S, (nh+2nkv)*hd] fused buffers of TTT blocks 0..J (RoPE already applied); queries = block J."""
+    l = _declare_ops()
+    J = len(qkv_list) - 1
+    dev = qkv_list[0].device
+    out = torch.empty(B * S, nh * hd, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(B, nh, S, dtype=torch.float32, device=dev)
+    sd = torch.empty(B * nh * S * max(J, 1), dtype=torch.float32, device=dev)
+    check(l.sf_ttt_attention_fwd(_ptr_array(qkv_list), J, out.data_ptr(), lse.data_ptr(), sd.data_ptr(), _ptr(key_mask), B, S,
+                                 nh, nkv, hd, _stream()), "sf_ttt_attention_fwd")
+    return out, lse
+
+
+def ttt_attention_bwd(qkv_list, out, dout, lse, B, S, nh, nkv, hd, key_mask=None):
+    l = _declare_ops()
+    J = len(qkv_list) - 1
+    dev = out.device
+    dk = [torch.zeros(B * S, nkv * hd, dtype=torch.float32, device=dev) for _ in range(J + 1)]
+    dv = [torch.zeros(B * S, nkv * hd, dtype=torch.float32, device=dev) for _ in range(J + 1)]
+    dq = torch.empty(B * S, nh * hd, dtype=torch.bfloat16, device=dev)
+    sd = torch.empty(B * nh * S * max(J, 1), dtype=torch.float32, device=dev)
+    delta = torch.empty(B * nh * S, dtype=torch.float32, device=dev)
+    dqd = torch.empty(B * S, nh * hd, dtype=torch.float32, device=dev)
+    check(l.sf_ttt_attention_bwd(_ptr_array(qkv_list), J, out.data_ptr(), dout.data_ptr(), lse.data_ptr(), sd.data_ptr(),
+                                 _ptr(key_mask), _ptr_array(dk), _ptr_array(dv), dq.data_ptr(), delta.data_ptr(),
+                                 dqd.data_ptr(), B, S, nh, nkv, hd, _stream()), "sf_ttt_attention_bwd")
+    return dq, dk, dv

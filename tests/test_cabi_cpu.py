@@ -1,0 +1,53 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/specforge_b200.h declares,
+and its pure-host entry points (layout / workspace planning / argument validation) behave."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from specforge_b200._lib import LIB_PATH, build_library, lib
+    if not os.path.exists(LIB_PATH):
+        build_library()
+    return lib()
+
+
+def test_exports_every_declared_symbol(L):
+    hdr = open(os.path.join(ROOT, "include", "specforge_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(sf_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 18, names
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_param_layout_and_workspace(L):
+    from specforge_b200.engine import P_COUNT, SfConfig, _declare
+    from ctypes import c_int64
+    _declare()
+    # Qwen3-8B EAGLE3 draft (configs/qwen3-8b-eagle3.json): 399.52 M trainable parameters
+    cfg = SfConfig(8, 2048, 7, 4096, 4096, 12288, 32, 8, 128, 151936, 32000, 0, 1, 40980, 1e-6, 0.8)
+    offs, sizes, total = (c_int64 * P_COUNT)(), (c_int64 * P_COUNT)(), c_int64()
+    assert L.sf_eagle3_param_layout(cfg, offs, sizes, ctypes.byref(total)) == 0
+    assert total.value == 399_523_840 + 0 or abs(total.value - 399.52e6) < 0.01e6
+    # q,k,v adjacent and gate,up adjacent (fused GEMM operands)
+    assert offs[2] == offs[1] + sizes[1] and offs[3] == offs[2] + sizes[2]
+    assert offs[6] == offs[5] + sizes[5]
+    ws = L.sf_eagle3_workspace_bytes(cfg)
+    assert 20e9 < ws < 80e9, ws
+    bad = SfConfig(8, 2048, 7, 4096, 4096, 12288, 32, 8, 96, 151936, 32000, 0, 1, 40980, 1e-6, 0.8)
+    assert L.sf_eagle3_workspace_bytes(bad) == 0
+    assert b"head_dim" in L.sf_last_error()
+
+
+def test_gemm_rejects_bad_arguments_without_a_gpu(L):
+    from specforge_b200 import _lib
+    rc = L.sf_gemm_bf16(None, 8, 0, None, 8, 0, None, 8, None, 0, 0, 16, 16, 0, 0, None)
+    assert rc != 0 and b"empty" in L.sf_last_error()
+    with pytest.raises(_lib.SfError):
+        _lib.check(rc, "sf_gemm_bf16")

@@ -1,0 +1,146 @@
+"""Kernel-level parity (GPU): each CUDA op, called through the C ABI, against the oracle / an fp32 torch
+restatement of the same op on the same seeded inputs.  Tolerances are bf16-level and stated per test."""
+import ctypes
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _trunc_normal(shape, std=0.02, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * std).clamp_(-2 * std, 2 * std)
+
+
+@pytest.mark.parametrize("G", [1, 2])
+@pytest.mark.parametrize("am,bm", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K,epi", [(512, 512, 256, 0), (384, 320, 200, 2), (1000, 776, 1096, 1), (130, 72, 64, 3)])
+def test_gemm(G, am, bm, M, N, K, epi):
+    from specforge_b200 import ops
+    torch.manual_seed(0)
+    dev = _dev()
+    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+    a = A if am == 0 else A.t().contiguous()
+    b = B if bm == 0 else B.t().contiguous()
+    ref = A.float() @ B.float().t()
+    R = out0 = out = None
+    if epi == 1:
+        R = torch.randn(M, N, device=dev).bfloat16()
+        ref = ref.bfloat16().float() + R.float()
+    if epi == 3:
+        out0 = torch.randn(M, N, device=dev)
+        ref = ref + out0
+        out = out0.clone()
+    got = ops.gemm(a, b, a_major=am, b_major=bm, out=out, residual=R, epi=epi, cta_group=G).float()
+    tol = 1e-5 if epi >= 2 else 2 ** -7     # fp32 out: accumulation-order noise only; bf16 out: 1 rounding (+1 for resid)
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= tol * scale * (2 if epi == 1 else 1) + 1e-4
+
+
+def test_rmsnorm_fwd_bwd():
+    from oracle import eagle3_oracle as O
+    from specforge_b200 import ops
+    dev = _dev()
+    M, H = 300, 896
+    x = torch.randn(M, H, device=dev).bfloat16()
+    w = (1 + 0.1 * torch.randn(H, device=dev)).bfloat16()
+    dy = torch.randn(M, H, device=dev).bfloat16()
+    add = torch.randn(M, H, device=dev).bfloat16()
+    y = ops.rmsnorm_fwd(x, w, 1e-6)
+    ref = O.rms_norm(x, w, 1e-6)
+    assert (y.float() - ref.float()).abs().max().item() <= 2 ** -6 * ref.float().abs().max().item()
+    # backward vs autograd of the fp32 restatement
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    yf = wf * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6))
+    yf.backward(dy.float())
+    dx, dw = ops.rmsnorm_bwd(x, w, dy, 1e-6, add=add)
+    ref_dx = xf.grad + add.float()
+    assert (dx.float() - ref_dx).abs().max().item() <= 2 ** -6 * ref_dx.abs().max().item()
+    assert (dw - wf.grad).abs().max().item() <= 2e-2 * wf.grad.abs().max().item()
+
+
+def test_swiglu_and_rope():
+    from oracle import eagle3_oracle as O
+    from specforge_b200 import ops
+    dev = _dev()
+    M, I = 257, 4864
+    gu = torch.randn(M, 2 * I, device=dev).bfloat16()
+    act = ops.swiglu_fwd(gu)
+    ref = torch.nn.functional.silu(gu[:, :I]) * gu[:, I:]
+    assert (act.float() - ref.float()).abs().max().item() <= 2 ** -7 * ref.float().abs().max().item()
+    g = gu[:, :I].float().requires_grad_(True)
+    u = gu[:, I:].float().requires_grad_(True)
+    d = torch.randn(M, I, device=dev).bfloat16()
+    (torch.nn.functional.silu(g) * u).backward(d.float())
+    dgu = ops.swiglu_bwd(gu, d)
+    refd = torch.cat([g.grad, u.grad], dim=1)
+    assert (dgu.float() - refd).abs().max().item() <= 2 ** -6 * refd.abs().max().item()
+    # rope at offset 3 vs the oracle formula evaluated in fp32 with the bf16 tables
+    cfg = O.Eagle3Config(hidden_size=256, intermediate_size=512, num_heads=4, num_kv_heads=1, head_dim=128, vocab_size=1024,
+                         draft_vocab_size=256, rope_theta=1e6, max_position_embeddings=512)
+    cos, sin = O.rope_tables(cfg, torch.bfloat16)
+    cos, sin = cos.to(dev), sin.to(dev)
+    B, S, nh, hd = 2, 70, 5, 128
+    x = torch.randn(B * S, nh * hd, device=dev).bfloat16()
+    pos = (torch.arange(S, device=dev) + 3).repeat(B)
+    xr = x.float().view(B * S, nh, hd)
+    c, s_ = cos[pos].float()[:, None], sin[pos].float()[:, None]
+    ref = xr * c + O.rotate_half(xr) * s_
+    y = x.clone()
+    ops.rope_(y, nh, hd, cos, sin, S, 3, inverse=False)
+    assert (y.float().view_as(ref) - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    ops.rope_(y, nh, hd, cos, sin, S, 3, inverse=True)   # transpose rotation: R^T R x = (cos^2+sin^2) x ~ x
+    assert (y.float() - x.float()).abs().max().item() <= 0.05 * x.float().abs().max().item()
+
+
+@pytest.mark.parametrize("hd,nh,nkv,S,J,pad", [(128, 4, 1, 160, 0, 0), (128, 4, 1, 160, 3, 9), (64, 14, 2, 128, 2, 0),
+                                               (128, 8, 2, 333, 6, 40), (64, 4, 4, 64, 1, 0)])
+def test_ttt_attention_fwd_bwd(hd, nh, nkv, S, J, pad):
+    """vs the oracle's eager TTT attention (llama3_eagle.py:717-785) in fp32 with autograd."""
+    from oracle import eagle3_oracle as O
+    from specforge_b200 import ops
+    dev = _dev()
+    torch.manual_seed(J + S)
+    B = 2
+    A, KV = nh * hd, nkv * hd
+    qkv = [(torch.randn(B * S, A + 2 * KV, device=dev) * 0.7).bfloat16() for _ in range(J + 1)]
+    am = torch.ones(B, S, dtype=torch.long, device=dev)
+    if pad:
+        am[-1, S - pad:] = 0
+    key_mask = am.to(torch.uint8) if pad else None
+    out, lse = ops.ttt_attention_fwd(qkv, B, S, nh, nkv, hd, key_mask=key_mask)
+    # reference (fp32, autograd)
+    leaves = [t.float().requires_grad_(True) for t in qkv]
+    cache_k, cache_v = [], []
+    mask = O.decoder_attention_mask(am.cpu(), S, torch.float32).to(dev)
+    ref = None
+    for i in range(J + 1):
+        q = leaves[i][:, :A].view(B, S, nh, hd).transpose(1, 2)
+        k = leaves[i][:, A:A + KV].view(B, S, nkv, hd).transpose(1, 2)
+        v = leaves[i][:, A + KV:].view(B, S, nkv, hd).transpose(1, 2)
+        ref = O.ttt_attention(q, k, v, cache_k, cache_v, mask, nh // nkv)
+    ref = ref.reshape(B * S, A)
+    valid = am.bool().view(-1)            # padded QUERY rows see a fully-masked block 0 in the reference (-inf quirk)
+    err = (out.float() - ref)[valid].abs().max().item()
+    assert err <= 2e-2 * ref[valid].abs().max().item() + 1e-3, err
+    dout = (torch.randn(B * S, A, device=dev) * 0.5).bfloat16()
+    dout[~valid] = 0
+    ref.backward(dout.float())
+    dq, dk, dv = ops.ttt_attention_bwd(qkv, out, dout, lse, B, S, nh, nkv, hd, key_mask=key_mask)
+    gq = leaves[J].grad[:, :A]
+    assert torch.nn.functional.cosine_similarity(dq.float().flatten(), gq.flatten(), dim=0) > 0.999
+    assert (dq.float() - gq).abs().max().item() <= 3e-2 * gq.abs().max().item() + 1e-3
+    for i in range(J + 1):
+        # grads w.r.t. block i's K/V from THIS step only (the query grad of block i<J is zero here)
+        gk = leaves[i].grad[:, A:A + KV]
+        gv = leaves[i].grad[:, A + KV:]
+        assert (dk[i] - gk).abs().max().item() <= 3e-2 * gk.abs().max().item() + 1e-3, i
+        assert (dv[i] - gv).abs().max().item() <= 3e-2 * gv.abs().max().item() + 1e-3, i
