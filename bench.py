@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py — EAGLE3 draft-step samples/sec (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm (CPU port) on the host cores
+
+One "step" = teacher + TTT-unrolled forward + loss + full backward + gradient all-reduce (N>1) + clip/AdamW on one
+micro-batch per GPU.  Workload at every N: BASELINE config 2 per GPU — Qwen3-8B EAGLE3 draft (configs/qwen3-8b-eagle3.json
+dims), B=8 sequences x S=2048, TTT=7, synthetic hidden states, random-init weights (weak scaling, DP).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+QWEN3_8B = dict(hidden_size=4096, intermediate_size=12288, num_heads=32, num_kv_heads=8, head_dim=128, vocab_size=151936,
+                draft_vocab_size=32000, rms_norm_eps=1e-6, rope_theta=1000000.0, max_position_embeddings=40960)
+B, S, T = 8, 2048, 7
+METRIC = "EAGLE3 draft-step samples/sec (Qwen3-8B, TTT=7, seq 2048)"
+CPU_SAMPLE_TOKENS = 256
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["bf16_tflops_sustained"], p["bf16_tflops"], "measured (MEASURED_PEAKS.json, sustained for a long step)"
+    except Exception:
+        return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(float(self.rows[0][1])) if self.rows else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step_rate(steps: int, warmup: int, tokens: int = CPU_SAMPLE_TOKENS):
+    """The reference algorithm (oracle port of the PyTorch path, bf16 modules, torch autograd + AdamW on fp32 masters)
+    on the host cores.  Bounded sample: 1 sequence x `tokens` tokens of the config-2 dims, TTT=7; samples/s is scaled by
+    tokens (tokens/2048 of a sample per step)."""
+    import torch
+    from oracle import eagle3_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.Eagle3Config(ttt_length=T, **{k: v for k, v in QWEN3_8B.items()})
+    g = torch.Generator().manual_seed(0)
+    P = {}
+    for name, shape in O.param_shapes(cfg).items():
+        P[name] = (torch.ones(shape) if len(shape) == 1 else torch.empty(shape).uniform_(-0.03, 0.03, generator=g)).to(torch.bfloat16)
+    P["embed_tokens.weight"] = torch.empty(cfg.vocab_size, cfg.hidden_size).uniform_(-0.03, 0.03, generator=g).to(torch.bfloat16)
+    head_w = torch.empty(cfg.vocab_size, cfg.target_hidden_size).uniform_(-1, 1, generator=g).to(torch.bfloat16)
+    t2d, d2t = O.make_vocab_map(cfg.vocab_size, cfg.draft_vocab_size, seed=0)
+    names = [n for n in O.PARAM_NAMES]
+    params = [P[n] for n in names]
+    masters = [p.float() for p in params]
+    ea = [torch.zeros_like(m) for m in masters]
+    es = [torch.zeros_like(m) for m in masters]
+    times = []
+    for it in range(warmup + steps):
+        batch = O.make_batch(cfg, 1, tokens, seed=it)
+        t0 = time.perf_counter()
+        res, grads = O.train_step(P, cfg, batch, head_w, t2d, d2t)
+        O.adamw_clip_step(params, masters, ea, es, [grads[n] for n in names], step=it + 1, lr=1e-4)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return (tokens / S) / (ms / 1e3), ms, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 6))
+    warm = max(1, min(args.warmup, 1))
+    val, ms, cores = cpu_reference_step_rate(steps, warm)
+    sample = (f"1 sequence x {CPU_SAMPLE_TOKENS} tokens of the Qwen3-8B draft dims, TTT=7, fwd+bwd+AdamW, bf16 modules, "
+              f"scaled by tokens ({CPU_SAMPLE_TOKENS}/2048 sample per step); {steps} timed steps after {warm} warm-up")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: Qwen3-8B EAGLE3 offline draft step, TTT=7, seq 2048 (CPU: bounded sample)",
+                       "ttt_length": T, "seq_len": S},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from specforge_b200._lib import lib
+    from specforge_b200.backend import B200TrainingBackend
+    from specforge_b200.contracts import TrainBatch
+    from specforge_b200.draft import B200Eagle3DraftModel
+    from specforge_b200.strategy import B200Eagle3TrainStrategy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the EAGLE3 hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = lib()
+    import ctypes
+    L.sf_profile_gemm.restype = None
+    L.sf_profile_gemm_collect.restype = ctypes.c_longlong
+    L.sf_profile_gemm_collect.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+
+    cfg = dict(QWEN3_8B)
+    cfg.update(num_attention_heads=cfg.pop("num_heads"), num_key_value_heads=cfg.pop("num_kv_heads"))
+    draft = B200Eagle3DraftModel(cfg)
+    eng = draft.bind_engine(batch=B, seq_len=S, ttt_length=T, device=dev, seed=0)
+    # frozen tables: random (no checkpoints offline), identical on every rank
+    gen = torch.Generator(device=dev).manual_seed(0)
+    V, H, DV = cfg["vocab_size"], cfg["hidden_size"], cfg["draft_vocab_size"]
+    draft.embed_tokens_weight.data = (torch.randn(V, H, device=dev, generator=gen) * 0.02).bfloat16()
+    head_w = torch.randn(V, H, device=dev, generator=gen).bfloat16()
+    perm = torch.randperm(V, device=dev, generator=gen)[:DV].sort().values
+    draft.t2d.zero_()
+    draft.t2d[perm] = True
+    draft.d2t.copy_(perm - torch.arange(DV, device=dev))
+    strategy = B200Eagle3TrainStrategy(draft, target_head_weight=head_w)
+    backend = B200TrainingBackend(lr=1e-4, max_grad_norm=0.5, total_steps=100000, warmup_ratio=0.015)
+    backend.attach(strategy)
+    backend.prepare_model(strategy.trainable_module())
+
+    # synthetic micro-batch, per-rank data seed
+    dgen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    dev_t = {
+        "input_ids": torch.randint(0, V, (B, S), device=dev, generator=dgen),
+        "attention_mask": torch.ones(B, S, dtype=torch.long, device=dev),
+        "loss_mask": torch.ones(B, S, dtype=torch.long, device=dev),
+        "hidden_state": torch.randn(B, S, 3 * H, device=dev, generator=dgen).bfloat16(),
+        "target": torch.randn(B, S, H, device=dev, generator=dgen).bfloat16(),
+    }
+    dev_t["loss_mask"][:, -1] = 0
+    host_t = {k: v.cpu().pin_memory() for k, v in dev_t.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host_t.values())
+    ids = [str(i) for i in range(B)]
+    dev_batch = TrainBatch(sample_ids=ids, strategy="eagle3", tensors=dev_t, metadata={"target_repr": "hidden_state"})
+    host_batch = TrainBatch(sample_ids=ids, strategy="eagle3", tensors=host_t, metadata={"target_repr": "hidden_state"})
+
+    def step(batch, read_loss):
+        out = strategy.forward_loss(batch)
+        backend.backward(out.loss, is_boundary=True)
+        backend.step()
+        return float(out.loss.item()) if read_loss else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batch, read_loss, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            last = step(batch, read_loss)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    for _ in range(max(3, args.warmup)):
+        step(dev_batch, False)
+    torch.cuda.synchronize()
+    # ---- kernel-resident measurement ("value"): inputs already in HBM, GEMM launches timed live with CUDA events
+    L.sf_launch_count_reset()
+    L.sf_profile_gemm(1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, _ = timed(dev_batch, False, args.steps)
+    clocks = sampler.stop()
+    launches = int(L.sf_launch_count())
+    gms, gfl = ctypes.c_double(), ctypes.c_double()
+    n_gemm = int(L.sf_profile_gemm_collect(ctypes.byref(gms), ctypes.byref(gfl)))
+    L.sf_profile_gemm(0)
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+    # ---- end-to-end through the public API with HOST (pinned) inputs: H2D of the batch + D2H of the loss each step
+    for _ in range(2):
+        step(host_batch, True)
+    ms_e2e, last_loss = timed(host_batch, True, args.steps)
+    e2e = world * B / (ms_e2e / args.steps / 1e3)
+
+    sustained, burst, peak_src = peaks()
+    flops_step = eng.flops_per_step()
+    achieved = (gfl.value / 1e12) / (gms.value / 1e3) if gms.value > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2 per GPU: Qwen3-8B EAGLE3 offline draft step (teacher + TTT fwd + loss + bwd + "
+                               "grad all-reduce + clip/AdamW)", "batch_per_gpu": B, "global_batch": world * B, "seq_len": S,
+                   "ttt_length": T, "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (per-step working set ~45 GB)",
+                   "weights": "random-init, reference shapes"},
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "sf::gemm_kernel (tcgen05, all %d launches/step)" % (n_gemm // max(1, args.steps)),
+                     "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained if sustained else None,
+                     "peak_burst": burst, "frac_of_burst": achieved / burst if burst else None, "peak_source": peak_src,
+                     "gemm_ms_per_step": gms.value / args.steps, "gemm_share_of_step": (gms.value / args.steps) / ms_step,
+                     "step_tflops_algorithmic": flops_step / 1e12 / (ms_step / 1e3) , "traffic": None},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            val, ms, cores = cpu_reference_step_rate(2, 1)
+            line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": f"oracle port of the reference PyTorch path, 1 sequence x {CPU_SAMPLE_TOKENS} tokens of the "
+                                              f"same dims, TTT=7, fwd+bwd+AdamW, 2 timed steps after 1 warm-up, scaled by tokens"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,12 @@ const char* sf_last_error(void);
 long long sf_launch_count(void);      /* kernels launched by this library since the last reset */
 void sf_launch_count_reset(void);
 
+/* Optional live timing of every tcgen05 GEMM launch with CUDA events on the launching stream (bench.py roofline).
+ * enable(1) resets the record; collect() (after a stream sync) returns the launch count and the summed device time
+ * and algorithmic FLOPs (2*M*N*K) of the recorded launches. */
+void sf_profile_gemm(int enable);
+long long sf_profile_gemm_collect(double* total_ms, double* total_flops);
+
 /* ---- model / step description ---- */
 typedef struct sf_eagle3_config {
     int32_t batch;            /* B  sequences per micro-batch on this GPU */
@@ -99,8 +105,10 @@ int sf_eagle3_backward(const sf_eagle3_config* cfg, const void* params_flat, con
                        const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float loss_scale,
                        float* grads_flat_f32, int accumulate, void* stream);
 
-/* grads_bf16[i] = bf16(grads_f32[i])  — the bf16 gradient buffer DDP all-reduces (backend.py:233-253). */
-int sf_grads_to_bf16(const float* grads_f32, void* grads_bf16, int64_t n, void* stream);
+/* grads_bf16[i] = bf16(grads_f32[i] * (scale_dev ? *scale_dev : 1))  — the bf16 gradient buffer DDP all-reduces
+ * (backend.py:233-253).  scale_dev is an optional DEVICE float (e.g. the 1/accumulation_steps that autograd hands
+ * to backward), so applying it needs no host synchronisation. */
+int sf_grads_to_bf16(const float* grads_f32, void* grads_bf16, int64_t n, const float* scale_dev, void* stream);
 
 /* BF16Optimizer.step (optimizer.py:140-168) fused: ||g|| over bf16(g * grad_scale), clip coefficient
  * min(1, max_norm/(||g||+1e-6)), AdamW on fp32 masters, bf16 write-back.  step is 1-based.

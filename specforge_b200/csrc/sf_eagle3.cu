@@ -368,8 +368,8 @@ extern "C" int sf_eagle3_backward(const sf_eagle3_config* cfg, const void* param
     }
     return 0;
 }
-extern "C" int sf_grads_to_bf16(const float* grads_f32, void* grads_bf16, int64_t n, void* stream) {
-    return cvt_flat_f32_bf16(grads_f32, grads_bf16, n, 0, reinterpret_cast<cudaStream_t>(stream));
+extern "C" int sf_grads_to_bf16(const float* grads_f32, void* grads_bf16, int64_t n, const float* scale_dev, void* stream) {
+    return cvt_flat_f32_bf16(grads_f32, grads_bf16, n, scale_dev, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int sf_optimizer_step(const void* grads_bf16, float* master, float* exp_avg, float* exp_avg_sq, void* params_bf16,
                                  int64_t n, float grad_scale, float max_grad_norm, float lr, float beta1, float beta2,

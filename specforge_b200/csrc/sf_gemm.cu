@@ -4,6 +4,7 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <vector>
 
 namespace sf {
 
@@ -39,6 +40,16 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t c
     if (r != CUDA_SUCCESS) return set_error(-22, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
+
+// ---- optional live timing of every GEMM launch (bench.py's roofline): CUDA events on the launching stream
+struct GemmProf {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;   // pairs
+    std::vector<double> flops;
+    size_t used = 0;
+};
+static GemmProf g_prof;
+static std::mutex g_prof_mu;
 
 static int num_sms() {
     static int n = 0;
@@ -87,7 +98,19 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_prof.on) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (g_prof.used + 2 > g_prof.ev.size()) {
+            for (int i = 0; i < 2; ++i) { cudaEvent_t ev; cudaEventCreate(&ev); g_prof.ev.push_back(ev); }
+        }
+        e0 = g_prof.ev[g_prof.used]; e1 = g_prof.ev[g_prof.used + 1];
+        g_prof.used += 2;
+        g_prof.flops.push_back(2.0 * (double)g.M * (double)g.N * (double)g.K);
+        cudaEventRecord(e0, stream);
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e1) cudaEventRecord(e1, stream);
     if (e != cudaSuccess) return set_error(-5, "gemm launch failed: %s", cudaGetErrorString(e));
     count_launch();
     return 0;
@@ -117,6 +140,26 @@ int gemm(const GemmDesc& g, cudaStream_t stream) {
 }
 
 }  // namespace sf
+
+extern "C" void sf_profile_gemm(int enable) {
+    std::lock_guard<std::mutex> lk(sf::g_prof_mu);
+    sf::g_prof.on = enable != 0;
+    sf::g_prof.used = 0;
+    sf::g_prof.flops.clear();
+}
+// Sums the recorded launches (call after synchronising the stream).  Returns the number of launches.
+extern "C" long long sf_profile_gemm_collect(double* total_ms, double* total_flops) {
+    std::lock_guard<std::mutex> lk(sf::g_prof_mu);
+    double ms = 0, fl = 0;
+    const size_t n = sf::g_prof.used / 2;
+    for (size_t i = 0; i < n; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sf::g_prof.ev[2 * i], sf::g_prof.ev[2 * i + 1]) == cudaSuccess) { ms += t; fl += sf::g_prof.flops[i]; }
+    }
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = fl;
+    return (long long)n;
+}
 
 extern "C" int sf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major,
                             void* D, int64_t ldd, const void* R, int64_t ldr, int M, int N, int K, int epi,

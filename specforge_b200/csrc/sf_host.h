@@ -60,7 +60,7 @@ int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod,
 int grad_norm(const void* g, int64_t n, float gscale, float* partials_ws, float* out, cudaStream_t st);
 int adamw(const void* g, float* master, float* m1, float* m2, void* param, int64_t n, const float* gnorm, float max_norm,
           float gscale, float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st);
-int cvt_flat_f32_bf16(const float* src, void* dst, int64_t n, int accumulate, cudaStream_t st);
+int cvt_flat_f32_bf16(const float* src, void* dst, int64_t n, const float* scale_dev, cudaStream_t st);
 
 #define SF_CUDA_CHECK_LAUNCH(what)                                                            \
     do {                                                                                      \

@@ -327,12 +327,18 @@ adamw_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ master, fl
     }
 }
 __global__ void __launch_bounds__(256) cvt_flat_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                               int64_t n, int accumulate) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float v = src[i];
-        if (accumulate) v += __bfloat162float(dst[i]);
-        dst[i] = __float2bfloat16_rn(v);
+                                                               int64_t n, const float* __restrict__ scale_dev) {
+    const float s = scale_dev ? scale_dev[0] : 1.0f;
+    const int64_t n4 = n / 4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        uint2 o;
+        o.x = pack_bf16x2(v.x * s, v.y * s);
+        o.y = pack_bf16x2(v.z * s, v.w * s);
+        reinterpret_cast<uint2*>(dst)[i] = o;
     }
+    if (blockIdx.x == 0)
+        for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16_rn(src[i] * s);
 }
 
 // ------------------------------------------------------------------ host wrappers
@@ -393,8 +399,8 @@ int adamw(const void* g, float* master, float* m1, float* m2, void* param, int64
     SF_CUDA_CHECK_LAUNCH("adamw");
     return 0;
 }
-int cvt_flat_f32_bf16(const float* src, void* dst, int64_t n, int accumulate, cudaStream_t st) {
-    cvt_flat_f32_bf16_kernel<<<148 * 8, 256, 0, st>>>(src, (__nv_bfloat16*)dst, n, accumulate);
+int cvt_flat_f32_bf16(const float* src, void* dst, int64_t n, const float* scale_dev, cudaStream_t st) {
+    cvt_flat_f32_bf16_kernel<<<148 * 8, 256, 0, st>>>(src, (__nv_bfloat16*)dst, n, scale_dev);
     SF_CUDA_CHECK_LAUNCH("cvt_flat");
     return 0;
 }

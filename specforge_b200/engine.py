@@ -78,7 +78,7 @@ def _declare():
     l.sf_eagle3_backward.argtypes = [POINTER(SfConfig), c_void_p, POINTER(SfFrozen), POINTER(SfBatch), c_void_p, c_size_t,
                                      c_float, c_void_p, ctypes.c_int, c_void_p]
     l.sf_grads_to_bf16.restype = ctypes.c_int
-    l.sf_grads_to_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    l.sf_grads_to_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     l.sf_optimizer_step.restype = ctypes.c_int
     l.sf_optimizer_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                     c_float, c_float, c_float, c_float, c_int32, c_void_p, c_void_p, c_void_p]
@@ -260,8 +260,14 @@ class Eagle3Engine:
                                        self._stream()), "sf_eagle3_backward")
         self._grads_dirty = True
 
-    def grads_to_bf16(self) -> torch.Tensor:
-        check(lib().sf_grads_to_bf16(self.grads_f32.data_ptr(), self.grads_bf16.data_ptr(), self.n_params, self._stream()),
+    def grads_to_bf16(self, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 accumulators -> the bf16 gradient buffer (optionally times a DEVICE scalar, no host sync)."""
+        sp = 0
+        if scale is not None:
+            scale = scale.detach().to(self.device, torch.float32).reshape(1)
+            self._scale_keep = scale
+            sp = scale.data_ptr()
+        check(lib().sf_grads_to_bf16(self.grads_f32.data_ptr(), self.grads_bf16.data_ptr(), self.n_params, sp, self._stream()),
               "sf_grads_to_bf16")
         return self.grads_bf16
 

@@ -1,0 +1,102 @@
+"""B200Eagle3TrainStrategy — drop-in for Eagle3TrainStrategy (specforge/training/strategies/base.py:123-319).
+
+Same `name`, `required_features`, `forward_loss(batch, ctx) -> StepOutput` (same metric keys, each a length-T list of
+0-dim tensors, controller.py:216-252), `ploss_decay`, `checkpoint_state_filter`; works under torch.no_grad() (eval,
+controller.py:794-815).  The whole step (teacher, TTT forward, loss, and later backward) runs in libspecforge_b200."""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .contracts import StepContext, StepOutput, TrainBatch
+from .draft import B200Eagle3DraftModel
+
+
+class _Eagle3StepFn(torch.autograd.Function):
+    """loss = f(params) with the forward/backward done by the C-ABI library.  The flat bf16 parameter buffer is the
+    single differentiable input; backward leaves dLoss/dparams in the engine's fp32 accumulator (the backend reads
+    it) and, for stock optimizers/DDP, also returns it to autograd as a bf16 tensor."""
+
+    @staticmethod
+    def forward(ctx, flat_params, strategy, batch_tensors, need_grad):
+        eng = strategy.engine
+        loss, _ = eng.forward(batch_tensors, need_grad=need_grad)
+        ctx.strategy = strategy
+        return loss.clone().reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        strategy = ctx.strategy
+        eng = strategy.engine
+        eng.backward(loss_scale=1.0, accumulate=strategy._micro_in_window > 0)
+        strategy._micro_in_window += 1
+        strategy._last_grad_out = grad_out.detach()
+        if strategy.return_autograd_grads:
+            g = eng.grads_to_bf16(scale=grad_out)
+            return g.clone(), None, None, None
+        return None, None, None, None
+
+
+class _Trainable(nn.Module):
+    """What `trainable_module()` returns: exposes `.draft_model` like OnlineEagle3Model (trainer.py:205,425)."""
+
+    def __init__(self, draft_model: B200Eagle3DraftModel):
+        super().__init__()
+        self.draft_model = draft_model
+
+
+class B200Eagle3TrainStrategy:
+    name = "eagle3"
+    required_features = {"input_ids", "attention_mask", "loss_mask", "hidden_state", "target"}
+
+    def __init__(self, draft_model: B200Eagle3DraftModel, *, target_head_weight: torch.Tensor, ploss_decay: float = 0.8,
+                 return_autograd_grads: bool = False):
+        if draft_model.engine is None:
+            raise RuntimeError("bind_engine() must be called on the draft model first")
+        self.draft_model = draft_model
+        self.engine = draft_model.engine
+        if abs(self.engine.ploss_decay - ploss_decay) > 1e-12:
+            raise ValueError("ploss_decay differs from the value the engine was bound with")
+        self.ploss_decay = ploss_decay
+        self.return_autograd_grads = return_autograd_grads
+        self._module = _Trainable(draft_model)
+        self._micro_in_window = 0
+        self._last_grad_out: Optional[torch.Tensor] = None
+        draft_model.sync_frozen(target_head_weight)
+
+    def trainable_module(self) -> nn.Module:
+        return self._module
+
+    def validate_batch(self, batch: TrainBatch) -> None:
+        missing = {f for f in self.required_features if f not in batch.tensors}
+        if missing:
+            raise ValueError(f"{self.name} batch missing required features {sorted(missing)}; present={sorted(batch.tensors)}")
+
+    def forward_loss(self, batch: TrainBatch, ctx: Optional[StepContext] = None) -> StepOutput:
+        self.validate_batch(batch)
+        target_repr = batch.metadata.get("target_repr", "hidden_state")
+        if target_repr != "hidden_state":
+            raise ValueError(f"target_repr={target_repr!r}: the CUDA path implements the offline hidden-state teacher only")
+        need_grad = torch.is_grad_enabled()
+        eng = self.engine
+        flat = eng.params if not need_grad else eng.params.detach().requires_grad_(True)
+        loss = _Eagle3StepFn.apply(flat, self, batch.tensors, need_grad)
+        m = eng.metrics.clone()  # [T, 8] on device; slicing below creates views, no host sync
+        T = eng.T
+        metrics = {
+            "plosses": [m[j, 0] for j in range(T)],
+            "acces": [m[j, 1] / m[j, 2] for j in range(T)],
+            "acceptance_rates": [m[j, 3] for j in range(T)],
+            "acc_corrects": [m[j, 1] for j in range(T)],
+            "acc_denoms": [m[j, 2] for j in range(T)],
+            "metric_losses": [m[j, 0] for j in range(T)],
+            "metric_loss_denoms": [m[j, 6] for j in range(T)],
+        }
+        return StepOutput(loss=loss, metrics=metrics)
+
+    def checkpoint_state_filter(self, state_dict: Dict[str, Any]) -> Dict[str, Any]:
+        """Same rule as the reference (strategies/base.py:306-319): draft weights without the `draft_model.` prefix,
+        frozen embedding dropped."""
+        return {k.replace("draft_model.", ""): v for k, v in state_dict.items() if "embed" not in k.lower()}

@@ -74,8 +74,10 @@ def test_step_matches_reference_golden(case):
         assert (got - ref).abs().max().item() <= 2.5 * gold["lr_used"] + 2 ** -8 * ref.abs().max().item(), n
 
 
-def test_step_matches_fp32_oracle_on_gpu_inputs():
-    """Independent of the goldens: fp32 oracle (CPU) vs CUDA path on a padded batch, d=64, GQA 2:1."""
+def test_step_matches_oracle_on_fresh_inputs():
+    """Independent of the goldens: the bf16 oracle (CPU, same rounding points as the reference) vs the CUDA path on a
+    padded batch, d=64, GQA 2:1.  (An fp32 oracle is NOT comparable at 1e-3: the reference rounds the teacher logits
+    to bf16, which alone moves the loss by ~1 % at these tiny dims.)"""
     from oracle import eagle3_oracle as O
     gold = {"cfg": dict(hidden_size=128, intermediate_size=384, num_heads=4, num_kv_heads=2, head_dim=64, vocab_size=512,
                         draft_vocab_size=128, rms_norm_eps=1e-5, rope_theta=10000.0, max_position_embeddings=256,
@@ -84,15 +86,13 @@ def test_step_matches_fp32_oracle_on_gpu_inputs():
     loss, metrics = eng.forward(batch, need_grad=True)
     eng.backward()
     torch.cuda.synchronize()
-    P32 = {k: v.float() for k, v in P.items()}
-    b32 = {k: (v.float() if v.is_floating_point() else v) for k, v in batch.items()}
-    res, grads = O.train_step(P32, cfg, b32, head_w.float(), t2d, d2t)
-    ref_pl = torch.stack([p.detach() for p in res.plosses])
-    torch.testing.assert_close(metrics[:, 0].cpu(), ref_pl, rtol=2e-3, atol=1e-5)
+    res, grads = O.train_step(P, cfg, batch, head_w, t2d, d2t)
+    ref_pl = torch.stack([p.detach().float() for p in res.plosses])
+    torch.testing.assert_close(metrics[:, 0].cpu(), ref_pl, rtol=1e-3, atol=1e-5)
     for n, ref in grads.items():
         got = eng.param_view(n, eng.grads_f32).float().cpu()
-        cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
-        assert cos >= 0.995, (n, cos)
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.float().flatten(), dim=0).item()
+        assert cos >= 0.999, (n, cos)
 
 
 def test_eval_forward_and_errors():
