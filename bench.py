@@ -28,7 +28,8 @@ QWEN3_8B = dict(hidden_size=4096, intermediate_size=12288, num_heads=32, num_kv_
                 draft_vocab_size=32000, rms_norm_eps=1e-6, rope_theta=1000000.0, max_position_embeddings=40960)
 B, S, T = 8, 2048, 7
 METRIC = "EAGLE3 draft-step samples/sec (Qwen3-8B, TTT=7, seq 2048)"
-CPU_SAMPLE_TOKENS = 256
+CPU_SAMPLE_TOKENS = 128
+CPU_MAX_THREADS = 32
 
 
 def peaks():
@@ -82,7 +83,7 @@ def cpu_reference_step_rate(steps: int, warmup: int, tokens: int = CPU_SAMPLE_TO
     tokens (tokens/2048 of a sample per step)."""
     import torch
     from oracle import eagle3_oracle as O
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, CPU_MAX_THREADS)   # more threads only add oneDNN/OpenMP contention on this path
     torch.set_num_threads(cores)
     cfg = O.Eagle3Config(ttt_length=T, **{k: v for k, v in QWEN3_8B.items()})
     g = torch.Generator().manual_seed(0)
@@ -114,7 +115,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 6))
+    steps = max(1, min(args.steps, 4))
     warm = max(1, min(args.warmup, 1))
     val, ms, cores = cpu_reference_step_rate(steps, warm)
     sample = (f"1 sequence x {CPU_SAMPLE_TOKENS} tokens of the Qwen3-8B draft dims, TTT=7, fwd+bwd+AdamW, bf16 modules, "
@@ -259,10 +260,10 @@ def run_ours(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            val, ms, cores = cpu_reference_step_rate(2, 1)
+            val, ms, cores = cpu_reference_step_rate(1, 1)
             line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": f"oracle port of the reference PyTorch path, 1 sequence x {CPU_SAMPLE_TOKENS} tokens of the "
-                                              f"same dims, TTT=7, fwd+bwd+AdamW, 2 timed steps after 1 warm-up, scaled by tokens"}
+                                              f"same dims, TTT=7, fwd+bwd+AdamW, 1 timed step after 1 warm-up, scaled by tokens"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -90,18 +90,21 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
 // y = w * xhat, xhat = x * rstd.  dx = rstd * (g - xhat * mean(g * xhat)), g = w * dy.
 // dx_out = dx + add1 + add2 (optional residual-path gradients), dw[c] += sum_r dy * xhat (fp32 atomics).
 // gather mode (ids != null): x rows come from the frozen embedding table, only dw is produced.
-__global__ void __launch_bounds__(kRowThreads)
+// One block per row (looping), kChunks 16-byte chunks per thread, ONE block reduction per row
+// (sum x^2 and sum g*x together), so several blocks stay resident per SM and hide the HBM latency.
+template <int kChunks, int kThreads>
+__global__ void __launch_bounds__(kThreads)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64_t* __restrict__ ids, int S, int shift,
                    const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ dy, int64_t lddy,
                    const __nv_bfloat16* __restrict__ add1, const __nv_bfloat16* __restrict__ add2,
                    __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int64_t M, int H, float eps) {
-    __shared__ float red[32];
+    __shared__ float2 red[32];
     const int nchunks = H / 8;
-    float dwacc[kMaxChunks][8];
-    float wf[kMaxChunks][8];
+    float dwacc[kChunks][8];
+    float wf[kChunks][8];
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-        const int ch = threadIdx.x + c * kRowThreads;
+    for (int c = 0; c < kChunks; ++c) {
+        const int ch = threadIdx.x + c * kThreads;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { dwacc[c][i] = 0.f; wf[c][i] = 0.f; }
         if (ch < nchunks) {
@@ -109,6 +112,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
             wt.unpack(wf[c]);
         }
     }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t r = blockIdx.x; r < M; r += gridDim.x) {
         const __nv_bfloat16* xr;
         if (ids) {
@@ -118,47 +122,42 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
         } else {
             xr = x + r * ldx;
         }
-        float xv[kMaxChunks][8], gv[kMaxChunks][8];
-        float ss = 0.f;
+        float xv[kChunks][8], gv[kChunks][8];
+        float ss = 0.f, gx = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxChunks; ++c) {
-            const int ch = threadIdx.x + c * kRowThreads;
+        for (int c = 0; c < kChunks; ++c) {
+            const int ch = threadIdx.x + c * kThreads;
             if (ch < nchunks) {
                 bf16x8 t; t.u = __ldg(reinterpret_cast<const uint4*>(xr) + ch);
                 t.unpack(xv[c]);
                 bf16x8 d; d.u = __ldg(reinterpret_cast<const uint4*>(dy + r * lddy) + ch);
                 d.unpack(gv[c]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ss += xv[c][i] * xv[c][i];
+                for (int i = 0; i < 8; ++i) { ss += xv[c][i] * xv[c][i]; gx += gv[c][i] * wf[c][i] * xv[c][i]; }
             }
         }
-        ss = block_sum(ss, red);
+        ss = warp_sum(ss); gx = warp_sum(gx);
+        __syncthreads();
+        if (lane == 0) red[warp] = make_float2(ss, gx);
+        __syncthreads();
+        {
+            float2 t = (lane < kThreads / 32) ? red[lane] : make_float2(0.f, 0.f);
+            ss = warp_sum(t.x); gx = warp_sum(t.y);
+        }
         const float rstd = rsqrtf(ss / (float)H + eps);
-        float dot = 0.f;
+        const float mean = gx * rstd / (float)H;   // mean(g * xhat)
 #pragma unroll
-        for (int c = 0; c < kMaxChunks; ++c) {
-            const int ch = threadIdx.x + c * kRowThreads;
+        for (int c = 0; c < kChunks; ++c) {
+            const int ch = threadIdx.x + c * kThreads;
             if (ch < nchunks) {
+                float o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float xh = xv[c][i] * rstd;
                     dwacc[c][i] += gv[c][i] * bf16_round(xh);
-                    gv[c][i] *= wf[c][i];  // g = w * dy
-                    dot += gv[c][i] * xh;
-                    xv[c][i] = xh;
+                    o[i] = rstd * (gv[c][i] * wf[c][i] - xh * mean);
                 }
-            }
-        }
-        if (dx) {
-            dot = block_sum(dot, red);
-            const float mean = dot / (float)H;
-#pragma unroll
-            for (int c = 0; c < kMaxChunks; ++c) {
-                const int ch = threadIdx.x + c * kRowThreads;
-                if (ch < nchunks) {
-                    float o[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = rstd * (gv[c][i] - xv[c][i] * mean);
+                if (dx) {
                     if (add1) {
                         bf16x8 a; a.u = __ldg(reinterpret_cast<const uint4*>(add1 + r * (int64_t)H) + ch);
                         float af[8]; a.unpack(af);
@@ -178,8 +177,8 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
         }
     }
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-        const int ch = threadIdx.x + c * kRowThreads;
+    for (int c = 0; c < kChunks; ++c) {
+        const int ch = threadIdx.x + c * kThreads;
         if (ch < nchunks) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) atomicAdd(dw + ch * 8 + i, dwacc[c][i]);
@@ -323,11 +322,20 @@ int rmsnorm_bwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift
                 int64_t lddy, const void* add1, const void* add2, void* dx, float* dw, int64_t M, int H, float eps,
                 cudaStream_t st) {
     if (H % 8 || H > kRowThreads * kMaxChunks * 8) return set_error(-22, "rmsnorm: H=%d must be a multiple of 8 and <= 8192", H);
-    int blocks = 148 * 4;
-    if (blocks > M) blocks = (int)M;
-    rmsnorm_bwd_kernel<<<blocks, kRowThreads, 0, st>>>((const __nv_bfloat16*)x, ldx, ids, S, shift, (const __nv_bfloat16*)w,
-                                                      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)add1,
-                                                      (const __nv_bfloat16*)add2, (__nv_bfloat16*)dx, dw, M, H, eps);
+    const int nch = H / 8;
+#define SF_RMS_BWD(CH, TH, BPS)                                                                                        \
+    do {                                                                                                               \
+        int blocks = 148 * BPS;                                                                                        \
+        if (blocks > M) blocks = (int)M;                                                                               \
+        rmsnorm_bwd_kernel<CH, TH><<<blocks, TH, 0, st>>>((const __nv_bfloat16*)x, ldx, ids, S, shift,                 \
+            (const __nv_bfloat16*)w, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)add1,                        \
+            (const __nv_bfloat16*)add2, (__nv_bfloat16*)dx, dw, M, H, eps);                                            \
+    } while (0)
+    if (nch <= 128) SF_RMS_BWD(1, 128, 12);
+    else if (nch <= 256) SF_RMS_BWD(1, 256, 8);
+    else if (nch <= 512) SF_RMS_BWD(1, 512, 4);
+    else SF_RMS_BWD(2, 512, 3);
+#undef SF_RMS_BWD
     SF_CUDA_CHECK_LAUNCH("rmsnorm_bwd");
     return 0;
 }

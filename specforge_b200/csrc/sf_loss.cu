@@ -72,31 +72,30 @@ teacher_kernel(const __nv_bfloat16* __restrict__ tl, int64_t ld, const int* __re
     const int64_t r = blockIdx.x;
     const int b = (int)(r / S), s = (int)(r % S);
     const __nv_bfloat16* row = tl + r * ld;
-    // pass 1: max / argmax, then sum exp
+    // pass 1 (single read of the 2*V-byte row): per-thread online (max, argmax, sum exp), then a block merge
     MaxIdx mi{-INFINITY, 0x7fffffff};
+    float d = 0.f;
     const int nch = V / 8;
     for (int c = threadIdx.x; c < nch; c += blockDim.x) {
         float f[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(row) + c), f);
+        float cm = f[0]; int ci = 0;
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if (f[e] > mi.v) { mi.v = f[e]; mi.i = c * 8 + e; }
+        for (int e = 1; e < 8; ++e)
+            if (f[e] > cm) { cm = f[e]; ci = e; }
+        if (cm > mi.v) { d *= __expf(mi.v - cm); mi.v = cm; mi.i = c * 8 + ci; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d += __expf(f[e] - mi.v);
     }
     for (int e = nch * 8 + threadIdx.x; e < V; e += blockDim.x) {
         const float f = __bfloat162float(row[e]);
-        if (f > mi.v) { mi.v = f; mi.i = e; }
+        if (f > mi.v) { d *= __expf(mi.v - f); mi.v = f; mi.i = e; }
+        d += __expf(f - mi.v);
     }
+    const float my_m = mi.v;
     mi = block_argmax(mi, redv, redi);
     const float m = mi.v;
-    float d = 0.f;
-    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(row) + c), f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d += __expf(f[e] - m);
-    }
-    for (int e = nch * 8 + threadIdx.x; e < V; e += blockDim.x) d += __expf(__bfloat162float(row[e]) - m);
-    d = block_sum_f(d, redv);
+    d = block_sum_f(my_m == -INFINITY ? 0.f : d * __expf(my_m - m), redv);
     const float lse = m + logf(d);
     // pass 2: gather the draft-vocab logits
     float md = -INFINITY;
@@ -314,17 +313,38 @@ adamw_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ master, fl
              __nv_bfloat16* __restrict__ param, int64_t n, const float* __restrict__ gnorm, float max_norm, float gscale,
              float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
     const float clip = (max_norm > 0.f) ? fminf(1.0f, max_norm / (gnorm[0] + 1e-6f)) : 1.0f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float gr = __bfloat162float(__float2bfloat16_rn(__bfloat162float(g[i]) * gscale)) * clip;
-        float w = master[i];
-        w *= (1.f - lr * wd);
-        const float a = m1[i] + (gr - m1[i]) * (1.f - beta1);       // lerp_
-        const float v = m2[i] * beta2 + (1.f - beta2) * gr * gr;
-        const float denom = sqrtf(v) / bc2_sqrt + eps;
-        w -= (lr / bc1) * (a / denom);
-        m1[i] = a; m2[i] = v; master[i] = w;
-        param[i] = __float2bfloat16_rn(w);
+    const float step_size = lr / bc1, decay = 1.f - lr * wd;
+    auto upd = [&](float gr_raw, float& w, float& a, float& v) {
+        const float gr = __bfloat162float(__float2bfloat16_rn(gr_raw * gscale)) * clip;
+        w *= decay;
+        a = a + (gr - a) * (1.f - beta1);                   // lerp_
+        v = v * beta2 + (1.f - beta2) * gr * gr;
+        w -= step_size * (a / (sqrtf(v) / bc2_sqrt + eps));
+    };
+    const int64_t n4 = n / 4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 gu = __ldg(reinterpret_cast<const uint2*>(g) + i);
+        const __nv_bfloat162 g01 = *reinterpret_cast<const __nv_bfloat162*>(&gu.x);
+        const __nv_bfloat162 g23 = *reinterpret_cast<const __nv_bfloat162*>(&gu.y);
+        float4 w = reinterpret_cast<float4*>(master)[i];
+        float4 a = reinterpret_cast<float4*>(m1)[i];
+        float4 v = reinterpret_cast<float4*>(m2)[i];
+        upd(__bfloat162float(g01.x), w.x, a.x, v.x);
+        upd(__bfloat162float(g01.y), w.y, a.y, v.y);
+        upd(__bfloat162float(g23.x), w.z, a.z, v.z);
+        upd(__bfloat162float(g23.y), w.w, a.w, v.w);
+        reinterpret_cast<float4*>(master)[i] = w;
+        reinterpret_cast<float4*>(m1)[i] = a;
+        reinterpret_cast<float4*>(m2)[i] = v;
+        uint2 o; o.x = pack_bf16x2(w.x, w.y); o.y = pack_bf16x2(w.z, w.w);
+        reinterpret_cast<uint2*>(param)[i] = o;
     }
+    if (blockIdx.x == 0)
+        for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+            float w = master[i], a = m1[i], v = m2[i];
+            upd(__bfloat162float(g[i]), w, a, v);
+            master[i] = w; m1[i] = a; m2[i] = v; param[i] = __float2bfloat16_rn(w);
+        }
 }
 __global__ void __launch_bounds__(256) cvt_flat_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                                int64_t n, const float* __restrict__ scale_dev) {
