@@ -127,11 +127,13 @@ int sf_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* out, int64_t
 int sf_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const void* dy, int64_t lddy, const void* add, void* dx,
                    float* dw, int64_t M, int H, float eps, void* stream);
 /* TTT attention at step J over the fused per-step qkv buffers qkv[i] = [B*S, (nh+2nkv)*d] (RoPE already applied). */
+/* key_mask: optional [B,S] bytes (1 = attend); kvlen_ws: 2*B ints of scratch, required with key_mask. */
 int sf_ttt_attention_fwd(const void* const* qkv, int J, void* out, float* lse, float* sd_ws, const uint8_t* key_mask,
-                         int B, int S, int nh, int nkv, int head_dim, void* stream);
+                         int* kvlen_ws, int B, int S, int nh, int nkv, int head_dim, void* stream);
 int sf_ttt_attention_bwd(const void* const* qkv, int J, const void* out, const void* dout, const float* lse,
                          float* sd_ws, const uint8_t* key_mask, float* const* dk_acc, float* const* dv_acc, void* dq,
-                         float* delta_ws, float* dq_diag_ws, int B, int S, int nh, int nkv, int head_dim, void* stream);
+                         float* delta_ws, float* dq_diag_ws, int* kvlen_ws, int B, int S, int nh, int nkv, int head_dim,
+                         void* stream);
 int sf_swiglu_fwd(const void* gu, void* act, int64_t M, int I, void* stream);
 int sf_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t M, int I, void* stream);
 int sf_rope(void* x, int64_t ld, int n_heads, int head_dim, const void* cos_t, const void* sin_t, int S, int pos_offset,

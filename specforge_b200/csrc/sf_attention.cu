@@ -14,6 +14,7 @@
 // TODO(round 2): move QK^T / PV to tcgen05 with S/P in TMEM.
 #include "sf_host.h"
 #include "sf_ptx.cuh"
+#include <cstdlib>
 
 namespace sf {
 
@@ -731,9 +732,49 @@ static void fill(AttnParams& p, const AttnDesc& a) {
     p.dk0_acc = a.dk_acc[0]; p.dv0_acc = a.dv_acc[0]; p.ldacc = a.ldacc;
     p.dq = (__nv_bfloat16*)a.dq; p.lddq = a.lddq; p.dq_diag = (a.J > 0) ? a.dq_diag_ws : nullptr;
 }
+// kvlen[b] = number of leading 1s of key_mask[b, :]; nonprefix[b] = 1 if a 1 follows a 0 (one warp per row)
+__global__ void mask_prefix_kernel(const uint8_t* __restrict__ key_mask, int B, int S, int* __restrict__ kvlen,
+                                   int* __restrict__ nonprefix) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    int first_zero = S, last_one = -1;
+    for (int s = lane; s < S; s += 32) {
+        if (key_mask[(int64_t)b * S + s]) last_one = max(last_one, s);
+        else first_zero = min(first_zero, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        first_zero = min(first_zero, __shfl_xor_sync(0xffffffffu, first_zero, o));
+        last_one = max(last_one, __shfl_xor_sync(0xffffffffu, last_one, o));
+    }
+    if (lane == 0) { kvlen[b] = first_zero; nonprefix[b] = last_one > first_zero ? 1 : 0; }
+}
+int mask_prefix(const uint8_t* key_mask, int B, int S, int* kvlen, int* nonprefix, cudaStream_t st) {
+    mask_prefix_kernel<<<(B + 7) / 8, 256, 0, st>>>(key_mask, B, S, kvlen, nonprefix);
+    SF_CUDA_CHECK_LAUNCH("mask_prefix");
+    return 0;
+}
+
+static bool use_legacy_attention() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SF_ATTN_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int attn_fwd(const AttnDesc& a, cudaStream_t st) {
     if (int rc = attn_validate(a)) return rc;
+    if (a.key_mask && !a.kvlen) return set_error(-22, "attention: key_mask given without kvlen/nonprefix (call mask_prefix)");
     AttnParams p; fill(p, a);
+    if (!use_legacy_attention()) {
+        // diagonal scores by the row kernel, block 0 on tcgen05
+        if (p.J > 0) {
+            const int64_t warps = (int64_t)p.B * p.S * p.nh;
+            if (a.head_dim == 128) diag_scores_kernel<128><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+            else diag_scores_kernel<64><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+            SF_CUDA_CHECK_LAUNCH("diag_scores");
+        }
+        return attn_fwd_tc(a, st);
+    }
     return a.head_dim == 128 ? attn_fwd_t<128>(p, st) : attn_fwd_t<64>(p, st);
 }
 int attn_bwd(const AttnDesc& a, cudaStream_t st) {

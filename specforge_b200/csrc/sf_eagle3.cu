@@ -60,7 +60,7 @@ static void layout(const sf_eagle3_config& c, int64_t* off, int64_t* sz, int64_t
 struct Plan {
     // persistent forward -> backward
     int64_t h, xcat, qkv, attn, lse, hmid, hn2, gu, act, hf, logits;
-    int64_t target_p, pod, ids, pos_mask, loss_mask32, key_mask, d2t_idx, row_ws, sd_ws, metrics, misc;
+    int64_t target_p, pod, ids, pos_mask, loss_mask32, key_mask, kvlen, d2t_idx, row_ws, sd_ws, metrics, misc;
     // union region: forward temporaries / backward buffers
     int64_t u_base;
     int64_t tgt_shift, tlogits;                       // forward temporaries
@@ -90,6 +90,7 @@ static Plan make_plan(const sf_eagle3_config& c) {
     p.pos_mask = take(M * 4);
     p.loss_mask32 = take(M * 4);
     p.key_mask = take(M);
+    p.kvlen = take(2 * (int64_t)x.B * 4 + 64);
     p.d2t_idx = take((int64_t)x.DV * 4);
     p.row_ws = take(3 * M * 4);
     p.sd_ws = take((int64_t)x.B * x.nh * x.S * (T > 1 ? T - 1 : 1) * 4);
@@ -190,6 +191,7 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
     // ---- fc: h_0 = hidden_state W_fc^T   (llama3_eagle.py:1762-1770)
     SF_TRY(mm(c, bt.hidden_state, 3 * x.Ht, MAJOR_K, c.W[SF_P_FC], 3 * x.Ht, MAJOR_K, c.bf(p.h), x.H, nullptr, 0, M, x.H, 3 * x.Ht, EPI_BF16));
     const uint8_t* key_mask = bt.attention_mask ? c.at<uint8_t>(p.key_mask) : nullptr;
+    if (key_mask) SF_TRY(mask_prefix(key_mask, x.B, x.S, c.at<int>(p.kvlen), c.at<int>(p.kvlen) + x.B, st));
     for (int j = 0; j < T; ++j) {
         __nv_bfloat16* h_in = c.bf(p.h, (int64_t)j * M * x.H);
         __nv_bfloat16* h_out = c.bf(p.h, (int64_t)(j + 1) * M * x.H);
@@ -213,6 +215,8 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         AttnDesc a{};
         a.q = qkv; a.ldq = x.QKV; a.ldkv = x.QKV; a.out = attn; a.ldo = x.A; a.lse = lse; a.sd_ws = c.at<float>(p.sd_ws);
         a.key_mask = key_mask; a.B = x.B; a.S = x.S; a.nh = x.nh; a.nkv = x.nkv; a.head_dim = x.d; a.J = j;
+        a.kvlen = key_mask ? c.at<int>(p.kvlen) : nullptr; a.nonprefix = key_mask ? c.at<int>(p.kvlen) + x.B : nullptr;
+        a.q_row_base = qkv; a.kv_row_base = c.bf(p.qkv); a.q_col0 = 0; a.k_col0 = (int)x.A; a.v_col0 = (int)(x.A + x.KV);
         for (int i = 0; i <= j; ++i) {
             const __nv_bfloat16* qi = c.bf(p.qkv, (int64_t)i * M * x.QKV);
             a.k[i] = qi + x.A; a.v[i] = qi + x.A + x.KV;
@@ -299,6 +303,8 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
         a.q = qkv; a.ldq = x.QKV; a.ldkv = x.QKV; a.out = const_cast<__nv_bfloat16*>(attn); a.ldo = x.A;
         a.lse = const_cast<float*>(lse); a.sd_ws = c.at<float>(p.sd_ws);
         a.key_mask = key_mask; a.B = x.B; a.S = x.S; a.nh = x.nh; a.nkv = x.nkv; a.head_dim = x.d; a.J = j;
+        a.kvlen = key_mask ? c.at<int>(p.kvlen) : nullptr; a.nonprefix = key_mask ? c.at<int>(p.kvlen) + x.B : nullptr;
+        a.q_row_base = qkv; a.kv_row_base = c.bf(p.qkv); a.q_col0 = 0; a.k_col0 = (int)x.A; a.v_col0 = (int)(x.A + x.KV);
         a.dout = d_attn; a.lddo = x.A; a.delta_ws = c.at<float>(p.delta); a.ldacc = x.KV;
         a.dq = dqkv; a.lddq = x.QKV; a.dq_diag_ws = c.at<float>(p.dq_diag);
         for (int i = 0; i <= j; ++i) {
@@ -404,26 +410,37 @@ extern "C" int sf_rope(void* x, int64_t ld, int n_heads, int head_dim, const voi
 static void fill_attn(AttnDesc& a, const void* const* qkv, int J, int B, int S, int nh, int nkv, int d) {
     const int64_t A = (int64_t)nh * d, KV = (int64_t)nkv * d, QKV = A + 2 * KV;
     a.q = qkv[J]; a.ldq = QKV; a.ldkv = QKV; a.ldo = A; a.B = B; a.S = S; a.nh = nh; a.nkv = nkv; a.head_dim = d; a.J = J;
+    a.q_row_base = qkv[J]; a.kv_row_base = qkv[0]; a.q_col0 = 0; a.k_col0 = (int)A; a.v_col0 = (int)(A + KV);
     for (int i = 0; i <= J; ++i) {
         const __nv_bfloat16* qi = reinterpret_cast<const __nv_bfloat16*>(qkv[i]);
         a.k[i] = qi + A; a.v[i] = qi + A + KV;
     }
 }
 extern "C" int sf_ttt_attention_fwd(const void* const* qkv, int J, void* out, float* lse, float* sd_ws, const uint8_t* key_mask,
-                                    int B, int S, int nh, int nkv, int head_dim, void* stream) {
+                                    int* kvlen_ws, int B, int S, int nh, int nkv, int head_dim, void* stream) {
     if (J < 0 || J > 8) return set_error(-22, "attention: J=%d outside [0, 8]", J);
     AttnDesc a{};
     fill_attn(a, qkv, J, B, S, nh, nkv, head_dim);
     a.out = out; a.lse = lse; a.sd_ws = sd_ws; a.key_mask = key_mask;
+    if (key_mask) {
+        if (!kvlen_ws) return set_error(-22, "attention: key_mask needs kvlen_ws (2*B ints)");
+        SF_TRY(mask_prefix(key_mask, B, S, kvlen_ws, kvlen_ws + B, reinterpret_cast<cudaStream_t>(stream)));
+        a.kvlen = kvlen_ws; a.nonprefix = kvlen_ws + B;
+    }
     return attn_fwd(a, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int sf_ttt_attention_bwd(const void* const* qkv, int J, const void* out, const void* dout, const float* lse,
                                     float* sd_ws, const uint8_t* key_mask, float* const* dk_acc, float* const* dv_acc,
-                                    void* dq, float* delta_ws, float* dq_diag_ws, int B, int S, int nh, int nkv, int head_dim,
-                                    void* stream) {
+                                    void* dq, float* delta_ws, float* dq_diag_ws, int* kvlen_ws, int B, int S, int nh, int nkv,
+                                    int head_dim, void* stream) {
     if (J < 0 || J > 8) return set_error(-22, "attention: J=%d outside [0, 8]", J);
     AttnDesc a{};
     fill_attn(a, qkv, J, B, S, nh, nkv, head_dim);
+    if (key_mask) {
+        if (!kvlen_ws) return set_error(-22, "attention: key_mask needs kvlen_ws (2*B ints)");
+        SF_TRY(mask_prefix(key_mask, B, S, kvlen_ws, kvlen_ws + B, reinterpret_cast<cudaStream_t>(stream)));
+        a.kvlen = kvlen_ws; a.nonprefix = kvlen_ws + B;
+    }
     a.out = const_cast<void*>(out); a.lse = const_cast<float*>(lse); a.sd_ws = sd_ws; a.key_mask = key_mask;
     a.dout = dout; a.lddo = (int64_t)nh * head_dim; a.delta_ws = delta_ws; a.ldacc = (int64_t)nkv * head_dim;
     for (int i = 0; i <= J; ++i) { a.dk_acc[i] = dk_acc[i]; a.dv_acc[i] = dv_acc[i]; }

@@ -29,6 +29,11 @@ struct AttnDesc {
     float* lse;                 // [B, nh, S]
     float* sd_ws;               // [B, nh, S, J] workspace (diagonal scores)
     const uint8_t* key_mask;    // [B, S] or null
+    const int* kvlen;           // [B] leading valid keys (required with key_mask), see mask_prefix()
+    const int* nonprefix;       // [B] 1 if that row's mask is not of prefix form
+    const void* q_row_base;     // base of the fused rows holding q (column q_col0 + h*d); tcgen05 path uses TMA on it
+    const void* kv_row_base;    // base of the fused rows holding block-0 k / v
+    int q_col0, k_col0, v_col0;
     int B, S, nh, nkv, head_dim, J;
     // backward only
     const void* dout; int64_t lddo;
@@ -38,6 +43,9 @@ struct AttnDesc {
     float* dq_diag_ws;          // [B*S, nh*D] fp32 workspace
 };
 int attn_fwd(const AttnDesc& a, cudaStream_t st);
+int attn_fwd_tc(const AttnDesc& a, cudaStream_t st);
+int mask_prefix(const uint8_t* key_mask, int B, int S, int* kvlen, int* nonprefix, cudaStream_t st);
+#define SF_TRY_RC(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
 int attn_bwd(const AttnDesc& a, cudaStream_t st);
 
 int rmsnorm_fwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift, const void* w, void* out, int64_t ldo,

@@ -52,12 +52,12 @@ def _declare_ops():
     l.sf_rope.restype = c_int
     l.sf_rope.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]
     l.sf_ttt_attention_fwd.restype = c_int
-    l.sf_ttt_attention_fwd.argtypes = [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                       c_int, c_int, c_void_p]
+    l.sf_ttt_attention_fwd.argtypes = [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                       c_int, c_int, c_int, c_void_p]
     l.sf_ttt_attention_bwd.restype = c_int
     l.sf_ttt_attention_bwd.argtypes = [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                       POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                       c_int, c_int, c_int, c_void_p]
+                                       POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                       c_int, c_int, c_int, c_int, c_void_p]
     l._sf_ops_declared = True
     return l
 
@@ -116,8 +116,9 @@ def ttt_attention_fwd(qkv_list, B, S, nh, nkv, hd, key_mask=None):
     out = torch.empty(B * S, nh * hd, dtype=torch.bfloat16, device=dev)
     lse = torch.empty(B, nh, S, dtype=torch.float32, device=dev)
     sd = torch.empty(B * nh * S * max(J, 1), dtype=torch.float32, device=dev)
-    check(l.sf_ttt_attention_fwd(_ptr_array(qkv_list), J, out.data_ptr(), lse.data_ptr(), sd.data_ptr(), _ptr(key_mask), B, S,
-                                 nh, nkv, hd, _stream()), "sf_ttt_attention_fwd")
+    kvl = torch.zeros(2 * B, dtype=torch.int32, device=dev)
+    check(l.sf_ttt_attention_fwd(_ptr_array(qkv_list), J, out.data_ptr(), lse.data_ptr(), sd.data_ptr(), _ptr(key_mask),
+                                 kvl.data_ptr(), B, S, nh, nkv, hd, _stream()), "sf_ttt_attention_fwd")
     return out, lse
 
 
@@ -131,7 +132,8 @@ def ttt_attention_bwd(qkv_list, out, dout, lse, B, S, nh, nkv, hd, key_mask=None
     sd = torch.empty(B * nh * S * max(J, 1), dtype=torch.float32, device=dev)
     delta = torch.empty(B * nh * S, dtype=torch.float32, device=dev)
     dqd = torch.empty(B * S, nh * hd, dtype=torch.float32, device=dev)
+    kvl = torch.zeros(2 * B, dtype=torch.int32, device=dev)
     check(l.sf_ttt_attention_bwd(_ptr_array(qkv_list), J, out.data_ptr(), dout.data_ptr(), lse.data_ptr(), sd.data_ptr(),
                                  _ptr(key_mask), _ptr_array(dk), _ptr_array(dv), dq.data_ptr(), delta.data_ptr(),
-                                 dqd.data_ptr(), B, S, nh, nkv, hd, _stream()), "sf_ttt_attention_bwd")
+                                 dqd.data_ptr(), kvl.data_ptr(), B, S, nh, nkv, hd, _stream()), "sf_ttt_attention_bwd")
     return dq, dk, dv
