@@ -777,9 +777,30 @@ int attn_fwd(const AttnDesc& a, cudaStream_t st) {
     }
     return a.head_dim == 128 ? attn_fwd_t<128>(p, st) : attn_fwd_t<64>(p, st);
 }
+template <int D>
+static int attn_bwd_prep_t(AttnParams& p, cudaStream_t st) {
+    {
+        const int64_t warps = (int64_t)p.B * p.S * p.nh;
+        attn_delta_kernel<D><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+        SF_CUDA_CHECK_LAUNCH("attn_delta");
+    }
+    if (p.J > 0) {
+        const int64_t warps = (int64_t)p.B * p.S * p.nkv;
+        attn_bwd_diag_kernel<D><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+        SF_CUDA_CHECK_LAUNCH("attn_bwd_diag");
+    }
+    return 0;
+}
+
 int attn_bwd(const AttnDesc& a, cudaStream_t st) {
     if (int rc = attn_validate(a)) return rc;
+    if (a.key_mask && !a.kvlen) return set_error(-22, "attention: key_mask given without kvlen/nonprefix (call mask_prefix)");
     AttnParams p; fill(p, a);
+    if (!use_legacy_attention()) {
+        // delta + diagonal terms by row kernels, block 0 (dK/dV and dQ) on tcgen05
+        if (int rc = (a.head_dim == 128 ? attn_bwd_prep_t<128>(p, st) : attn_bwd_prep_t<64>(p, st))) return rc;
+        return attn_bwd_tc(a, st);
+    }
     return a.head_dim == 128 ? attn_bwd_t<128>(p, st) : attn_bwd_t<64>(p, st);
 }
 

@@ -53,13 +53,18 @@ struct FwdCfg {
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = 2 * Q_BYTES;
     static constexpr int OFF_V = OFF_K + kStages * KV_BYTES;
-    static constexpr int OFF_P = OFF_V + kStages * KV_BYTES;
-    static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-    static constexpr int SMEM = OFF_BAR + 256 + 1024;
-    static constexpr int TM_S = 0;            // S_a at col 0, S_b at col 64
-    static constexpr int TM_O = 128;          // O_a at 128, O_b at 128 + D
+    static constexpr int OFF_P = OFF_V + kStages * KV_BYTES;   // [head][buf]
+    static constexpr int OFF_BAR = OFF_P + 4 * P_BYTES;
+    static constexpr int SMEM = OFF_BAR + 512 + 1024;
+    static constexpr int TM_S = 0;            // S[head][buf] at col (head*2+buf)*64
+    static constexpr int TM_O = 256;          // O[head] at 256 + head*D  (accumulated across kv tiles)
+    static constexpr float kRescaleThreshold = 8.0f;   // log2 units: P stays <= 2^8 between lazy rescales
 };
 
+// Forward.  O accumulates in TMEM across the kv tiles (PV MMAs with accumulate); the softmax threads keep a
+// *reference* max m_ref and only rescale O / l when the running max exceeds it by > 2^8 (exact: softmax is
+// shift invariant, the final division by l uses the same reference) — the per-tile TMEM round trip of O is gone.
+// S and P are double-buffered per head so the MMA issuer computes S(t+1) while the warpgroup exponentiates S(t).
 template <int D>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const AttnTcParams p) {
@@ -68,18 +73,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t bar0 = sbase + C::OFF_BAR;
-    // barrier map
     const uint32_t b_qfull = bar0;
     auto b_kfull = [&](int s) { return bar0 + 8u * (1 + s); };
     auto b_kempty = [&](int s) { return bar0 + 8u * (3 + s); };
     auto b_vfull = [&](int s) { return bar0 + 8u * (5 + s); };
     auto b_vempty = [&](int s) { return bar0 + 8u * (7 + s); };
-    auto b_sfull = [&](int x) { return bar0 + 8u * (9 + x); };
-    auto b_pfull = [&](int x) { return bar0 + 8u * (11 + x); };
-    auto b_pempty = [&](int x) { return bar0 + 8u * (13 + x); };
-    auto b_ofull = [&](int x) { return bar0 + 8u * (15 + x); };
-    auto b_oempty = [&](int x) { return bar0 + 8u * (17 + x); };
-    const uint32_t tmem_slot = bar0 + 8u * 19;
+    auto b_sfull = [&](int x, int u) { return bar0 + 8u * (9 + x * 2 + u); };
+    auto b_pfull = [&](int x, int u) { return bar0 + 8u * (13 + x * 2 + u); };
+    auto b_pvdone = [&](int x, int u) { return bar0 + 8u * (17 + x * 2 + u); };
+    const uint32_t tmem_slot = bar0 + 8u * 21;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = gridDim.x - 1 - blockIdx.x;
@@ -98,17 +100,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     if (warp == 1 && lane == 0) {
         mbar_init(b_qfull, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(b_kfull(s), 1); mbar_init(b_kempty(s), 1); mbar_init(b_vfull(s), 1); mbar_init(b_vempty(s), 1); }
-        for (int x = 0; x < 2; ++x) {
-            mbar_init(b_sfull(x), 1); mbar_init(b_pfull(x), 4); mbar_init(b_pempty(x), 1);
-            mbar_init(b_ofull(x), 1); mbar_init(b_oempty(x), 4);
-        }
+        for (int x = 0; x < 2; ++x)
+            for (int u = 0; u < 2; ++u) { mbar_init(b_sfull(x, u), 1); mbar_init(b_pfull(x, u), 4); mbar_init(b_pvdone(x, u), 1); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 19);
+    const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 21);
 
     if (warp < 4) {
         reg_dec<40>();
@@ -136,49 +136,49 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         } else if (warp == 1 && lane == 0) {
             // ================= MMA issuer =================
             constexpr uint32_t idesc_s = make_idesc_bf16(128, C::BKV, 0, 0);   // S[128 x 64]  = Q(K-major) K^T(K-major)
-            constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O[128 x D]   = P(K-major) V(MN-major)
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O[128 x D]  += P(K-major) V(MN-major)
+            auto issue_s = [&](int t) {
+                const int s = t & 1, u = t & 1;
+                mbar_wait(b_kfull(s), (t >> 1) & 1, 17);
+                tc_fence_after();
+                const uint32_t sk = sbase + C::OFF_K + s * C::KV_BYTES;
+                for (int x = 0; x < nx; ++x) {
+                    // S buffer u of head x was last read by softmax(t-2): its p_full was awaited before PV(t-2)
+                    const uint32_t sq = sbase + C::OFF_Q + x * C::Q_BYTES;
+#pragma unroll
+                    for (int kb = 0; kb < C::NB; ++kb) {
+                        const uint64_t adesc = make_smem_desc_sw128(sq + kb * (C::BQ * 128), 0, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(sk + kb * (C::BKV * 128), 0, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16<1>(tmem + C::TM_S + (x * 2 + u) * C::BKV, adesc + ((k * 32) >> 4), bdesc + ((k * 32) >> 4),
+                                         idesc_s, (kb | k) != 0);
+                    }
+                    umma_commit(b_sfull(x, u));
+                }
+                umma_commit(b_kempty(s));
+            };
             mbar_wait(b_qfull, 0, 13);
             tc_fence_after();
-            for (int t = 0; t <= n_kv; ++t) {
+            issue_s(0);
+            for (int t = 0; t < n_kv; ++t) {
+                if (t + 1 < n_kv) issue_s(t + 1);
+                const int s = t & 1, u = t & 1;
+                mbar_wait(b_vfull(s), (t >> 1) & 1, 15);
+                const uint32_t sv = sbase + C::OFF_V + s * C::KV_BYTES;
                 for (int x = 0; x < nx; ++x) {
-                    if (t >= 1) {
-                        // O_tile_x = P_x(t-1) V_{t-1}
-                        const int u = t - 1, s = u & 1;
-                        mbar_wait(b_pfull(x), u & 1, 14);
-                        if (x == 0) mbar_wait(b_vfull(s), (u >> 1) & 1, 15);
-                        mbar_wait(b_oempty(x), (u & 1) ^ 1u, 16);
-                        tc_fence_after();
-                        const uint32_t sp = sbase + C::OFF_P + x * C::P_BYTES;
-                        const uint32_t sv = sbase + C::OFF_V + s * C::KV_BYTES;
-                        const uint64_t adesc = make_smem_desc_sw128(sp, 0, 1024);
-                        const uint64_t bdesc = make_smem_desc_sw128(sv, C::BKV * 128, 1024);   // MN-major: LBO = 64-col block stride
+                    mbar_wait(b_pfull(x, u), (t >> 1) & 1, 14);
+                    tc_fence_after();
+                    const uint32_t sp = sbase + C::OFF_P + (x * 2 + u) * C::P_BYTES;
+                    const uint64_t adesc = make_smem_desc_sw128(sp, 0, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(sv, C::BKV * 128, 1024);   // MN-major: LBO = 64-col block stride
 #pragma unroll
-                        for (int k = 0; k < C::BKV / 16; ++k)
-                            umma_bf16<1>(tmem + C::TM_O + x * D, adesc + ((k * 32) >> 4), bdesc + ((k * 2048) >> 4), idesc_o, k != 0);
-                        umma_commit(b_ofull(x));
-                        umma_commit(b_pempty(x));
-                        if (x == nx - 1) umma_commit(b_vempty(s));
-                    }
-                    if (t < n_kv) {
-                        // S_x = Q_x K_t^T   (S_x(t-1) has been fully read: p_full[x](t-1) was awaited above)
-                        const int s = t & 1;
-                        if (x == 0) mbar_wait(b_kfull(s), (t >> 1) & 1, 17);
-                        tc_fence_after();
-                        const uint32_t sq = sbase + C::OFF_Q + x * C::Q_BYTES;
-                        const uint32_t sk = sbase + C::OFF_K + s * C::KV_BYTES;
-#pragma unroll
-                        for (int kb = 0; kb < C::NB; ++kb) {
-                            const uint64_t adesc = make_smem_desc_sw128(sq + kb * (C::BQ * 128), 0, 1024);
-                            const uint64_t bdesc = make_smem_desc_sw128(sk + kb * (C::BKV * 128), 0, 1024);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16<1>(tmem + C::TM_S + x * C::BKV, adesc + ((k * 32) >> 4), bdesc + ((k * 32) >> 4), idesc_s,
-                                             (kb | k) != 0);
-                        }
-                        umma_commit(b_sfull(x));
-                        if (x == nx - 1) umma_commit(b_kempty(s));
-                    }
+                    for (int k = 0; k < C::BKV / 16; ++k)
+                        umma_bf16<1>(tmem + C::TM_O + x * D, adesc + ((k * 32) >> 4), bdesc + ((k * 2048) >> 4), idesc_o,
+                                     (t | k) != 0);
+                    umma_commit(b_pvdone(x, u));
                 }
+                umma_commit(b_vempty(s));
             }
         }
     } else {
@@ -192,112 +192,123 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             const int row = q0 + r;
             const bool row_ok = row < p.S;
             const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
-            float m = -INFINITY, l = 0.f;
+            const uint32_t t_o = t_lane + C::TM_O + x * D;
+            float m_ref = -INFINITY, l = 0.f;
             const float* sdr = nullptr;
             if (p.J > 0) {
                 sdr = p.sd + (((int64_t)b * p.nh + h) * p.S + min(row, p.S - 1)) * p.J;
-                for (int i = 0; i < p.J; ++i) m = fmaxf(m, sdr[i]);
-                for (int i = 0; i < p.J; ++i) l += exp2f(sdr[i] - m);
+                for (int i = 0; i < p.J; ++i) m_ref = fmaxf(m_ref, sdr[i]);
+                for (int i = 0; i < p.J; ++i) l += exp2f(sdr[i] - m_ref);
             }
-            float o[D];
-#pragma unroll
-            for (int i = 0; i < D; ++i) o[i] = 0.f;
-            float alpha_prev = 1.f;
-            uint8_t* sp = sgen + C::OFF_P + x * C::P_BYTES;
-
-            auto accumulate_o = [&](int u) {
-                mbar_wait(b_ofull(x), u & 1, 20 + x);
-                tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < D / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_lane + C::TM_O + x * D + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) o[c * 32 + e] = o[c * 32 + e] * alpha_prev + __uint_as_float(v[e]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(b_oempty(x));
-            };
-
+            const float c = p.scale_log2;
             for (int t = 0; t < n_kv; ++t) {
+                const int u = t & 1;
                 const int kv0 = t * C::BKV;
                 const bool need_mask = (kv0 + C::BKV - 1 > q0 + wq * 32) || (kv0 + C::BKV > kvlen) || general_mask;
-                mbar_wait(b_sfull(x), t & 1, 22 + x);
+                mbar_wait(b_sfull(x, u), (t >> 1) & 1, 22 + x);
                 tc_fence_after();
                 uint32_t sv[C::BKV];
-                tmem_ld_32x32b_x32(t_lane + C::TM_S + x * C::BKV, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-                tmem_ld_32x32b_x32(t_lane + C::TM_S + x * C::BKV + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+                tmem_ld_32x32b_x32(t_lane + C::TM_S + (x * 2 + u) * C::BKV, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+                tmem_ld_32x32b_x32(t_lane + C::TM_S + (x * 2 + u) * C::BKV + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
                 tmem_ld_wait();
-                float mx = m;
+                float mx = -INFINITY;
+                if (need_mask) {
 #pragma unroll
-                for (int c = 0; c < C::BKV; ++c) {
-                    float v = __uint_as_float(sv[c]) * p.scale_log2;
-                    if (need_mask) {
-                        const int key = kv0 + c;
+                    for (int cc = 0; cc < C::BKV; ++cc) {
+                        const int key = kv0 + cc;
                         bool ok = key <= row && key < kvlen;
                         if (ok && general_mask) ok = p.key_mask[(int64_t)b * p.S + key] != 0;
-                        if (!ok) v = -INFINITY;
+                        if (!ok) sv[cc] = 0xff800000u;   // -inf
                     }
-                    sv[c] = __float_as_uint(v);
-                    mx = fmaxf(mx, v);
                 }
-                const float base = (mx == -INFINITY) ? 0.f : mx;
-                const float alpha = exp2f(m - base);
-                m = mx;
-                // P tile buffer must have been consumed by PV(t-1)
-                mbar_wait(b_pempty(x), (t & 1) ^ 1u, 24 + x);
+#pragma unroll
+                for (int cc = 0; cc < C::BKV; ++cc) mx = fmaxf(mx, __uint_as_float(sv[cc]));
+                mx *= c;                                   // c > 0
+                // ---- lazy rescale (warp-collective TMEM round trip only when some row's max jumped by > 2^8)
+                const bool jump = mx > m_ref + C::kRescaleThreshold;   // also true when m_ref == -inf and mx finite
+                if (__any_sync(0xffffffffu, jump)) {
+                    const float m_new = jump ? mx : m_ref;
+                    const float f = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);   // jump==false -> 1
+                    l *= f;
+                    m_ref = m_new;
+                    if (t > 0) {
+                        // O holds tiles < t: PV(t-1) must have landed before it is rescaled
+                        mbar_wait(b_pvdone(x, (t - 1) & 1), ((t - 1) >> 1) & 1, 26 + x);
+                        tc_fence_after();
+#pragma unroll
+                        for (int cc = 0; cc < D / 32; ++cc) {
+                            uint32_t v[32];
+                            tmem_ld_32x32b_x32(t_o + cc * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
+                            tmem_st_32x32b_x32(t_o + cc * 32, v);
+                        }
+                        tmem_st_wait();
+                    }
+                }
+                const float base = (m_ref == -INFINITY) ? 0.f : m_ref;
+                // P buffer u must have been consumed by PV(t-2)
+                mbar_wait(b_pvdone(x, u), ((t >> 1) & 1) ^ 1u, 24 + x);
+                uint8_t* sp = sgen + C::OFF_P + (x * 2 + u) * C::P_BYTES;
                 float rs = 0.f;
 #pragma unroll
                 for (int j = 0; j < C::BKV / 8; ++j) {
                     float e[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { e[k] = exp2f(__uint_as_float(sv[j * 8 + k]) - base); rs += e[k]; }
+                    for (int k = 0; k < 8; ++k) { e[k] = ex2_approx(fmaf(__uint_as_float(sv[j * 8 + k]), c, -base)); rs += e[k]; }
                     uint4 pk;
                     pk.x = pack_bf16x2(e[0], e[1]); pk.y = pack_bf16x2(e[2], e[3]);
                     pk.z = pack_bf16x2(e[4], e[5]); pk.w = pack_bf16x2(e[6], e[7]);
                     *reinterpret_cast<uint4*>(sp + sw128(r, j)) = pk;
                 }
-                l = l * alpha + rs;
+                l += rs;
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(b_pfull(x));
-                if (t >= 1) accumulate_o(t - 1);
-                alpha_prev = alpha;
+                if (lane == 0) mbar_arrive(b_pfull(x, u));
             }
-            accumulate_o(n_kv - 1);
-            // ---- epilogue: diagonal P*V terms (never masked), normalise, store
-            if (row_ok) {
-                for (int i = 0; i < p.J; ++i) {
-                    const float w = exp2f(sdr[i] - m);
-                    const uint4* vp = reinterpret_cast<const uint4*>(p.vdiag[i] + ((int64_t)b * p.S + row) * p.ldkv + kvh * D);
+            // ---- epilogue: O from TMEM, diagonal P*V terms (never masked), normalise, store
+            mbar_wait(b_pvdone(x, (n_kv - 1) & 1), ((n_kv - 1) >> 1) & 1, 28 + x);
+            tc_fence_after();
+            const float inv = (l > 0.f) ? 1.f / l : 0.f;
+            __nv_bfloat16* orow = p.out + ((int64_t)b * p.S + min(row, p.S - 1)) * p.ldo + h * D;
 #pragma unroll
-                    for (int c = 0; c < D / 8; ++c) {
-                        const uint4 u = __ldg(vp + c);
-                        const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+            for (int cc = 0; cc < D / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_o + cc * 32, v);
+                tmem_ld_wait();
+                float o[32];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(&wds[e]);
-                            o[c * 8 + 2 * e] += w * __bfloat162float(bb.x);
-                            o[c * 8 + 2 * e + 1] += w * __bfloat162float(bb.y);
+                for (int e = 0; e < 32; ++e) o[e] = __uint_as_float(v[e]);
+                if (row_ok) {
+                    for (int i = 0; i < p.J; ++i) {
+                        const float w = exp2f(sdr[i] - m_ref);
+                        const uint4* vp = reinterpret_cast<const uint4*>(p.vdiag[i] + ((int64_t)b * p.S + row) * p.ldkv + kvh * D + cc * 32);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 uu = __ldg(vp + q);
+                            const uint32_t wds[4] = {uu.x, uu.y, uu.z, uu.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(&wds[e]);
+                                o[q * 8 + 2 * e] += w * __bfloat162float(bb.x);
+                                o[q * 8 + 2 * e + 1] += w * __bfloat162float(bb.y);
+                            }
                         }
                     }
-                }
-                const float inv = (l > 0.f) ? 1.f / l : 0.f;
-                uint4* op = reinterpret_cast<uint4*>(p.out + ((int64_t)b * p.S + row) * p.ldo + h * D);
 #pragma unroll
-                for (int c = 0; c < D / 8; ++c) {
-                    uint4 u;
-                    u.x = pack_bf16x2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
-                    u.y = pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
-                    u.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
-                    u.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
-                    op[c] = u;
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 uu;
+                        uu.x = pack_bf16x2(o[q * 8 + 0] * inv, o[q * 8 + 1] * inv);
+                        uu.y = pack_bf16x2(o[q * 8 + 2] * inv, o[q * 8 + 3] * inv);
+                        uu.z = pack_bf16x2(o[q * 8 + 4] * inv, o[q * 8 + 5] * inv);
+                        uu.w = pack_bf16x2(o[q * 8 + 6] * inv, o[q * 8 + 7] * inv);
+                        reinterpret_cast<uint4*>(orow + cc * 32)[q] = uu;
+                    }
                 }
-                p.lse[((int64_t)b * p.nh + h) * p.S + row] = m + log2f(l);
             }
+            if (row_ok) p.lse[((int64_t)b * p.nh + h) * p.S + row] = m_ref + log2f(l);
         }
     }
     __syncwarp();

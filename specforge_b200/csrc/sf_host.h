@@ -44,6 +44,7 @@ struct AttnDesc {
 };
 int attn_fwd(const AttnDesc& a, cudaStream_t st);
 int attn_fwd_tc(const AttnDesc& a, cudaStream_t st);
+int attn_bwd_tc(const AttnDesc& a, cudaStream_t st);
 int mask_prefix(const uint8_t* key_mask, int B, int S, int* kvlen, int* nonprefix, cudaStream_t st);
 #define SF_TRY_RC(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
 int attn_bwd(const AttnDesc& a, cudaStream_t st);
