@@ -41,13 +41,14 @@ struct DkvCfg {
     static constexpr int OFF_Q = 2 * KT_BYTES;             // [stage] Q then dO
     static constexpr int OFF_P = OFF_Q + kStages * 2 * QT_BYTES;
     static constexpr int OFF_DS = OFF_P + PT_BYTES;
-    static constexpr int OFF_BAR = OFF_DS + PT_BYTES;
+    static constexpr int OFF_LD = OFF_DS + PT_BYTES;       // [2 buffers][L(64) | delta(64)] floats
+    static constexpr int OFF_BAR = OFF_LD + 2 * 2 * BQ * 4;
     static constexpr int SMEM = OFF_BAR + 256 + 1024;
     static constexpr int TM_ST = 0, TM_DP = 128, TM_DV = 256, TM_DK = 256 + D;   // S^T[2], dP^T[2] double-buffered
 };
 
 template <int D>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                        const __grid_constant__ CUtensorMap tm_kv, const AttnBwdTcParams p) {
     using C = DkvCfg<D>;
@@ -62,6 +63,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t b_pdsfull = bar0 + 8u * 9;
     const uint32_t b_mmadone = bar0 + 8u * 10;
     const uint32_t tmem_slot = bar0 + 8u * 11;
+    auto b_ldfull = [&](int u) { return bar0 + 8u * (12 + u); };
+    auto b_ldempty = [&](int u) { return bar0 + 8u * (14 + u); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -80,8 +83,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     if (warp == 1 && lane == 0) {
         mbar_init(b_kvfull, 1);
         for (int s = 0; s < C::kStages; ++s) { mbar_init(b_qfull(s), 1); mbar_init(b_qempty(s), 1); }
-        for (int u = 0; u < 2; ++u) mbar_init(b_sdpfull(u), 1);
-        mbar_init(b_pdsfull, 4);
+        for (int u = 0; u < 2; ++u) { mbar_init(b_sdpfull(u), 1); mbar_init(b_ldfull(u), 1); mbar_init(b_ldempty(u), 8); }
+        mbar_init(b_pdsfull, 8);
         mbar_init(b_mmadone, 1);
         fence_mbar_init();
     }
@@ -92,8 +95,25 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 11);
 
     if (warp < 4) {
-        reg_dec_b<48>();
-        if (warp == 0 && lane == 0) {
+        if (warp == 3) {
+            // ================= L / delta stager: 64 + 64 floats per iteration into a 2-deep smem ring =================
+            for (int it = 0; it < n_it; ++it) {
+                const int u = it & 1;
+                const int h = kvh * g + it / per_head;
+                const int q0 = (first_qt + it % per_head) * C::BQ;
+                mbar_wait(b_ldempty(u), ((it >> 1) & 1) ^ 1u, 30);
+                float* dst = reinterpret_cast<float*>(sgen + C::OFF_LD) + u * 2 * C::BQ;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int qi = q0 + e * 32 + lane;
+                    const int64_t idx = ((int64_t)b * p.nh + h) * p.S + qi;
+                    dst[e * 32 + lane] = qi < p.S ? p.lse[idx] : INFINITY;
+                    dst[C::BQ + e * 32 + lane] = qi < p.S ? p.delta[idx] : 0.f;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_ldfull(u));
+            }
+        } else if (warp == 0 && lane == 0) {
             // ================= TMA producer =================
             mbar_expect_tx(b_kvfull, 2 * C::KT_BYTES);
             for (int kbk = 0; kbk < C::NB; ++kbk) {
@@ -166,8 +186,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             }
         }
     } else {
-        // ================= P^T / dS^T warpgroup: one thread per key row =================
-        reg_inc_b<232>();
+        // ================= P^T / dS^T warpgroups: one thread per key row, WG x handles q columns [32x, 32x+32) ===========
+        const int x = (warp - 4) >> 2;
         const int wq = warp & 3;
         const int r = wq * 32 + lane;
         const int key = k0 + r;
@@ -178,54 +198,47 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const float scale = c * 0.6931471805599453f;
         for (int it = 0; it < n_it; ++it) {
             const int u = it & 1;
-            const int h = kvh * g + it / per_head;
             const int q0 = (first_qt + it % per_head) * C::BQ;
-            const float* Lp = p.lse + ((int64_t)b * p.nh + h) * p.S + q0;
-            const float* Dp = p.delta + ((int64_t)b * p.nh + h) * p.S + q0;
-            const bool tail = (q0 + C::BQ > p.S) || (p.S & 3);
+            const bool causal_tile = q0 < k0 + C::BK - 1;         // some (key, q) pairs of this tile have key > q
             mbar_wait(b_sdpfull(u), (it >> 1) & 1, 36);
+            mbar_wait(b_ldfull(u), (it >> 1) & 1, 35);
             tc_fence_after();
-            uint32_t pk[C::BQ / 2], dk[C::BQ / 2];
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32b_x32(t_lane + C::TM_ST + u * C::BQ + x * 32, sv);
+            tmem_ld_32x32b_x32(t_lane + C::TM_DP + u * C::BQ + x * 32, dv);
+            const float4* L4 = reinterpret_cast<const float4*>(sgen + C::OFF_LD) + (u * 2 * C::BQ + x * 32) / 4;
+            const float4* D4 = L4 + C::BQ / 4;
+            tmem_ld_wait();
+            uint32_t pk[16], dk[16];
+            if (!key_ok) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t sv[32], dv[32];
-                tmem_ld_32x32b_x32(t_lane + C::TM_ST + u * C::BQ + half * 32, sv);
-                tmem_ld_32x32b_x32(t_lane + C::TM_DP + u * C::BQ + half * 32, dv);
-                tmem_ld_wait();
+                for (int j = 0; j < 16; ++j) { pk[j] = 0u; dk[j] = 0u; }
+            } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float L4[4], D4[4];
-                    if (!tail) {
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(Lp + half * 32) + j);
-                        const float4 d4 = __ldg(reinterpret_cast<const float4*>(Dp + half * 32) + j);
-                        L4[0] = a.x; L4[1] = a.y; L4[2] = a.z; L4[3] = a.w; D4[0] = d4.x; D4[1] = d4.y; D4[2] = d4.z; D4[3] = d4.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int qi = q0 + half * 32 + j * 4 + e;
-                            L4[e] = qi < p.S ? Lp[half * 32 + j * 4 + e] : INFINITY;
-                            D4[e] = qi < p.S ? Dp[half * 32 + j * 4 + e] : 0.f;
-                        }
-                    }
+                    const float4 l4 = L4[j], d4 = D4[j];
+                    const float Lv[4] = {l4.x, l4.y, l4.z, l4.w}, Dv[4] = {d4.x, d4.y, d4.z, d4.w};
                     float pv[4], dsv[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int cq = half * 32 + j * 4 + e;
-                        const bool ok = key_ok && (key <= q0 + cq);
-                        const float pr = ok ? ex2_approx(fmaf(__uint_as_float(sv[j * 4 + e]), c, -L4[e])) : 0.f;
+                        float sval = __uint_as_float(sv[j * 4 + e]);
+                        if (causal_tile && key > q0 + x * 32 + j * 4 + e) sval = -INFINITY;
+                        const float pr = ex2_approx(fmaf(sval, c, -Lv[e]));
                         pv[e] = pr;
-                        dsv[e] = pr * (__uint_as_float(dv[j * 4 + e]) - D4[e]) * scale;
+                        dsv[e] = pr * (__uint_as_float(dv[j * 4 + e]) - Dv[e]) * scale;
                     }
-                    pk[half * 16 + j * 2] = pack_bf16x2(pv[0], pv[1]); pk[half * 16 + j * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
-                    dk[half * 16 + j * 2] = pack_bf16x2(dsv[0], dsv[1]); dk[half * 16 + j * 2 + 1] = pack_bf16x2(dsv[2], dsv[3]);
+                    pk[j * 2] = pack_bf16x2(pv[0], pv[1]); pk[j * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+                    dk[j * 2] = pack_bf16x2(dsv[0], dsv[1]); dk[j * 2 + 1] = pack_bf16x2(dsv[2], dsv[3]);
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_ldempty(u));
             // the single P^T / dS^T buffers are free once the accumulate MMAs of iteration it-1 completed
             if (it > 0) mbar_wait(b_mmadone, (it - 1) & 1, 37);
 #pragma unroll
-            for (int j = 0; j < C::BQ / 8; ++j) {
-                *reinterpret_cast<uint4*>(sgen + C::OFF_P + sw128b(r, j)) = make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]);
-                *reinterpret_cast<uint4*>(sgen + C::OFF_DS + sw128b(r, j)) = make_uint4(dk[j * 4], dk[j * 4 + 1], dk[j * 4 + 2], dk[j * 4 + 3]);
+            for (int j = 0; j < 4; ++j) {
+                *reinterpret_cast<uint4*>(sgen + C::OFF_P + sw128b(r, x * 4 + j)) = make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]);
+                *reinterpret_cast<uint4*>(sgen + C::OFF_DS + sw128b(r, x * 4 + j)) = make_uint4(dk[j * 4], dk[j * 4 + 1], dk[j * 4 + 2], dk[j * 4 + 3]);
             }
             fence_proxy_async();
             tc_fence_before();
@@ -239,7 +252,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         float* dkp = p.dk_acc + ((int64_t)b * p.S + min(key, p.S - 1)) * p.ldacc + kvh * D;
         float* dvp = p.dv_acc + ((int64_t)b * p.S + min(key, p.S - 1)) * p.ldacc + kvh * D;
 #pragma unroll
-        for (int cc = 0; cc < D / 32; ++cc) {
+        for (int cc = x * (D / 64); cc < (x + 1) * (D / 64); ++cc) {
             uint32_t a[32], v[32];
             tmem_ld_32x32b_x32(t_lane + C::TM_DK + cc * 32, a);
             tmem_ld_32x32b_x32(t_lane + C::TM_DV + cc * 32, v);
@@ -280,7 +293,7 @@ struct DqCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                       const __grid_constant__ CUtensorMap tm_kv, const AttnBwdTcParams p) {
     using C = DqCfg<D>;
@@ -315,7 +328,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         for (int s = 0; s < C::kKStages; ++s) { mbar_init(b_kfull(s), 1); mbar_init(b_kempty(s), 1); }
         for (int s = 0; s < C::kVStages; ++s) { mbar_init(b_vfull(s), 1); mbar_init(b_vempty(s), 1); }
         for (int u = 0; u < 2; ++u) mbar_init(b_sdpfull(u), 1);
-        mbar_init(b_dsfull, 4);
+        mbar_init(b_dsfull, 8);
         mbar_init(b_mmadone, 1);
         fence_mbar_init();
     }
@@ -326,7 +339,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 15);
 
     if (warp < 4) {
-        reg_dec_b<48>();
         if (warp == 0 && lane == 0) {
             mbar_expect_tx(b_qfull, 2 * C::QT_BYTES);
             for (int kbk = 0; kbk < C::NB; ++kbk) {
@@ -391,7 +403,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             }
         }
     } else {
-        reg_inc_b<232>();
+        // ================= dS warpgroups: one thread per query row, WG x handles kv columns [32x, 32x+32) =================
+        const int x = (warp - 4) >> 2;
         const int wq = warp & 3;
         const int r = wq * 32 + lane;
         const int row = q0 + r;
@@ -407,34 +420,30 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const bool need_mask = (kv0 + C::BKV - 1 > q0 + wq * 32) || (kv0 + C::BKV > kvlen) || general_mask;
             mbar_wait(b_sdpfull(u), (t >> 1) & 1, 47);
             tc_fence_after();
-            uint32_t dsk[C::BKV / 2];
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32b_x32(t_lane + C::TM_S + u * C::BKV + x * 32, sv);
+            tmem_ld_32x32b_x32(t_lane + C::TM_DP + u * C::BKV + x * 32, dv);
+            tmem_ld_wait();
+            if (need_mask) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t sv[32], dv[32];
-                tmem_ld_32x32b_x32(t_lane + C::TM_S + u * C::BKV + half * 32, sv);
-                tmem_ld_32x32b_x32(t_lane + C::TM_DP + u * C::BKV + half * 32, dv);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float ds2[2];
-#pragma unroll
-                    for (int w = 0; w < 2; ++w) {
-                        const int key = kv0 + half * 32 + e + w;
-                        bool ok = true;
-                        if (need_mask) {
-                            ok = key <= row && key < kvlen;
-                            if (ok && general_mask) ok = p.key_mask[(int64_t)b * p.S + key] != 0;
-                        }
-                        const float pr = ok ? ex2_approx(fmaf(__uint_as_float(sv[e + w]), c, -L)) : 0.f;
-                        ds2[w] = pr * (__uint_as_float(dv[e + w]) - Dl) * scale;
-                    }
-                    dsk[half * 16 + e / 2] = pack_bf16x2(ds2[0], ds2[1]);
+                for (int e = 0; e < 32; ++e) {
+                    const int key = kv0 + x * 32 + e;
+                    bool ok = key <= row && key < kvlen;
+                    if (ok && general_mask) ok = p.key_mask[(int64_t)b * p.S + key] != 0;
+                    if (!ok) sv[e] = 0xff800000u;   // -inf -> p = 0
                 }
+            }
+            uint32_t dsk[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), c, -L));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c, -L));
+                dsk[e / 2] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - Dl) * scale, p1 * (__uint_as_float(dv[e + 1]) - Dl) * scale);
             }
             if (t > 0) mbar_wait(b_mmadone, (t - 1) & 1, 48);
 #pragma unroll
-            for (int j = 0; j < C::BKV / 8; ++j)
-                *reinterpret_cast<uint4*>(sgen + C::OFF_DS + sw128b(r, j)) = make_uint4(dsk[j * 4], dsk[j * 4 + 1], dsk[j * 4 + 2], dsk[j * 4 + 3]);
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(sgen + C::OFF_DS + sw128b(r, x * 4 + j)) = make_uint4(dsk[j * 4], dsk[j * 4 + 1], dsk[j * 4 + 2], dsk[j * 4 + 3]);
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
@@ -445,7 +454,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         __nv_bfloat16* dqp = p.dq + ((int64_t)b * p.S + min(row, p.S - 1)) * p.lddq + h * D;
         const float* ddp = p.dq_diag ? p.dq_diag + ((int64_t)b * p.S + min(row, p.S - 1)) * (int64_t)(p.nh * D) + h * D : nullptr;
 #pragma unroll
-        for (int cc = 0; cc < D / 32; ++cc) {
+        for (int cc = x * (D / 64); cc < (x + 1) * (D / 64); ++cc) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(t_lane + C::TM_DQ + cc * 32, v);
             tmem_ld_wait();
@@ -499,7 +508,7 @@ static int bwd_tc_t(const AttnDesc& a, cudaStream_t st) {
             set = true;
         }
         dim3 grid((a.S + C::BK - 1) / C::BK, a.nkv, a.B);
-        attn_bwd_dkv_tc_kernel<D><<<grid, 256, C::SMEM, st>>>(tq64, tdo64, tkv128, p);
+        attn_bwd_dkv_tc_kernel<D><<<grid, 384, C::SMEM, st>>>(tq64, tdo64, tkv128, p);
         SF_CUDA_CHECK_LAUNCH("attn_bwd_dkv_tc");
     }
     {
@@ -511,7 +520,7 @@ static int bwd_tc_t(const AttnDesc& a, cudaStream_t st) {
             set = true;
         }
         dim3 grid((a.S + C::BQ - 1) / C::BQ, a.nh, a.B);
-        attn_bwd_dq_tc_kernel<D><<<grid, 256, C::SMEM, st>>>(tq128, tdo128, tkv64, p);
+        attn_bwd_dq_tc_kernel<D><<<grid, 384, C::SMEM, st>>>(tq128, tdo128, tkv64, p);
         SF_CUDA_CHECK_LAUNCH("attn_bwd_dq_tc");
     }
     return 0;
