@@ -150,9 +150,13 @@ struct Ctx {
     __nv_bfloat16* bf(int64_t off, int64_t elem_off = 0) const { return reinterpret_cast<__nv_bfloat16*>(ws + off) + elem_off; }
 };
 
+static bool fuse_swiglu(const Dims& x) { return x.M > 128 && x.I % 128 == 0; }
+
 static int mm(const Ctx& c, const void* A, int64_t lda, int am, const void* B, int64_t ldb, int bm, void* D, int64_t ldd,
-              const void* R, int64_t ldr, int64_t M, int64_t N, int64_t K, int epi) {
+              const void* R, int64_t ldr, int64_t M, int64_t N, int64_t K, int epi, void* D2 = nullptr, int64_t ldd2 = 0,
+              int n_half = 0) {
     GemmDesc g;
+    g.D2 = D2; g.ldd2 = ldd2; g.n_half = n_half;
     g.A = A; g.lda = lda; g.a_major = am; g.B = B; g.ldb = ldb; g.b_major = bm; g.D = D; g.ldd = ldd; g.R = R; g.ldr = ldr;
     g.M = (int)M; g.N = (int)N; g.K = (int)K; g.epi = epi; g.cta_group = 0;
     return gemm(g, c.st);
@@ -225,8 +229,12 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         // h_mid = h_j + attn W_o^T ; MLP ; h_{j+1} = h_mid + down(silu(gate) * up)   (llama3_eagle.py:1641-1648)
         SF_TRY(mm(c, attn, x.A, MAJOR_K, c.W[SF_P_O], x.A, MAJOR_K, hmid, x.H, h_in, x.H, M, x.H, x.A, EPI_BF16_RESID));
         SF_TRY(rmsnorm_fwd(hmid, x.H, nullptr, x.S, 0, c.W[SF_P_POST_NORM], hn2, x.H, M, x.H, cfg.rms_eps, nullptr, st));
-        SF_TRY(mm(c, hn2, x.H, MAJOR_K, c.W[SF_P_GATE], x.H, MAJOR_K, gu, 2 * x.I, nullptr, 0, M, 2 * x.I, x.H, EPI_BF16));
-        SF_TRY(swiglu_fwd(gu, act, M, x.I, st));
+        if (fuse_swiglu(x)) {   // gate/up GEMM with the SwiGLU fused into its epilogue
+            SF_TRY(mm(c, hn2, x.H, MAJOR_K, c.W[SF_P_GATE], x.H, MAJOR_K, gu, 2 * x.I, nullptr, 0, M, 2 * x.I, x.H, EPI_SWIGLU, act, x.I, x.I));
+        } else {
+            SF_TRY(mm(c, hn2, x.H, MAJOR_K, c.W[SF_P_GATE], x.H, MAJOR_K, gu, 2 * x.I, nullptr, 0, M, 2 * x.I, x.H, EPI_BF16));
+            SF_TRY(swiglu_fwd(gu, act, M, x.I, st));
+        }
         SF_TRY(mm(c, act, x.I, MAJOR_K, c.W[SF_P_DOWN], x.I, MAJOR_K, h_out, x.H, hmid, x.H, M, x.H, x.I, EPI_BF16_RESID));
         // logits = lm_head(norm(h_{j+1}))   (llama3_eagle.py:1772-1777)
         if (cfg.norm_output)
@@ -293,8 +301,12 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
             return set_error(-38, "norm_output=false backward not implemented");
         }
         // MLP
-        SF_TRY(mm(c, dh_tot, x.H, MAJOR_K, c.W[SF_P_DOWN], x.I, MAJOR_MN, d_act, x.I, nullptr, 0, M, x.I, x.H, EPI_BF16));
-        SF_TRY(swiglu_bwd(gu, d_act, dgu, M, x.I, st));
+        if (fuse_swiglu(x)) {   // d(act) never touches HBM: the dgrad epilogue applies the SwiGLU backward
+            SF_TRY(mm(c, dh_tot, x.H, MAJOR_K, c.W[SF_P_DOWN], x.I, MAJOR_MN, dgu, 2 * x.I, gu, 2 * x.I, M, x.I, x.H, EPI_SWIGLU_BWD, nullptr, 0, x.I));
+        } else {
+            SF_TRY(mm(c, dh_tot, x.H, MAJOR_K, c.W[SF_P_DOWN], x.I, MAJOR_MN, d_act, x.I, nullptr, 0, M, x.I, x.H, EPI_BF16));
+            SF_TRY(swiglu_bwd(gu, d_act, dgu, M, x.I, st));
+        }
         SF_TRY(mm(c, dgu, 2 * x.I, MAJOR_K, c.W[SF_P_GATE], x.H, MAJOR_MN, d_hn2, x.H, nullptr, 0, M, x.H, 2 * x.I, EPI_BF16));
         SF_TRY(rmsnorm_bwd(hmid, x.H, nullptr, x.S, 0, c.W[SF_P_POST_NORM], d_hn2, x.H, dh_tot, nullptr, dhmid, Gn + off[SF_P_POST_NORM], M, x.H, cfg.rms_eps, st));
         // attention

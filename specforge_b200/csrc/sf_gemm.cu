@@ -76,6 +76,7 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     GemmParams p;
     p.D = g.D; p.R = reinterpret_cast<const __nv_bfloat16*>(g.R);
     p.M = g.M; p.N = g.N; p.K = g.K; p.ldd = (int)g.ldd; p.ldr = (int)g.ldr; p.epi = g.epi;
+    p.D2 = g.D2; p.ldd2 = (int)g.ldd2; p.n_half = g.n_half;
     p.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
     p.num_n_blocks = (g.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
     const int tiles = p.num_m_blocks * p.num_n_blocks;
@@ -118,9 +119,15 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
 
 int gemm(const GemmDesc& g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(-22, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
-    if (g.epi < 0 || g.epi > 3) return set_error(-22, "gemm: bad epilogue %d", g.epi);
+    if (g.epi < 0 || g.epi > 5) return set_error(-22, "gemm: bad epilogue %d", g.epi);
+    if (g.epi == EPI_SWIGLU) {
+        if (g.cta_group == 1 || g.M <= 128) return set_error(-22, "gemm: fused SwiGLU needs the 2-CTA configuration (M > 128)");
+        if (!g.D2 || g.n_half <= 0 || g.N != 2 * g.n_half || g.n_half % 128) return set_error(-22, "gemm: fused SwiGLU needs D2 and N == 2*n_half, n_half %% 128 == 0");
+        if (g.a_major || g.b_major) return set_error(-22, "gemm: fused SwiGLU forward is K-major x K-major");
+    }
+    if (g.epi == EPI_SWIGLU_BWD && (!g.R || g.n_half <= 0 || g.N != g.n_half || g.n_half % 32)) return set_error(-22, "gemm: fused SwiGLU backward needs R = gu and N == n_half");
     if (g.epi == EPI_BF16_RESID && !g.R) return set_error(-22, "gemm: residual epilogue without R");
-    const int elt = (g.epi >= EPI_F32) ? 4 : 2;
+    const int elt = (g.epi == EPI_F32 || g.epi == EPI_F32_ACCUM) ? 4 : 2;
     if ((reinterpret_cast<uintptr_t>(g.D) & 15) || (g.ldd * elt) % 16)
         return set_error(-22, "gemm: D must be 16-byte aligned with 16-byte aligned rows");
     if (g.epi == EPI_BF16_RESID && ((reinterpret_cast<uintptr_t>(g.R) & 15) || (g.ldr % 8)))

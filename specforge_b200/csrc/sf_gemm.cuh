@@ -27,6 +27,13 @@ enum : int {
     EPI_BF16_RESID = 1,  // D(bf16) = bf16(acc) + R   (R bf16; sum rounded once more to bf16)
     EPI_F32 = 2,         // D(f32)  = acc
     EPI_F32_ACCUM = 3,   // D(f32) += acc
+    // Fused SwiGLU (llama3_eagle.py:1547).  Forward: B = [gate ; up] weight ([2I, K]); each 256-wide tile holds 128
+    // gate and the matching 128 up columns (CTA rank 0 stages gate rows, rank 1 up rows; 2-CTA only).
+    // D = gu [M, 2I] (bf16 gate | up, saved for backward), D2 = act [M, I] = bf16(bf16(silu(g)) * u).
+    EPI_SWIGLU = 4,
+    // Backward: acc = d(act) tile [128 x 256] over columns j of I; R = gu [M, 2I]; D = d(gu) [M, 2I]:
+    // d(gate) = d(act) * u * silu'(g), d(up) = d(act) * silu(g).
+    EPI_SWIGLU_BWD = 5,
 };
 
 struct GemmParams {
@@ -36,6 +43,8 @@ struct GemmParams {
     int ldd, ldr;
     int epi;
     int num_m_blocks, num_n_blocks;
+    void* D2; int ldd2;   // EPI_SWIGLU: act output
+    int n_half;           // EPI_SWIGLU / EPI_SWIGLU_BWD: I (columns of gate == columns of up)
 };
 
 template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN>
@@ -127,7 +136,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             int m_blk, n_blk;
             tile_coords(tile, m_blk, n_blk);
             const int m0 = m_blk * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M;
-            const int n0 = n_blk * Cfg::BLOCK_N + (int)cta_rank * Cfg::B_ROWS;
+            int n0 = n_blk * Cfg::BLOCK_N + (int)cta_rank * Cfg::B_ROWS;
+            if (p.epi == EPI_SWIGLU) n0 = n_blk * (Cfg::BLOCK_N / 2) + (int)cta_rank * p.n_half;   // gate rows | up rows
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u, 1);
                 const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -216,6 +226,77 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + astage * Cfg::BLOCK_N;
             const bool row_ok = row < p.M;
+            if (p.epi == EPI_SWIGLU) {
+                // columns [0,128) of the accumulator = gate(j0 + .), [128,256) = up(j0 + .)
+                const int j0 = n_blk * (Cfg::BLOCK_N / 2);
+                __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
+                __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.D2) + (size_t)row * p.ldd2;
+#pragma unroll 1
+                for (int c = 0; c < Cfg::BLOCK_N / 64; ++c) {
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, g);
+                    tmem_ld_32x32b_x32(t_row + Cfg::BLOCK_N / 2 + c * 32, u);
+                    tmem_ld_wait();
+                    const int col = j0 + c * 32;
+                    if (!row_ok || col >= p.n_half) continue;
+                    uint32_t og[16], ou[16], oa[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        og[e] = pack_bf16x2(__uint_as_float(g[2 * e]), __uint_as_float(g[2 * e + 1]));
+                        ou[e] = pack_bf16x2(__uint_as_float(u[2 * e]), __uint_as_float(u[2 * e + 1]));
+                        const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&og[e]);
+                        const __nv_bfloat162 ub = *reinterpret_cast<const __nv_bfloat162*>(&ou[e]);
+                        const float g0 = __bfloat162float(gb.x), g1 = __bfloat162float(gb.y);
+                        const float s0 = __bfloat162float(__float2bfloat16_rn(g0 / (1.f + __expf(-g0))));
+                        const float s1 = __bfloat162float(__float2bfloat16_rn(g1 / (1.f + __expf(-g1))));
+                        oa[e] = pack_bf16x2(s0 * __bfloat162float(ub.x), s1 * __bfloat162float(ub.y));
+                    }
+                    // host guarantees n_half % 128 == 0: every 32-column chunk is whole
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        reinterpret_cast<uint4*>(gu + col)[q] = make_uint4(og[q * 4], og[q * 4 + 1], og[q * 4 + 2], og[q * 4 + 3]);
+                        reinterpret_cast<uint4*>(gu + p.n_half + col)[q] = make_uint4(ou[q * 4], ou[q * 4 + 1], ou[q * 4 + 2], ou[q * 4 + 3]);
+                        reinterpret_cast<uint4*>(act + col)[q] = make_uint4(oa[q * 4], oa[q * 4 + 1], oa[q * 4 + 2], oa[q * 4 + 3]);
+                    }
+                }
+            } else if (p.epi == EPI_SWIGLU_BWD) {
+                const __nv_bfloat16* gu = p.R + (size_t)row * p.ldr;
+                __nv_bfloat16* dgu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
+#pragma unroll 1
+                for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    const int col = n0 + c * 32;
+                    if (!row_ok || col >= p.n_half) continue;
+                    // host guarantees n_half % 32 == 0
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(gu + col) + q);
+                        const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(gu + p.n_half + col) + q);
+                        const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
+                        uint32_t odg[4], odu[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&gw[e]);
+                            const __nv_bfloat162 ub = *reinterpret_cast<const __nv_bfloat162*>(&uw[e]);
+                            float dg[2], du[2];
+#pragma unroll
+                            for (int w = 0; w < 2; ++w) {
+                                const float gg = __bfloat162float(w ? gb.y : gb.x), uu = __bfloat162float(w ? ub.y : ub.x);
+                                const float da = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[q * 8 + e * 2 + w])));
+                                const float sg = 1.f / (1.f + __expf(-gg));
+                                dg[w] = da * uu * (sg * (1.f + gg * (1.f - sg)));
+                                du[w] = da * gg * sg;
+                            }
+                            odg[e] = pack_bf16x2(dg[0], dg[1]);
+                            odu[e] = pack_bf16x2(du[0], du[1]);
+                        }
+                        reinterpret_cast<uint4*>(dgu + col)[q] = make_uint4(odg[0], odg[1], odg[2], odg[3]);
+                        reinterpret_cast<uint4*>(dgu + p.n_half + col)[q] = make_uint4(odu[0], odu[1], odu[2], odu[3]);
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
                 uint32_t v[32];

@@ -18,6 +18,8 @@ struct GemmDesc {
     int M, N, K;
     int epi;                                   // sf::EPI_*
     int cta_group;                             // 0 = auto, 1, 2
+    void* D2 = nullptr; int64_t ldd2 = 0;      // EPI_SWIGLU: act output [M, I]
+    int n_half = 0;                            // EPI_SWIGLU(_BWD): I
 };
 int gemm(const GemmDesc& g, cudaStream_t stream);
 
