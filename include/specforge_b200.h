@@ -59,6 +59,9 @@ typedef struct sf_eagle3_config {
     int32_t rope_rows;        /* rows in the cos/sin tables (>= S + T) */
     float rms_eps;
     float ploss_decay;        /* 0.8 */
+    int32_t lk_loss_type;     /* 0 = KL only (default), 1 = "lambda", 2 = "alpha"  (core/lk_loss.py:83-99) */
+    float kl_scale;           /* lambda: w = kl_scale * exp(-kl_decay * acceptance) */
+    float kl_decay;
 } sf_eagle3_config;
 
 /* Offsets (in elements) of each trainable parameter inside the flat bf16 parameter buffer; the fp32 gradient
@@ -92,7 +95,7 @@ typedef struct sf_eagle3_batch {      /* one collated micro-batch, already on th
 size_t sf_eagle3_workspace_bytes(const sf_eagle3_config* cfg);
 
 /* Teacher + TTT-unrolled forward + loss/metrics.  metrics: device float [T][8] =
- * {ploss, acc_correct, acc_denom, acceptance_rate, accept_num, accept_den, loss_denom, 0};
+ * {ploss, acc_correct, acc_denom, acceptance_rate, accept_num, accept_den, loss_denom, kl_weight};
  * loss: device float scalar = sum_j decay^j * ploss_j.  need_grad != 0 also leaves d(loss)/d(logits) and the
  * activations in the workspace for sf_eagle3_backward. */
 int sf_eagle3_forward(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,

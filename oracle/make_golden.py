@@ -46,6 +46,19 @@ CASES = {
     "small_d128": (dict(hidden_size=256, intermediate_size=512, num_heads=4, num_kv_heads=1, head_dim=128,
                         vocab_size=1024, draft_vocab_size=256, rms_norm_eps=1e-6, rope_theta=1000000.0,
                         max_position_embeddings=2048, ttt_length=7), 2, 160, 9, None),
+    # head_dim 64 cases the CUDA path can run: LK objectives, EAGLE3.1 fc_norm (target hidden != draft hidden), norm_output=False
+    "small_lk_lambda": (dict(hidden_size=128, intermediate_size=256, num_heads=2, num_kv_heads=1, head_dim=64, vocab_size=512,
+                             draft_vocab_size=128, rms_norm_eps=1e-5, rope_theta=10000.0, max_position_embeddings=512,
+                             ttt_length=3), 2, 96, 7, "lambda"),
+    "small_lk_alpha": (dict(hidden_size=128, intermediate_size=256, num_heads=2, num_kv_heads=1, head_dim=64, vocab_size=512,
+                            draft_vocab_size=128, rms_norm_eps=1e-5, rope_theta=10000.0, max_position_embeddings=512,
+                            ttt_length=3), 2, 96, 7, "alpha"),
+    "small_fcnorm": (dict(hidden_size=128, intermediate_size=256, num_heads=2, num_kv_heads=2, head_dim=64, vocab_size=512,
+                          draft_vocab_size=128, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=512,
+                          ttt_length=3, fc_norm=True, target_hidden_size=192), 2, 64, 0, None),
+    "small_nonorm": (dict(hidden_size=128, intermediate_size=256, num_heads=2, num_kv_heads=2, head_dim=64, vocab_size=512,
+                          draft_vocab_size=128, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=512,
+                          ttt_length=2, norm_output=False), 2, 64, 0, None),
     # BASELINE config 1 shape: Qwen2.5-0.5B draft, TTT=3, bs=1, seq=128 (configs/qwen2.5-0.5b-eagle3.json)
     "qwen25_05b_cfg1": (dict(hidden_size=896, intermediate_size=4864, num_heads=14, num_kv_heads=2, head_dim=64,
                              vocab_size=151936, draft_vocab_size=16000, rms_norm_eps=1e-6, rope_theta=1000000.0,
@@ -78,6 +91,9 @@ def build_reference(cfg: O.Eagle3Config, P, t2d, d2t, head_w, lk_loss_type, work
     hf.head_dim = cfg.head_dim
     hf.draft_vocab_size = cfg.draft_vocab_size
     hf.rope_theta = cfg.rope_theta
+    hf.fc_norm = cfg.fc_norm
+    hf.norm_output = cfg.norm_output
+    hf.target_hidden_size = cfg.target_hidden_size
     draft = LlamaForCausalLMEagle3(hf, attention_backend="sdpa")
     sd = {k: v.clone() for k, v in P.items()}
     sd["t2d"], sd["d2t"] = t2d, d2t

@@ -9,6 +9,7 @@
 #include "sf_host.h"
 #include "../../include/specforge_b200.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace sf {
@@ -36,7 +37,7 @@ static int validate(const sf_eagle3_config& c) {
     if (c.hidden_size > 8192 || c.target_hidden > 8192) return set_error(-22, "config: hidden size > 8192 unsupported");
     if (c.num_heads % c.num_kv_heads) return set_error(-22, "config: num_heads %% num_kv_heads != 0");
     if (c.rope_rows < c.seq_len + c.ttt_length) return set_error(-22, "config: rope tables have %d rows, need >= S+T=%d", c.rope_rows, c.seq_len + c.ttt_length);
-    if (c.fc_norm) return set_error(-38, "config: fc_norm (EAGLE3.1) is not implemented yet");
+    if (c.lk_loss_type < 0 || c.lk_loss_type > 2) return set_error(-22, "config: lk_loss_type=%d (0 none, 1 lambda, 2 alpha)", c.lk_loss_type);
     return 0;
 }
 
@@ -59,12 +60,12 @@ static void layout(const sf_eagle3_config& c, int64_t* off, int64_t* sz, int64_t
 // ------------------------------------------------------------------ workspace plan
 struct Plan {
     // persistent forward -> backward
-    int64_t h, xcat, qkv, attn, lse, hmid, hn2, gu, act, hf, logits;
+    int64_t h, xcat, qkv, attn, lse, hmid, hn2, gu, act, hf, logits, hs3n;
     int64_t target_p, pod, ids, pos_mask, loss_mask32, key_mask, kvlen, d2t_idx, row_ws, sd_ws, metrics, misc;
     // union region: forward temporaries / backward buffers
     int64_t u_base;
     int64_t tgt_shift, tlogits;                       // forward temporaries
-    int64_t dh_tot, dgu, dhmid, dqkv, d_hf, d_act, d_hn2, d_attn, d_xcat, dh_carry, dk_acc, dv_acc, dq_diag, delta;
+    int64_t dh_tot, dgu, dhmid, dqkv, d_hf, d_act, d_hn2, d_attn, d_xcat, dh_carry, dk_acc, dv_acc, dq_diag, delta, d_hs3n;
     int64_t total;
 };
 static Plan make_plan(const sf_eagle3_config& c) {
@@ -84,6 +85,7 @@ static Plan make_plan(const sf_eagle3_config& c) {
     p.act = take(T * M * x.I * 2);
     p.hf = c.norm_output ? take(T * M * x.H * 2) : p.h + M * x.H * 2;
     p.logits = take(T * M * x.DV * 2);
+    p.hs3n = c.fc_norm ? take(M * 3 * x.Ht * 2) : 0;
     p.target_p = take((int64_t)x.B * (x.S + T) * x.DV * 4);
     p.pod = take((int64_t)x.B * (x.S + T) * x.DV * 4);
     p.ids = take((int64_t)x.B * (x.S + T) * 8);
@@ -117,6 +119,7 @@ static Plan make_plan(const sf_eagle3_config& c) {
     p.dv_acc = take(T * M * x.KV * 4);
     p.dq_diag = take(M * x.A * 4);
     p.delta = take((int64_t)x.B * x.nh * x.S * 4);
+    p.d_hs3n = c.fc_norm ? take(M * 3 * x.Ht * 2) : 0;
     p.total = (o > fwd_end ? o : fwd_end) + 1024;
     return p;
 }
@@ -150,7 +153,11 @@ struct Ctx {
     __nv_bfloat16* bf(int64_t off, int64_t elem_off = 0) const { return reinterpret_cast<__nv_bfloat16*>(ws + off) + elem_off; }
 };
 
-static bool fuse_swiglu(const Dims& x) { return x.M > 128 && x.I % 128 == 0; }
+static bool fuse_swiglu(const Dims& x) {
+    static int off = -1;   // SF_NO_SWIGLU_FUSION=1: A/B switch for profiling
+    if (off < 0) { const char* e = getenv("SF_NO_SWIGLU_FUSION"); off = (e && e[0] == '1') ? 1 : 0; }
+    return !off && x.M > 128 && x.I % 128 == 0;
+}
 
 static int mm(const Ctx& c, const void* A, int64_t lda, int am, const void* B, int64_t ldb, int bm, void* D, int64_t ldd,
               const void* R, int64_t ldr, int64_t M, int64_t N, int64_t K, int epi, void* D2 = nullptr, int64_t ldd2 = 0,
@@ -192,8 +199,15 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
     SF_TRY(mm(c, c.bf(p.tgt_shift), x.Ht, MAJOR_K, fz.target_head, x.Ht, MAJOR_K, c.bf(p.tlogits), x.V, nullptr, 0, M, x.V, x.Ht, EPI_BF16));
     SF_TRY(teacher(c.bf(p.tlogits), x.V, c.at<int>(p.d2t_idx), fz.t2d, c.at<int>(p.loss_mask32), c.at<float>(p.target_p),
                    c.at<float>(p.pod), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask), x.B, x.S, T, x.V, x.DV, st));
-    // ---- fc: h_0 = hidden_state W_fc^T   (llama3_eagle.py:1762-1770)
-    SF_TRY(mm(c, bt.hidden_state, 3 * x.Ht, MAJOR_K, c.W[SF_P_FC], 3 * x.Ht, MAJOR_K, c.bf(p.h), x.H, nullptr, 0, M, x.H, 3 * x.Ht, EPI_BF16));
+    // ---- fc: h_0 = [fc_norm_i(chunk_i)] W_fc^T   (llama3_eagle.py:1762-1770; per-third RMSNorm = EAGLE3.1)
+    const void* fc_in = bt.hidden_state;
+    if (cfg.fc_norm) {
+        const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(bt.hidden_state);
+        for (int i = 0; i < 3; ++i)
+            SF_TRY(rmsnorm_fwd(hs + i * x.Ht, 3 * x.Ht, nullptr, x.S, 0, c.W[SF_P_FC_NORM0 + i], c.bf(p.hs3n) + i * x.Ht, 3 * x.Ht, M, x.Ht, cfg.rms_eps, nullptr, st));
+        fc_in = c.bf(p.hs3n);
+    }
+    SF_TRY(mm(c, fc_in, 3 * x.Ht, MAJOR_K, c.W[SF_P_FC], 3 * x.Ht, MAJOR_K, c.bf(p.h), x.H, nullptr, 0, M, x.H, 3 * x.Ht, EPI_BF16));
     const uint8_t* key_mask = bt.attention_mask ? c.at<uint8_t>(p.key_mask) : nullptr;
     if (key_mask) SF_TRY(mask_prefix(key_mask, x.B, x.S, c.at<int>(p.kvlen), c.at<int>(p.kvlen) + x.B, st));
     for (int j = 0; j < T; ++j) {
@@ -241,10 +255,10 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
             SF_TRY(rmsnorm_fwd(h_out, x.H, nullptr, x.S, 0, c.W[SF_P_NORM], hf, x.H, M, x.H, cfg.rms_eps, nullptr, st));
         SF_TRY(mm(c, hf, x.H, MAJOR_K, c.W[SF_P_LM_HEAD], x.H, MAJOR_K, logits, x.DV, nullptr, 0, M, x.DV, x.H, EPI_BF16));
         // loss / metrics / d(logits) in place   (eagle3/model.py:142-199, core/loss.py, core/lk_loss.py)
-        const float coef = powf(cfg.ploss_decay, (float)j) / (float)M;
+        const float step_weight = powf(cfg.ploss_decay, (float)j);
         SF_TRY(loss_step(logits, x.DV, c.at<float>(p.target_p), c.at<float>(p.pod), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask),
-                         c.at<int>(p.loss_mask32), fz.d2t, x.B, x.S, T, x.DV, j, coef, need_grad, c.at<float>(p.row_ws),
-                         c.at<float>(p.metrics), st));
+                         c.at<int>(p.loss_mask32), fz.d2t, x.B, x.S, T, x.DV, j, step_weight, need_grad, cfg.lk_loss_type,
+                         cfg.kl_scale, cfg.kl_decay, c.at<float>(p.row_ws), c.at<float>(p.metrics), st));
     }
     total_loss_kernel<<<1, 64, 0, st>>>(c.at<float>(p.metrics), T, cfg.ploss_decay, loss_out ? loss_out : c.at<float>(p.misc), metrics_out);
     SF_CUDA_CHECK_LAUNCH("total_loss");
@@ -298,7 +312,7 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
         if (cfg.norm_output) {
             SF_TRY(rmsnorm_bwd(h_out, x.H, nullptr, x.S, 0, c.W[SF_P_NORM], d_hf, x.H, carry_in, nullptr, dh_tot, Gn + off[SF_P_NORM], M, x.H, cfg.rms_eps, st));
         } else {
-            return set_error(-38, "norm_output=false backward not implemented");
+            SF_TRY(add_bf16(d_hf, carry_in, dh_tot, M * x.H, st));   // lm_head reads h_{j+1} directly
         }
         // MLP
         if (fuse_swiglu(x)) {   // d(act) never touches HBM: the dgrad epilogue applies the SwiGLU backward
@@ -342,8 +356,16 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
     SF_TRY(mm(c, c.bf(p.dgu), 2 * x.I, MAJOR_MN, c.bf(p.hn2), x.H, MAJOR_MN, Gn + off[SF_P_GATE], x.H, nullptr, 0, 2 * x.I, x.H, TM, EPI_F32_ACCUM));
     SF_TRY(mm(c, c.bf(p.dhmid), x.H, MAJOR_MN, c.bf(p.attn), x.A, MAJOR_MN, Gn + off[SF_P_O], x.A, nullptr, 0, x.H, x.A, TM, EPI_F32_ACCUM));
     SF_TRY(mm(c, c.bf(p.dqkv), x.QKV, MAJOR_MN, c.bf(p.xcat), 2 * x.H, MAJOR_MN, Gn + off[SF_P_Q], 2 * x.H, nullptr, 0, x.QKV, 2 * x.H, TM, EPI_F32_ACCUM));
-    // fc: dW_fc = d(h_0)^T hidden_state
-    SF_TRY(mm(c, c.bf(p.dh_carry), x.H, MAJOR_MN, bt.hidden_state, 3 * x.Ht, MAJOR_MN, Gn + off[SF_P_FC], 3 * x.Ht, nullptr, 0, x.H, 3 * x.Ht, M, EPI_F32_ACCUM));
+    // fc: dW_fc = d(h_0)^T fc_in ; with fc_norm also the three norm-weight gradients through d(fc_in) = d(h_0) W_fc
+    const void* fc_in = bt.hidden_state;
+    if (cfg.fc_norm) {
+        fc_in = c.bf(p.hs3n);
+        const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(bt.hidden_state);
+        SF_TRY(mm(c, c.bf(p.dh_carry), x.H, MAJOR_K, c.W[SF_P_FC], 3 * x.Ht, MAJOR_MN, c.bf(p.d_hs3n), 3 * x.Ht, nullptr, 0, M, 3 * x.Ht, x.H, EPI_BF16));
+        for (int i = 0; i < 3; ++i)
+            SF_TRY(rmsnorm_bwd(hs + i * x.Ht, 3 * x.Ht, nullptr, x.S, 0, c.W[SF_P_FC_NORM0 + i], c.bf(p.d_hs3n) + i * x.Ht, 3 * x.Ht, nullptr, nullptr, nullptr, Gn + off[SF_P_FC_NORM0 + i], M, x.Ht, cfg.rms_eps, st));
+    }
+    SF_TRY(mm(c, c.bf(p.dh_carry), x.H, MAJOR_MN, fc_in, 3 * x.Ht, MAJOR_MN, Gn + off[SF_P_FC], 3 * x.Ht, nullptr, 0, x.H, 3 * x.Ht, M, EPI_F32_ACCUM));
     return 0;
 }
 

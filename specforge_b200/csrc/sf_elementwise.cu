@@ -303,6 +303,22 @@ shift_left_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restri
     }
 }
 
+// out = a (+ b)   (bf16, n % 8 == 0)
+__global__ void __launch_bounds__(256)
+add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, int64_t n8) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        bf16x8 x; x.u = __ldg(reinterpret_cast<const uint4*>(a) + i);
+        if (b) {
+            bf16x8 y; y.u = __ldg(reinterpret_cast<const uint4*>(b) + i);
+            float xf[8], yf[8]; x.unpack(xf); y.unpack(yf);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xf[k] += yf[k];
+            x.pack(xf);
+        }
+        reinterpret_cast<uint4*>(out)[i] = x.u;
+    }
+}
+
 static inline int grid_for(int64_t total, int threads = 256, int max_blocks = 148 * 16) {
     int64_t b = (total + threads - 1) / threads;
     if (b > max_blocks) b = max_blocks;
@@ -366,6 +382,12 @@ int swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t M, int I, cu
     swiglu_bwd_kernel<<<grid_for(M * (I / 8)), 256, 0, st>>>((const __nv_bfloat16*)gu, (const __nv_bfloat16*)dact,
                                                             (__nv_bfloat16*)dgu, M, I);
     SF_CUDA_CHECK_LAUNCH("swiglu_bwd");
+    return 0;
+}
+int add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t st) {
+    if (n % 8) return set_error(-22, "add: n=%lld must be a multiple of 8", (long long)n);
+    add_bf16_kernel<<<grid_for(n / 8), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n / 8);
+    SF_CUDA_CHECK_LAUNCH("add_bf16");
     return 0;
 }
 int shift_left(const void* src, void* dst, int64_t B, int S, int H, cudaStream_t st) {

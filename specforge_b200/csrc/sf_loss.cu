@@ -248,33 +248,124 @@ __global__ void __launch_bounds__(512) loss_kernel(LossParams p) {
 }
 
 // Deterministic reduction of the per-row values into the step's metric slots.
-// metrics[step][0..7] = {ploss, acc_correct, acc_denom, acceptance_rate, accept_num, accept_den, loss_denom, 0}
+// metrics[step][0..7] = {ploss, acc_correct, acc_denom, acceptance_rate, accept_num, accept_den, loss_denom, kl_weight}
+// ploss follows core/lk_loss.py:83-99: lk_type 0: the KL term; 1 ("lambda"): w*kl + (1-w)*(1-a), w = kl_scale*exp(-kl_decay*a);
+// 2 ("alpha"): -mean_masked(log a_r).
 __global__ void __launch_bounds__(1024)
 metrics_reduce_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_accept,
                       const float* __restrict__ row_correct, const int* __restrict__ position_mask,
-                      const int* __restrict__ loss_mask, int B, int S, int step, float* __restrict__ metrics) {
+                      const int* __restrict__ loss_mask, int B, int S, int step, int lk_type, float kl_scale, float kl_decay,
+                      float* __restrict__ metrics) {
     __shared__ float red[32];
     const int64_t M = (int64_t)B * S;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
     for (int64_t r = threadIdx.x; r < M; r += blockDim.x) {
         const int s = (int)(r % S);
         a0 += row_loss[r];
-        a1 += row_accept[r];
+        const float acc = row_accept[r];
+        a1 += acc;
         a2 += row_correct[r];
-        if (s + step < S) { a3 += (float)position_mask[r + step]; a4 += (float)loss_mask[r + step]; }
+        if (s + step < S) {
+            const int pm = position_mask[r + step];
+            a3 += (float)pm; a4 += (float)loss_mask[r + step];
+            if (pm && acc > 0.f) a5 += logf(acc);
+        }
     }
     a0 = block_sum_f(a0, red); a1 = block_sum_f(a1, red); a2 = block_sum_f(a2, red);
-    a3 = block_sum_f(a3, red); a4 = block_sum_f(a4, red);
+    a3 = block_sum_f(a3, red); a4 = block_sum_f(a4, red); a5 = block_sum_f(a5, red);
     if (threadIdx.x == 0) {
         float* o = metrics + step * 8;
-        o[0] = a0 / (float)M;
+        const float kl = a0 / (float)M;
+        const float den = fmaxf(a3, 1e-8f);
+        const float rate = a1 / den;
+        float ploss = kl, w = 0.f;
+        if (lk_type == 1) { w = kl_scale * expf(-kl_decay * rate); ploss = w * kl + (1.f - w) * (1.f - rate); }
+        else if (lk_type == 2) { ploss = -(a5 / den); }
+        o[0] = ploss;
         o[1] = a2;
         o[2] = fmaxf(a4, 1e-6f);
-        o[3] = a1 / fmaxf(a3, 1e-8f);
+        o[3] = rate;
         o[4] = a1;
-        o[5] = fmaxf(a3, 1e-8f);
+        o[5] = den;
         o[6] = (float)M;
-        o[7] = 0.f;
+        o[7] = w;
+    }
+}
+
+// LK-loss gradient (second pass, only when lk_loss_type is set): d ploss / d logits written in place.
+//   a_r = sum_v min(pod_v, q_v),  d a_r / d x_v = q_v (1[q_v < pod_v] - s_r),  s_r = sum_u 1[q_u < pod_u] q_u
+//   lambda: g = w * dKL + -(1-w) * pm/den * d a_r        alpha: g = -pm / (den * a_r) * d a_r
+__global__ void __launch_bounds__(512) lk_grad_kernel(LossParams p, int lk_type, float step_weight, int64_t M,
+                                                      const float* __restrict__ metrics) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ float redv[32];
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / p.S), s = (int)(r % p.S);
+    const bool in_range = s + p.step < p.S;
+    const int pm = in_range ? p.position_mask[(int64_t)b * p.S + s + p.step] : 0;
+    __nv_bfloat16* grow = p.logits + r * p.ld;
+    const int nch = p.DV / 8;
+    if (pm == 0) {
+        for (int c = threadIdx.x; c < nch; c += blockDim.x) reinterpret_cast<uint4*>(grow)[c] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const uint4* xrow = p.use_smem ? reinterpret_cast<const uint4*>(smem_raw) : reinterpret_cast<const uint4*>(grow);
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        const uint4 u = reinterpret_cast<const uint4*>(grow)[c];
+        if (p.use_smem) reinterpret_cast<uint4*>(smem_raw)[c] = u;
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx = fmaxf(mx, f[e]);
+    }
+    const float m = block_max_f(mx, redv);
+    float d = 0.f;
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        float f[8];
+        unpack8(xrow[c], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d += __expf(f[e] - m);
+    }
+    d = block_sum_f(d, redv);
+    const float inv_d = 1.f / d;
+    const int64_t trow = (int64_t)b * (p.S + p.T) + s + p.step;
+    const float4* tp = reinterpret_cast<const float4*>(p.target_p + trow * p.DV);
+    const float4* pp = reinterpret_cast<const float4*>(p.pod + trow * p.DV);
+    float sum_p = 0.f, s_r = 0.f;
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        float f[8];
+        unpack8(xrow[c], f);
+        const float4 t0 = __ldg(tp + 2 * c), t1 = __ldg(tp + 2 * c + 1);
+        const float4 q0 = __ldg(pp + 2 * c), q1 = __ldg(pp + 2 * c + 1);
+        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        sum_p += t0.x + t0.y + t0.z + t0.w + t1.x + t1.y + t1.z + t1.w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float q = __expf(f[e] - m) * inv_d; if (q < qv[e]) s_r += q; }
+    }
+    sum_p = block_sum_f(sum_p, redv);
+    s_r = block_sum_f(s_r, redv);
+    const float* mt = metrics + p.step * 8;
+    const float den = mt[5], w = mt[7];
+    const float a_r = p.row_accept[r];
+    float ck, ca;
+    if (lk_type == 1) { ck = w * step_weight / (float)M; ca = -(1.f - w) * step_weight / den; }
+    else { ck = 0.f; ca = (a_r > 0.f) ? -step_weight / (den * a_r) : 0.f; }
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        float f[8], o[8];
+        unpack8(xrow[c], f);
+        const float4 t0 = __ldg(tp + 2 * c), t1 = __ldg(tp + 2 * c + 1);
+        const float4 q0 = __ldg(pp + 2 * c), q1 = __ldg(pp + 2 * c + 1);
+        const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float q = __expf(f[e] - m) * inv_d;
+            o[e] = ck * (q * sum_p - tv[e]) + ca * q * ((q < qv[e] ? 1.f : 0.f) - s_r);
+        }
+        uint4 ou;
+        ou.x = pack_bf16x2(o[0], o[1]); ou.y = pack_bf16x2(o[2], o[3]); ou.z = pack_bf16x2(o[4], o[5]); ou.w = pack_bf16x2(o[6], o[7]);
+        reinterpret_cast<uint4*>(grow)[c] = ou;
     }
 }
 
@@ -381,13 +472,14 @@ int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, 
 
 int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod, const int64_t* tgt_ids,
               const int* position_mask, const int* loss_mask, const int64_t* d2t, int B, int S, int T, int DV, int step,
-              float grad_coef, int write_grad, float* row_ws, float* metrics, cudaStream_t st) {
+              float step_weight, int write_grad, int lk_type, float kl_scale, float kl_decay, float* row_ws, float* metrics,
+              cudaStream_t st) {
     if (DV % 8 || ld % 8) return set_error(-22, "loss: draft vocab %d / ld must be multiples of 8", DV);
     LossParams p;
     p.logits = (__nv_bfloat16*)logits; p.ld = ld; p.target_p = target_p; p.pod = pod; p.tgt_ids = tgt_ids;
     p.position_mask = position_mask; p.loss_mask = loss_mask; p.d2t = d2t; p.S = S; p.T = T; p.DV = DV; p.step = step;
-    p.grad_coef = grad_coef; p.write_grad = write_grad;
     const int64_t M = (int64_t)B * S;
+    p.grad_coef = step_weight / (float)M; p.write_grad = (lk_type == 0) ? write_grad : 0;
     p.row_loss = row_ws; p.row_accept = row_ws + M; p.row_correct = row_ws + 2 * M;
     int smem = DV * 2;
     p.use_smem = smem <= 100 * 1024;
@@ -397,8 +489,14 @@ int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod,
     loss_kernel<<<(unsigned)M, 512, smem, st>>>(p);
     SF_CUDA_CHECK_LAUNCH("loss");
     metrics_reduce_kernel<<<1, 1024, 0, st>>>(p.row_loss, p.row_accept, p.row_correct, position_mask, loss_mask, B, S, step,
-                                             metrics);
+                                             lk_type, kl_scale, kl_decay, metrics);
     SF_CUDA_CHECK_LAUNCH("metrics_reduce");
+    if (lk_type != 0 && write_grad) {
+        static int smem_set2 = 0;
+        if (smem > smem_set2) { cudaFuncSetAttribute(lk_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set2 = smem; }
+        lk_grad_kernel<<<(unsigned)M, 512, smem, st>>>(p, lk_type, step_weight, M, metrics);
+        SF_CUDA_CHECK_LAUNCH("lk_grad");
+    }
     return 0;
 }
 

@@ -46,6 +46,7 @@ class SfConfig(Structure):
         ("target_hidden", c_int32), ("intermediate", c_int32), ("num_heads", c_int32), ("num_kv_heads", c_int32),
         ("head_dim", c_int32), ("vocab", c_int32), ("draft_vocab", c_int32), ("fc_norm", c_int32),
         ("norm_output", c_int32), ("rope_rows", c_int32), ("rms_eps", c_float), ("ploss_decay", c_float),
+        ("lk_loss_type", c_int32), ("kl_scale", c_float), ("kl_decay", c_float),
     ]
 
 
@@ -119,20 +120,26 @@ def rope_tables(dims: DraftDims, rows: int, device) -> tuple:
 
 
 class Eagle3Engine:
+    LK_TYPES = {None: 0, "lambda": 1, "alpha": 2}
+
     def __init__(self, dims: DraftDims, *, batch: int, seq_len: int, ttt_length: int = 7, ploss_decay: float = 0.8,
+                 lk_loss_type: Optional[str] = None, kl_scale: float = 1.0, kl_decay: float = 1.0,
                  device: Optional[torch.device] = None):
         _declare()
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         if device.type != "cuda":
             raise RuntimeError("specforge_b200 has no CPU path: a CUDA (sm_100a) device is required")
+        if lk_loss_type not in self.LK_TYPES:
+            raise ValueError(f"Unknown lk loss type: {lk_loss_type}")
         self.dims, self.device = dims, device
         self.B, self.S, self.T = batch, seq_len, ttt_length
         self.ploss_decay = ploss_decay
         rope_rows = max(dims.max_position_embeddings + 20, seq_len + ttt_length)
         self.cfg = SfConfig(batch, seq_len, ttt_length, dims.hidden_size, dims.target_hidden_size, dims.intermediate_size,
                             dims.num_heads, dims.num_kv_heads, dims.head_dim, dims.vocab_size, dims.draft_vocab_size,
-                            int(dims.fc_norm), int(dims.norm_output), rope_rows, dims.rms_norm_eps, ploss_decay)
+                            int(dims.fc_norm), int(dims.norm_output), rope_rows, dims.rms_norm_eps, ploss_decay,
+                            self.LK_TYPES[lk_loss_type], kl_scale, kl_decay)
         offs = (c_int64 * P_COUNT)()
         sizes = (c_int64 * P_COUNT)()
         total = c_int64()

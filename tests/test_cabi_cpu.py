@@ -31,7 +31,7 @@ def test_param_layout_and_workspace(L):
     from ctypes import c_int64
     _declare()
     # Qwen3-8B EAGLE3 draft (configs/qwen3-8b-eagle3.json): 399.52 M trainable parameters
-    cfg = SfConfig(8, 2048, 7, 4096, 4096, 12288, 32, 8, 128, 151936, 32000, 0, 1, 40980, 1e-6, 0.8)
+    cfg = SfConfig(8, 2048, 7, 4096, 4096, 12288, 32, 8, 128, 151936, 32000, 0, 1, 40980, 1e-6, 0.8, 0, 1.0, 1.0)
     offs, sizes, total = (c_int64 * P_COUNT)(), (c_int64 * P_COUNT)(), c_int64()
     assert L.sf_eagle3_param_layout(cfg, offs, sizes, ctypes.byref(total)) == 0
     assert total.value == 399_523_840 + 0 or abs(total.value - 399.52e6) < 0.01e6
@@ -40,7 +40,7 @@ def test_param_layout_and_workspace(L):
     assert offs[6] == offs[5] + sizes[5]
     ws = L.sf_eagle3_workspace_bytes(cfg)
     assert 20e9 < ws < 80e9, ws
-    bad = SfConfig(8, 2048, 7, 4096, 4096, 12288, 32, 8, 96, 151936, 32000, 0, 1, 40980, 1e-6, 0.8)
+    bad = SfConfig(8, 2048, 7, 4096, 4096, 12288, 32, 8, 96, 151936, 32000, 0, 1, 40980, 1e-6, 0.8, 0, 1.0, 1.0)
     assert L.sf_eagle3_workspace_bytes(bad) == 0
     assert b"head_dim" in L.sf_last_error()
 

@@ -21,8 +21,10 @@ def _engine_for(gold):
     dims = DraftDims(hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size, num_heads=cfg.num_heads,
                      num_kv_heads=cfg.num_kv_heads, head_dim=cfg.head_dim, vocab_size=cfg.vocab_size,
                      draft_vocab_size=cfg.draft_vocab_size, rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta,
-                     max_position_embeddings=cfg.max_position_embeddings)
-    eng = Eagle3Engine(dims, batch=gold["B"], seq_len=gold["S"], ttt_length=cfg.ttt_length)
+                     max_position_embeddings=cfg.max_position_embeddings, target_hidden_size=cfg.target_hidden_size,
+                     fc_norm=cfg.fc_norm, norm_output=cfg.norm_output)
+    eng = Eagle3Engine(dims, batch=gold["B"], seq_len=gold["S"], ttt_length=cfg.ttt_length,
+                       lk_loss_type=gold.get("lk_loss_type"))
     P = O.init_params(cfg, seed=0)
     t2d, d2t = O.make_vocab_map(cfg.vocab_size, cfg.draft_vocab_size, seed=0)
     g = torch.Generator().manual_seed(gold["head_seed"])
@@ -33,7 +35,8 @@ def _engine_for(gold):
     return eng, cfg, P, batch, head_w, t2d, d2t
 
 
-@pytest.mark.parametrize("case", ["small_d128", "qwen25_05b_cfg1"])
+@pytest.mark.parametrize("case", ["small_d128", "qwen25_05b_cfg1", "small_lk_lambda", "small_lk_alpha", "small_fcnorm",
+                                  "small_nonorm"])
 def test_step_matches_reference_golden(case):
     gold = torch.load(os.path.join(GOLD_DIR, f"eagle3_{case}.pt"))
     eng, cfg, P, batch, *_ = _engine_for(gold)
