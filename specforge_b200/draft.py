@@ -26,15 +26,15 @@ def dims_from_config(config: Any) -> DraftDims:
     head_dim = get("head_dim") or H // nh
     rope_params = get("rope_parameters")
     theta = rope_params["rope_theta"] if rope_params else get("rope_theta", 10000.0)
-    scaling = get("rope_scaling")
-    if scaling and (scaling.get("rope_type", scaling.get("type")) not in (None, "default")):
-        raise NotImplementedError(f"rope_scaling={scaling!r}: only default RoPE is implemented on the CUDA path")
+    scaling = get("rope_scaling") or (rope_params if rope_params and rope_params.get("rope_type") not in (None, "default") else None)
+    if scaling and scaling.get("rope_type", scaling.get("type")) == "mrope":
+        raise NotImplementedError("mrope (three-axis multimodal positions) is not implemented on the CUDA path")
     return DraftDims(hidden_size=H, intermediate_size=get("intermediate_size"), num_heads=nh,
                      num_kv_heads=get("num_key_value_heads", nh), head_dim=head_dim, vocab_size=get("vocab_size"),
                      draft_vocab_size=get("draft_vocab_size"), target_hidden_size=get("target_hidden_size", H),
                      rms_norm_eps=get("rms_norm_eps", 1e-6), rope_theta=float(theta),
                      max_position_embeddings=get("max_position_embeddings", 2048), fc_norm=bool(get("fc_norm", False)),
-                     norm_output=bool(get("norm_output", True)))
+                     norm_output=bool(get("norm_output", True)), rope_scaling=dict(scaling) if scaling else None)
 
 
 class B200Eagle3DraftModel(nn.Module):

@@ -102,21 +102,80 @@ class DraftDims:
     max_position_embeddings: int = 2048
     fc_norm: bool = False
     norm_output: bool = True
+    rope_scaling: Optional[dict] = None
 
     def __post_init__(self):
         if self.target_hidden_size is None:
             self.target_hidden_size = self.hidden_size
 
 
-def rope_tables(dims: DraftDims, rows: int, device) -> tuple:
-    """cos/sin tables exactly as LlamaRotaryEmbedding builds them (llama3_eagle.py:218-301): fp32 math, then the
-    module-wide .to(bfloat16) (algorithms/model_providers.py:112).  `rows` >= S + T."""
-    d = dims.head_dim
-    inv_freq = 1.0 / (dims.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
-    t = torch.arange(rows, dtype=torch.float32)
-    freqs = torch.einsum("i,j->ij", t, inv_freq)
+def _rope_inv_freq_and_scale(dims: "DraftDims", rows: int):
+    """inv_freq / position divisor / table multiplier for every RoPE flavour the reference supports through
+    `rope_scaling` (llama3_eagle.py:218-536), restated: default, "linear", "dynamic" (NTK), "llama3", "yarn".
+    "mrope" (three-axis multimodal positions) is not a table transform and is not implemented."""
+    d, base = dims.head_dim, float(dims.rope_theta)
+    idx = torch.arange(0, d, 2, dtype=torch.float32)
+    inv_freq = 1.0 / (base ** (idx / d))
+    t_div, mult = 1.0, 1.0
+    sc = dims.rope_scaling
+    if not sc:
+        return inv_freq, t_div, mult
+    kind = sc.get("rope_type", sc.get("type"))
+    factor = sc.get("factor")
+    if kind in (None, "default"):
+        pass
+    elif kind == "linear":
+        if factor is None:
+            raise ValueError("Linear RoPE scaling requires 'factor' in rope_scaling config.")
+        t_div = float(factor)
+    elif kind == "dynamic":
+        if factor is None:
+            raise ValueError("Dynamic RoPE scaling requires 'factor' in rope_scaling config.")
+        if rows > dims.max_position_embeddings:      # NTK: the base grows with the cached length
+            nb = base * ((factor * rows / dims.max_position_embeddings) - (factor - 1)) ** (d / (d - 2))
+            inv_freq = 1.0 / (nb ** (idx / d))
+    elif kind == "llama3":
+        f = 1.0 if factor is None else float(factor)
+        lo, hi, orig = sc.get("low_freq_factor"), sc.get("high_freq_factor"), sc.get("original_max_position_embeddings")
+        if None not in (lo, hi, orig):
+            wave = 2 * math.pi / inv_freq
+            smooth = (orig / wave - lo) / (hi - lo) if lo != hi else 0
+            mid = (1 - smooth) * inv_freq / f + smooth * inv_freq
+            inv_freq = torch.where(wave < orig / hi, inv_freq, torch.where(wave > orig / lo, inv_freq / f, mid))
+    elif kind == "yarn":
+        f = float(factor)
+        orig = sc.get("original_max_position_embeddings")
+        bf, bs = sc.get("beta_fast") or 32, sc.get("beta_slow") or 1
+        ms, msa = sc.get("mscale") or 1, sc.get("mscale_all_dim") or 0
+
+        def corr_dim(rot):
+            return (d * math.log(orig / (rot * 2 * math.pi))) / (2 * math.log(base))
+
+        low, high = max(math.floor(corr_dim(bf)), 0), min(math.ceil(corr_dim(bs)), d - 1)
+        if low == high:
+            high += 0.001
+        ramp = torch.clamp((torch.arange(d // 2, dtype=torch.float32) - low) / (high - low), 0, 1)
+        keep = 1.0 - ramp
+        inv_freq = (inv_freq / f) * (1 - keep) + inv_freq * keep
+
+        def mscale(scale, m):
+            return 1.0 if scale <= 1 else 0.1 * m * math.log(scale) + 1.0
+
+        mult = float(mscale(f, ms) / mscale(f, msa))
+    else:
+        raise NotImplementedError(f"rope_scaling type {kind!r} is not implemented on the CUDA path")
+    return inv_freq, t_div, mult
+
+
+def rope_tables(dims: "DraftDims", rows: int, device) -> tuple:
+    """cos/sin tables as the reference's rotary modules build them (fp32 math) followed by the module-wide
+    .to(bfloat16) (algorithms/model_providers.py:112).  `rows` >= S + T."""
+    inv_freq, t_div, mult = _rope_inv_freq_and_scale(dims, rows)
+    t = torch.arange(rows, dtype=torch.float32) / t_div
+    freqs = torch.outer(t, inv_freq)
     emb = torch.cat((freqs, freqs), dim=-1)
-    return emb.cos().to(torch.bfloat16).to(device).contiguous(), emb.sin().to(torch.bfloat16).to(device).contiguous()
+    cos, sin = emb.cos() * mult, emb.sin() * mult
+    return cos.to(torch.bfloat16).to(device).contiguous(), sin.to(torch.bfloat16).to(device).contiguous()
 
 
 class Eagle3Engine:
