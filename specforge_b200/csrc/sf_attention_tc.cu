@@ -49,12 +49,12 @@ struct FwdCfg {
     static constexpr int Q_BYTES = BQ * D * 2;                  // per head
     static constexpr int KV_BYTES = BKV * D * 2;
     static constexpr int P_BYTES = BQ * BKV * 2;
-    static constexpr int kStages = 2;
+    static constexpr int kStages = 4;         // K and V rings: loads run 3 tiles ahead of the MMAs (TMA latency >> one tile)
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = 2 * Q_BYTES;
     static constexpr int OFF_V = OFF_K + kStages * KV_BYTES;
-    static constexpr int OFF_P = OFF_V + kStages * KV_BYTES;   // [head][buf]
-    static constexpr int OFF_BAR = OFF_P + 4 * P_BYTES;
+    static constexpr int OFF_P = OFF_V + kStages * KV_BYTES;   // [head], single-buffered
+    static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
     static constexpr int SMEM = OFF_BAR + 512 + 1024;
     static constexpr int TM_S = 0;            // S[head][buf] at col (head*2+buf)*64
     static constexpr int TM_O = 256;          // O[head] at 256 + head*D  (accumulated across kv tiles)
@@ -75,13 +75,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t bar0 = sbase + C::OFF_BAR;
     const uint32_t b_qfull = bar0;
     auto b_kfull = [&](int s) { return bar0 + 8u * (1 + s); };
-    auto b_kempty = [&](int s) { return bar0 + 8u * (3 + s); };
-    auto b_vfull = [&](int s) { return bar0 + 8u * (5 + s); };
-    auto b_vempty = [&](int s) { return bar0 + 8u * (7 + s); };
-    auto b_sfull = [&](int x, int u) { return bar0 + 8u * (9 + x * 2 + u); };
-    auto b_pfull = [&](int x, int u) { return bar0 + 8u * (13 + x * 2 + u); };
-    auto b_pvdone = [&](int x, int u) { return bar0 + 8u * (17 + x * 2 + u); };
-    const uint32_t tmem_slot = bar0 + 8u * 21;
+    auto b_kempty = [&](int s) { return bar0 + 8u * (5 + s); };
+    auto b_vfull = [&](int s) { return bar0 + 8u * (9 + s); };
+    auto b_vempty = [&](int s) { return bar0 + 8u * (13 + s); };
+    auto b_sfull = [&](int x, int u) { return bar0 + 8u * (17 + x * 2 + u); };
+    auto b_pfull = [&](int x) { return bar0 + 8u * (21 + x); };
+    auto b_pvdone = [&](int x) { return bar0 + 8u * (23 + x); };
+    const uint32_t tmem_slot = bar0 + 8u * 25;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = gridDim.x - 1 - blockIdx.x;
@@ -99,16 +99,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); }
     if (warp == 1 && lane == 0) {
         mbar_init(b_qfull, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(b_kfull(s), 1); mbar_init(b_kempty(s), 1); mbar_init(b_vfull(s), 1); mbar_init(b_vempty(s), 1); }
-        for (int x = 0; x < 2; ++x)
-            for (int u = 0; u < 2; ++u) { mbar_init(b_sfull(x, u), 1); mbar_init(b_pfull(x, u), 4); mbar_init(b_pvdone(x, u), 1); }
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(b_kfull(s), 1); mbar_init(b_kempty(s), 1); mbar_init(b_vfull(s), 1); mbar_init(b_vempty(s), 1); }
+        for (int x = 0; x < 2; ++x) {
+            for (int u = 0; u < 2; ++u) mbar_init(b_sfull(x, u), 1);
+            mbar_init(b_pfull(x), 4); mbar_init(b_pvdone(x), 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 21);
+    const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 25);
 
     if (warp < 4) {
         reg_dec<40>();
@@ -120,14 +122,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     tma_load_3d(sbase + C::OFF_Q + x * C::Q_BYTES + kb * (C::BQ * 128), &tm_q, b_qfull,
                                 p.q_col0 + (h0 + x) * D + kb * 64, q0, b);
             for (int t = 0; t < n_kv; ++t) {
-                const int s = t & 1;
-                const uint32_t ph = ((t >> 1) & 1) ^ 1u;
-                mbar_wait(b_kempty(s), ph, 11);
+                const int s = t % C::kStages;
+                mbar_wait(b_kempty(s), ((t / C::kStages) & 1) ^ 1u, 11);
                 mbar_expect_tx(b_kfull(s), C::KV_BYTES);
                 for (int kb = 0; kb < C::NB; ++kb)
                     tma_load_3d(sbase + C::OFF_K + s * C::KV_BYTES + kb * (C::BKV * 128), &tm_kv, b_kfull(s),
                                 p.k_col0 + kvh * D + kb * 64, t * C::BKV, b);
-                mbar_wait(b_vempty(s), ph, 12);
+            }
+        } else if (warp == 3 && lane == 0) {
+            // ================= V producer (own thread: a late PV never delays the K loads) =================
+            for (int t = 0; t < n_kv; ++t) {
+                const int s = t % C::kStages;
+                mbar_wait(b_vempty(s), ((t / C::kStages) & 1) ^ 1u, 12);
                 mbar_expect_tx(b_vfull(s), C::KV_BYTES);
                 for (int kb = 0; kb < C::NB; ++kb)
                     tma_load_3d(sbase + C::OFF_V + s * C::KV_BYTES + kb * (C::BKV * 128), &tm_kv, b_vfull(s),
@@ -138,8 +144,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             constexpr uint32_t idesc_s = make_idesc_bf16(128, C::BKV, 0, 0);   // S[128 x 64]  = Q(K-major) K^T(K-major)
             constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O[128 x D]  += P(K-major) V(MN-major)
             auto issue_s = [&](int t) {
-                const int s = t & 1, u = t & 1;
-                mbar_wait(b_kfull(s), (t >> 1) & 1, 17);
+                const int s = t % C::kStages, u = t & 1;
+                mbar_wait(b_kfull(s), (t / C::kStages) & 1, 17);
                 tc_fence_after();
                 const uint32_t sk = sbase + C::OFF_K + s * C::KV_BYTES;
                 for (int x = 0; x < nx; ++x) {
@@ -163,20 +169,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             issue_s(0);
             for (int t = 0; t < n_kv; ++t) {
                 if (t + 1 < n_kv) issue_s(t + 1);
-                const int s = t & 1, u = t & 1;
-                mbar_wait(b_vfull(s), (t >> 1) & 1, 15);
+                const int s = t % C::kStages;
+                mbar_wait(b_vfull(s), (t / C::kStages) & 1, 15);
                 const uint32_t sv = sbase + C::OFF_V + s * C::KV_BYTES;
                 for (int x = 0; x < nx; ++x) {
-                    mbar_wait(b_pfull(x, u), (t >> 1) & 1, 14);
+                    mbar_wait(b_pfull(x), t & 1, 14);
                     tc_fence_after();
-                    const uint32_t sp = sbase + C::OFF_P + (x * 2 + u) * C::P_BYTES;
+                    const uint32_t sp = sbase + C::OFF_P + x * C::P_BYTES;
                     const uint64_t adesc = make_smem_desc_sw128(sp, 0, 1024);
                     const uint64_t bdesc = make_smem_desc_sw128(sv, C::BKV * 128, 1024);   // MN-major: LBO = 64-col block stride
 #pragma unroll
                     for (int k = 0; k < C::BKV / 16; ++k)
                         umma_bf16<1>(tmem + C::TM_O + x * D, adesc + ((k * 32) >> 4), bdesc + ((k * 2048) >> 4), idesc_o,
                                      (t | k) != 0);
-                    umma_commit(b_pvdone(x, u));
+                    umma_commit(b_pvdone(x));
                 }
                 umma_commit(b_vempty(s));
             }
@@ -233,7 +239,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     m_ref = m_new;
                     if (t > 0) {
                         // O holds tiles < t: PV(t-1) must have landed before it is rescaled
-                        mbar_wait(b_pvdone(x, (t - 1) & 1), ((t - 1) >> 1) & 1, 26 + x);
+                        mbar_wait(b_pvdone(x), (t - 1) & 1, 26 + x);
                         tc_fence_after();
 #pragma unroll
                         for (int cc = 0; cc < D / 32; ++cc) {
@@ -248,9 +254,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     }
                 }
                 const float base = (m_ref == -INFINITY) ? 0.f : m_ref;
-                // P buffer u must have been consumed by PV(t-2)
-                mbar_wait(b_pvdone(x, u), ((t >> 1) & 1) ^ 1u, 24 + x);
-                uint8_t* sp = sgen + C::OFF_P + (x * 2 + u) * C::P_BYTES;
+                // the (single) P buffer must have been consumed by PV(t-1)
+                if (t > 0) mbar_wait(b_pvdone(x), (t - 1) & 1, 24 + x);
+                uint8_t* sp = sgen + C::OFF_P + x * C::P_BYTES;
                 float rs = 0.f;
 #pragma unroll
                 for (int j = 0; j < C::BKV / 8; ++j) {
@@ -266,10 +272,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(b_pfull(x, u));
+                if (lane == 0) mbar_arrive(b_pfull(x));
             }
             // ---- epilogue: O from TMEM, diagonal P*V terms (never masked), normalise, store
-            mbar_wait(b_pvdone(x, (n_kv - 1) & 1), ((n_kv - 1) >> 1) & 1, 28 + x);
+            mbar_wait(b_pvdone(x), (n_kv - 1) & 1, 28 + x);
             tc_fence_after();
             const float inv = (l > 0.f) ? 1.f / l : 0.f;
             __nv_bfloat16* orow = p.out + ((int64_t)b * p.S + min(row, p.S - 1)) * p.ldo + h * D;

@@ -33,7 +33,7 @@ struct AttnBwdTcParams {
 // ============================================================================================ dK / dV
 template <int D>
 struct DkvCfg {
-    static constexpr int BK = 128, BQ = 64, NB = D / 64, kStages = 3;
+    static constexpr int BK = 128, BQ = 64, NB = D / 64, kStages = 4;   // Q/dO ring: loads run 3 tiles ahead (TMA latency)
     static constexpr int KT_BYTES = BK * D * 2;            // K (or V) tile
     static constexpr int QT_BYTES = BQ * D * 2;            // Q (or dO) stage
     static constexpr int PT_BYTES = BK * BQ * 2;           // P^T (or dS^T) tile
@@ -58,13 +58,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t bar0 = sbase + C::OFF_BAR;
     const uint32_t b_kvfull = bar0;
     auto b_qfull = [&](int s) { return bar0 + 8u * (1 + s); };
-    auto b_qempty = [&](int s) { return bar0 + 8u * (4 + s); };
-    auto b_sdpfull = [&](int u) { return bar0 + 8u * (7 + u); };
-    const uint32_t b_pdsfull = bar0 + 8u * 9;
-    const uint32_t b_mmadone = bar0 + 8u * 10;
-    const uint32_t tmem_slot = bar0 + 8u * 11;
-    auto b_ldfull = [&](int u) { return bar0 + 8u * (12 + u); };
-    auto b_ldempty = [&](int u) { return bar0 + 8u * (14 + u); };
+    auto b_qempty = [&](int s) { return bar0 + 8u * (5 + s); };
+    auto b_sdpfull = [&](int u) { return bar0 + 8u * (9 + u); };
+    const uint32_t b_pdsfull = bar0 + 8u * 11;
+    const uint32_t b_mmadone = bar0 + 8u * 12;
+    const uint32_t tmem_slot = bar0 + 8u * 13;
+    auto b_ldfull = [&](int u) { return bar0 + 8u * (14 + u); };
+    auto b_ldempty = [&](int u) { return bar0 + 8u * (16 + u); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -92,7 +92,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 11);
+    const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 13);
 
     if (warp < 4) {
         if (warp == 3) {
@@ -279,7 +279,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 // ============================================================================================ dQ
 template <int D>
 struct DqCfg {
-    static constexpr int BQ = 128, BKV = 64, NB = D / 64, kKStages = 3, kVStages = 2;
+    static constexpr int BQ = 128, BKV = 64, NB = D / 64, kKStages = 5, kVStages = 4;
     static constexpr int QT_BYTES = BQ * D * 2;
     static constexpr int KT_BYTES = BKV * D * 2;
     static constexpr int DS_BYTES = BQ * BKV * 2;
@@ -303,13 +303,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const uint32_t bar0 = sbase + C::OFF_BAR;
     const uint32_t b_qfull = bar0;
     auto b_kfull = [&](int s) { return bar0 + 8u * (1 + s); };
-    auto b_kempty = [&](int s) { return bar0 + 8u * (4 + s); };
-    auto b_vfull = [&](int s) { return bar0 + 8u * (7 + s); };
-    auto b_vempty = [&](int s) { return bar0 + 8u * (9 + s); };
-    auto b_sdpfull = [&](int u) { return bar0 + 8u * (11 + u); };
-    const uint32_t b_dsfull = bar0 + 8u * 13;
-    const uint32_t b_mmadone = bar0 + 8u * 14;
-    const uint32_t tmem_slot = bar0 + 8u * 15;
+    auto b_kempty = [&](int s) { return bar0 + 8u * (6 + s); };
+    auto b_vfull = [&](int s) { return bar0 + 8u * (11 + s); };
+    auto b_vempty = [&](int s) { return bar0 + 8u * (15 + s); };
+    auto b_sdpfull = [&](int u) { return bar0 + 8u * (19 + u); };
+    const uint32_t b_dsfull = bar0 + 8u * 21;
+    const uint32_t b_mmadone = bar0 + 8u * 22;
+    const uint32_t tmem_slot = bar0 + 8u * 23;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = gridDim.x - 1 - blockIdx.x;
@@ -336,7 +336,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 15);
+    const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 23);
 
     if (warp < 4) {
         if (warp == 0 && lane == 0) {
@@ -346,12 +346,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 tma_load_3d(sbase + C::OFF_DO + kbk * (C::BQ * 128), &tm_do, b_qfull, h * D + kbk * 64, q0, b);
             }
             for (int t = 0; t < n_kv; ++t) {
-                const int sk = t % C::kKStages, sv = t % C::kVStages;
+                const int sk = t % C::kKStages;
                 mbar_wait(b_kempty(sk), ((t / C::kKStages) & 1) ^ 1u, 41);
                 mbar_expect_tx(b_kfull(sk), C::KT_BYTES);
                 for (int kbk = 0; kbk < C::NB; ++kbk)
                     tma_load_3d(sbase + C::OFF_K + sk * C::KT_BYTES + kbk * (C::BKV * 128), &tm_kv, b_kfull(sk),
                                 p.k_col0 + kvh * D + kbk * 64, t * C::BKV, b);
+            }
+        } else if (warp == 3 && lane == 0) {
+            for (int t = 0; t < n_kv; ++t) {
+                const int sv = t % C::kVStages;
                 mbar_wait(b_vempty(sv), ((t / C::kVStages) & 1) ^ 1u, 42);
                 mbar_expect_tx(b_vfull(sv), C::KT_BYTES);
                 for (int kbk = 0; kbk < C::NB; ++kbk)
