@@ -163,9 +163,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             };
             mbar_wait(b_kvfull, 0, 32);
             tc_fence_after();
+            // tcgen05.mma issue blocks while the in-order tensor queue is full: never sit inside a long S^T/dP^T batch
+            // while a finished P^T/dS^T tile waits.  S^T/dP^T run two tiles ahead; the accumulate MMAs go first.
             issue_sdp(0);
+            if (n_it > 1) issue_sdp(1);
             for (int it = 0; it < n_it; ++it) {
-                if (it + 1 < n_it) issue_sdp(it + 1);
                 const int s = it % C::kStages;
                 mbar_wait(b_pdsfull, it & 1, 34);
                 tc_fence_after();
@@ -183,6 +185,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                     umma_bf16<1>(tmem + C::TM_DK, ads + ((k * 32) >> 4), bq + ((k * 2048) >> 4), idesc_acc, (it | k) != 0);
                 umma_commit(b_mmadone);
                 umma_commit(b_qempty(s));
+                if (it + 2 < n_it) issue_sdp(it + 2);
             }
         }
     } else {
@@ -392,8 +395,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             mbar_wait(b_qfull, 0, 45);
             tc_fence_after();
             issue_sdp(0);
+            if (n_kv > 1) issue_sdp(1);
             for (int t = 0; t < n_kv; ++t) {
-                if (t + 1 < n_kv) issue_sdp(t + 1);
                 const int sk = t % C::kKStages;
                 mbar_wait(b_dsfull, t & 1, 46);
                 tc_fence_after();
@@ -404,6 +407,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     umma_bf16<1>(tmem + C::TM_DQ, ads + ((k * 32) >> 4), bk + ((k * 2048) >> 4), idesc_dq, (t | k) != 0);
                 umma_commit(b_mmadone);
                 umma_commit(b_kempty(sk));
+                if (t + 2 < n_kv) issue_sdp(t + 2);
             }
         }
     } else {
