@@ -102,7 +102,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); }
     if (warp == 1 && lane == 0) {
         mbar_init(b_qfull, 1);
-        for (int s = 0; s < C::kStages; ++s) { mbar_init(b_kfull(s), 1); mbar_init(b_kempty(s), 1); mbar_init(b_vfull(s), 1); mbar_init(b_vempty(s), 1); }
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(b_kfull(s), 1); mbar_init(b_kempty(s), nx); mbar_init(b_vfull(s), 1); mbar_init(b_vempty(s), nx); }
         for (int x = 0; x < 2; ++x) {
             for (int u = 0; u < 2; ++u) mbar_init(b_sfull(x, u), 1);
             mbar_init(b_pfull(x), 4); mbar_init(b_pvdone(x), 1);
@@ -142,16 +142,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     tma_load_3d(sbase + C::OFF_V + s * C::KV_BYTES + kb * (C::BKV * 128), &tm_kv, b_vfull(s),
                                 p.v_col0 + kvh * D + kb * 64, t * C::BKV, b);
             }
-        } else if (warp == 1 && lane == 0) {
-            // ================= MMA issuer =================
+        } else if ((warp == 1 || warp == 2) && lane == 0 && (warp - 1) < nx) {
+            // ================= MMA issuers: one thread per head =================
+            // tcgen05.mma issue blocks while the in-order tensor queue is full, so one thread serving two heads would
+            // sit inside one head's S batch while the other head's finished P tile waits.  Each head gets its own
+            // issuer (ordering is only needed within a head): PV_x(t) the moment P_x(t) lands, then S_x(t+2) into the
+            // S buffer head x just finished reading.  K/V ring stages are released by both issuers (barrier count nx).
+            const int x = warp - 1;
             constexpr uint32_t idesc_s = make_idesc_bf16(128, C::BKV, 0, 0);   // S[128 x 64]  = Q(K-major) K^T(K-major)
             constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O[128 x D]  += P(K-major) V(MN-major)
-            // S_x(t) = Q_x K_t^T into S buffer (t & 1) of head x
-            auto issue_s = [&](int x, int t) {
+            const uint32_t sq = sbase + C::OFF_Q + x * C::Q_BYTES;
+            auto issue_s = [&](int t) {
                 const int s = t % C::kStages, u = t & 1;
-                if (x == 0) { mbar_wait(b_kfull(s), (t / C::kStages) & 1, 17); tc_fence_after(); }
+                mbar_wait(b_kfull(s), (t / C::kStages) & 1, 17);
+                tc_fence_after();
                 const uint32_t sk = sbase + C::OFF_K + s * C::KV_BYTES;
-                const uint32_t sq = sbase + C::OFF_Q + x * C::Q_BYTES;
 #pragma unroll
                 for (int kb = 0; kb < C::NB; ++kb) {
                     const uint64_t adesc = make_smem_desc_sw128(sq + kb * (C::BQ * 128), 0, 1024);
@@ -162,34 +167,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                                      idesc_s, (kb | k) != 0);
                 }
                 umma_commit(b_sfull(x, u));
-                if (x == nx - 1) umma_commit(b_kempty(s));
+                umma_commit(b_kempty(s));
             };
             mbar_wait(b_qfull, 0, 13);
             tc_fence_after();
-            // Issue order matters: tcgen05.mma issue blocks while the (in-order) tensor queue is full, so the issuer
-            // must never sit inside a long S batch while a finished P tile waits.  S runs TWO tiles ahead (both S
-            // buffers primed here); inside the loop each head gets PV(t) the moment its P(t) lands, then S(t+2) into the
-            // buffer that head just finished reading.
-            for (int x = 0; x < nx; ++x) issue_s(x, 0);
-            if (n_kv > 1) for (int x = 0; x < nx; ++x) issue_s(x, 1);
+            issue_s(0);
+            if (n_kv > 1) issue_s(1);
             for (int t = 0; t < n_kv; ++t) {
                 const int s = t % C::kStages;
                 mbar_wait(b_vfull(s), (t / C::kStages) & 1, 15);
+                mbar_wait(b_pfull(x), t & 1, 14);
+                tc_fence_after();
+                const uint32_t sp = sbase + C::OFF_P + x * C::P_BYTES;
                 const uint32_t sv = sbase + C::OFF_V + s * C::KV_BYTES;
-                for (int x = 0; x < nx; ++x) {
-                    mbar_wait(b_pfull(x), t & 1, 14);
-                    tc_fence_after();
-                    const uint32_t sp = sbase + C::OFF_P + x * C::P_BYTES;
-                    const uint64_t adesc = make_smem_desc_sw128(sp, 0, 1024);
-                    const uint64_t bdesc = make_smem_desc_sw128(sv, C::BKV * 128, 1024);   // MN-major: LBO = 64-col block stride
+                const uint64_t adesc = make_smem_desc_sw128(sp, 0, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(sv, C::BKV * 128, 1024);   // MN-major: LBO = 64-col block stride
 #pragma unroll
-                    for (int k = 0; k < C::BKV / 16; ++k)
-                        umma_bf16<1>(tmem + C::TM_O + x * D, adesc + ((k * 32) >> 4), bdesc + ((k * 2048) >> 4), idesc_o,
-                                     (t | k) != 0);
-                    umma_commit(b_pvdone(x));
-                    if (x == nx - 1) umma_commit(b_vempty(s));
-                    if (t + 2 < n_kv) issue_s(x, t + 2);   // head x has finished reading S_x(t): its buffer is free
-                }
+                for (int k = 0; k < C::BKV / 16; ++k)
+                    umma_bf16<1>(tmem + C::TM_O + x * D, adesc + ((k * 32) >> 4), bdesc + ((k * 2048) >> 4), idesc_o, (t | k) != 0);
+                umma_commit(b_pvdone(x));
+                umma_commit(b_vempty(s));
+                if (t + 2 < n_kv) issue_s(t + 2);
             }
         }
     } else {

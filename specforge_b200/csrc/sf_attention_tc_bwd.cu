@@ -65,6 +65,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t tmem_slot = bar0 + 8u * 13;
     auto b_ldfull = [&](int u) { return bar0 + 8u * (14 + u); };
     auto b_ldempty = [&](int u) { return bar0 + 8u * (16 + u); };
+    auto b_sdpfree = [&](int u) { return bar0 + 8u * (18 + u); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -83,7 +84,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     if (warp == 1 && lane == 0) {
         mbar_init(b_kvfull, 1);
         for (int s = 0; s < C::kStages; ++s) { mbar_init(b_qfull(s), 1); mbar_init(b_qempty(s), 1); }
-        for (int u = 0; u < 2; ++u) { mbar_init(b_sdpfull(u), 1); mbar_init(b_ldfull(u), 1); mbar_init(b_ldempty(u), 8); }
+        for (int u = 0; u < 2; ++u) { mbar_init(b_sdpfull(u), 1); mbar_init(b_ldfull(u), 1); mbar_init(b_ldempty(u), 8); mbar_init(b_sdpfree(u), 8); }
         mbar_init(b_pdsfull, 8);
         mbar_init(b_mmadone, 1);
         fence_mbar_init();
@@ -134,11 +135,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                 }
             }
         } else if (warp == 1 && lane == 0) {
-            // ================= MMA issuer =================
-            constexpr uint32_t idesc_st = make_idesc_bf16(128, C::BQ, 0, 0);   // S^T[128 keys x 64 q] = K(K-major) Q^T(K-major)
-            constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, 0, 1);      // dV/dK[128 x D]     += P^T(K-major) dO(MN-major)
-            auto issue_sdp = [&](int it) {
+            // ================= MMA issuer A: S^T = K Q^T, dP^T = V dO^T (runs ahead, double-buffered in TMEM) =========
+            // Two issuer threads because tcgen05.mma issue blocks while the in-order tensor queue is full: the thread
+            // that feeds S^T/dP^T batches must not delay the accumulate MMAs of a finished P^T/dS^T tile (issuer B).
+            constexpr uint32_t idesc_st = make_idesc_bf16(128, C::BQ, 0, 0);   // [128 keys x 64 q] = K(K-major) Q^T(K-major)
+            mbar_wait(b_kvfull, 0, 32);
+            tc_fence_after();
+            for (int it = 0; it < n_it; ++it) {
                 const int s = it % C::kStages, u = it & 1;
+                mbar_wait(b_sdpfree(u), ((it >> 1) & 1) ^ 1u, 39);     // warpgroups finished reading S^T/dP^T(it-2)
                 mbar_wait(b_qfull(s), (it / C::kStages) & 1, 33);
                 tc_fence_after();
                 const uint32_t sq = sbase + C::OFF_Q + s * 2 * C::QT_BYTES;
@@ -160,15 +165,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                         umma_bf16<1>(tmem + C::TM_DP + u * C::BQ, a + ((k * 32) >> 4), bd + ((k * 32) >> 4), idesc_st, (kbk | k) != 0);
                 }
                 umma_commit(b_sdpfull(u));
-            };
-            mbar_wait(b_kvfull, 0, 32);
-            tc_fence_after();
-            // tcgen05.mma issue blocks while the in-order tensor queue is full: never sit inside a long S^T/dP^T batch
-            // while a finished P^T/dS^T tile waits.  S^T/dP^T run two tiles ahead; the accumulate MMAs go first.
-            issue_sdp(0);
-            if (n_it > 1) issue_sdp(1);
+            }
+        } else if (warp == 2 && lane == 0) {
+            // ================= MMA issuer B: dV += P^T dO, dK += dS^T Q =================
+            constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, 0, 1);      // [128 x D] += A(K-major) B(MN-major)
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % C::kStages;
+                mbar_wait(b_qfull(s), (it / C::kStages) & 1, 33);
                 mbar_wait(b_pdsfull, it & 1, 34);
                 tc_fence_after();
                 const uint32_t sq = sbase + C::OFF_Q + s * 2 * C::QT_BYTES;
@@ -184,8 +187,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                 for (int k = 0; k < C::BQ / 16; ++k)
                     umma_bf16<1>(tmem + C::TM_DK, ads + ((k * 32) >> 4), bq + ((k * 2048) >> 4), idesc_acc, (it | k) != 0);
                 umma_commit(b_mmadone);
-                umma_commit(b_qempty(s));
-                if (it + 2 < n_it) issue_sdp(it + 2);
+                umma_commit(b_qempty(s));     // S^T/dP^T of this tile completed before its P^T/dS^T existed
             }
         }
     } else {
@@ -212,6 +214,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             const float4* L4 = reinterpret_cast<const float4*>(sgen + C::OFF_LD) + (u * 2 * C::BQ + x * 32) / 4;
             const float4* D4 = L4 + C::BQ / 4;
             tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_sdpfree(u));
             uint32_t pk[16], dk[16];
             if (!key_ok) {
 #pragma unroll
@@ -313,6 +318,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const uint32_t b_dsfull = bar0 + 8u * 21;
     const uint32_t b_mmadone = bar0 + 8u * 22;
     const uint32_t tmem_slot = bar0 + 8u * 23;
+    auto b_sdpfree = [&](int u) { return bar0 + 8u * (24 + u); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = gridDim.x - 1 - blockIdx.x;
@@ -330,7 +336,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         mbar_init(b_qfull, 1);
         for (int s = 0; s < C::kKStages; ++s) { mbar_init(b_kfull(s), 1); mbar_init(b_kempty(s), 1); }
         for (int s = 0; s < C::kVStages; ++s) { mbar_init(b_vfull(s), 1); mbar_init(b_vempty(s), 1); }
-        for (int u = 0; u < 2; ++u) mbar_init(b_sdpfull(u), 1);
+        for (int u = 0; u < 2; ++u) { mbar_init(b_sdpfull(u), 1); mbar_init(b_sdpfree(u), 8); }
         mbar_init(b_dsfull, 8);
         mbar_init(b_mmadone, 1);
         fence_mbar_init();
@@ -366,10 +372,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                                 p.v_col0 + kvh * D + kbk * 64, t * C::BKV, b);
             }
         } else if (warp == 1 && lane == 0) {
+            // ================= MMA issuer A: S = Q K^T, dP = dO V^T (runs ahead) =================
             constexpr uint32_t idesc_s = make_idesc_bf16(128, C::BKV, 0, 0);
-            constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, 0, 1);
-            auto issue_sdp = [&](int t) {
+            mbar_wait(b_qfull, 0, 45);
+            tc_fence_after();
+            for (int t = 0; t < n_kv; ++t) {
                 const int sk = t % C::kKStages, sv = t % C::kVStages, u = t & 1;
+                mbar_wait(b_sdpfree(u), ((t >> 1) & 1) ^ 1u, 50);
                 mbar_wait(b_kfull(sk), (t / C::kKStages) & 1, 43);
                 mbar_wait(b_vfull(sv), (t / C::kVStages) & 1, 44);
                 tc_fence_after();
@@ -391,13 +400,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 }
                 umma_commit(b_sdpfull(u));
                 umma_commit(b_vempty(sv));
-            };
-            mbar_wait(b_qfull, 0, 45);
-            tc_fence_after();
-            issue_sdp(0);
-            if (n_kv > 1) issue_sdp(1);
+            }
+        } else if (warp == 2 && lane == 0) {
+            // ================= MMA issuer B: dQ += dS K =================
+            constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, 0, 1);
             for (int t = 0; t < n_kv; ++t) {
                 const int sk = t % C::kKStages;
+                mbar_wait(b_kfull(sk), (t / C::kKStages) & 1, 43);
                 mbar_wait(b_dsfull, t & 1, 46);
                 tc_fence_after();
                 const uint64_t ads = make_smem_desc_sw128(sbase + C::OFF_DS, 0, 1024);
@@ -407,7 +416,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     umma_bf16<1>(tmem + C::TM_DQ, ads + ((k * 32) >> 4), bk + ((k * 2048) >> 4), idesc_dq, (t | k) != 0);
                 umma_commit(b_mmadone);
                 umma_commit(b_kempty(sk));
-                if (t + 2 < n_kv) issue_sdp(t + 2);
             }
         }
     } else {
@@ -432,6 +440,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             tmem_ld_32x32b_x32(t_lane + C::TM_S + u * C::BKV + x * 32, sv);
             tmem_ld_32x32b_x32(t_lane + C::TM_DP + u * C::BKV + x * 32, dv);
             tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_sdpfree(u));
             if (need_mask) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
