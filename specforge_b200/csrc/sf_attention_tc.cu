@@ -42,8 +42,6 @@ struct AttnTcParams {
     int heads_per_cta;             // 1 or 2
     int q_col0, k_col0, v_col0;    // column of head 0 inside the fused qkv row
     float scale_log2;
-    long long* dbg;                // optional timeline buffer (SF_ATTN_TRACE=1), CTA (0,0,0) only
-    int debug;                     // SF_ATTN_DEBUG (timing experiments only): 1 skip S TMEM load, 2 skip exp/P store
 };
 
 template <int D>
@@ -214,20 +212,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 const int u = t & 1;
                 const int kv0 = t * C::BKV;
                 const bool need_mask = (kv0 + C::BKV - 1 > q0 + wq * 32) || (kv0 + C::BKV > kvlen) || general_mask;
-                const bool trw = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 4 && lane == 0 && t < 12;
-                if (trw) p.dbg[t * 16 + 8] = clock64();
                 mbar_wait(b_sfull(x, u), (t >> 1) & 1, 22 + x);
-                if (trw) p.dbg[t * 16 + 9] = clock64();
                 tc_fence_after();
                 uint32_t sv[C::BKV];
-                if (!(p.debug & 1)) {
                 tmem_ld_32x32b_x32(t_lane + C::TM_S + (x * 2 + u) * C::BKV, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
                 tmem_ld_32x32b_x32(t_lane + C::TM_S + (x * 2 + u) * C::BKV + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
                 tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int cc = 0; cc < C::BKV; ++cc) sv[cc] = __float_as_uint(0.01f * (float)(cc + r));
-                }
                 float mx = -INFINITY;
                 if (need_mask) {
 #pragma unroll
@@ -266,12 +256,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 }
                 const float base = (m_ref == -INFINITY) ? 0.f : m_ref;
                 // the (single) P buffer must have been consumed by PV(t-1)
-                if (trw) p.dbg[t * 16 + 10] = clock64();
                 if (t > 0) mbar_wait(b_pvdone(x), (t - 1) & 1, 24 + x);
-                if (trw) p.dbg[t * 16 + 11] = clock64();
                 uint8_t* sp = sgen + C::OFF_P + x * C::P_BYTES;
                 float rs = 0.f;
-                if (!(p.debug & 2))
 #pragma unroll
                 for (int j = 0; j < C::BKV / 8; ++j) {
                     float e[8];
@@ -287,7 +274,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_pfull(x));
-                if (trw) p.dbg[t * 16 + 12] = clock64();
             }
             // ---- epilogue: O from TMEM, diagonal P*V terms (never masked), normalise, store
             mbar_wait(b_pvdone(x), (n_kv - 1) & 1, 28 + x);
@@ -383,16 +369,6 @@ static int fwd_tc_t(const AttnDesc& a, cudaStream_t st) {
     p.heads_per_cta = (g % 2 == 0) ? 2 : 1;
     p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0;
     p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
-    { const char* e = getenv("SF_ATTN_DEBUG"); p.debug = e ? atoi(e) : 0; }
-    {
-        static long long* dbg = nullptr;
-        const char* e = getenv("SF_ATTN_TRACE");
-        if (e && e[0] == '1') {
-            if (!dbg) { cudaMalloc(&dbg, 16 * 16 * 8); }
-            cudaMemsetAsync(dbg, 0, 16 * 16 * 8, st);
-            p.dbg = dbg;
-        } else p.dbg = nullptr;
-    }
     static bool set = false;
     if (!set) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -402,20 +378,6 @@ static int fwd_tc_t(const AttnDesc& a, cudaStream_t st) {
     dim3 grid((a.S + C::BQ - 1) / C::BQ, a.nh / p.heads_per_cta, a.B);
     attn_fwd_tc_kernel<D><<<grid, 384, C::SMEM, st>>>(tq, tkv, p);
     SF_CUDA_CHECK_LAUNCH("attn_fwd_tc");
-    if (p.dbg) {
-        long long h[16 * 16];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        const long long t0 = h[0];
-        fprintf(stderr, "[trace] t | mma: top s_issued vfull pfull_a pfull_b end | wg: top sfull pre_pv post_pv arrived (cycles rel.)\n");
-        for (int t = 0; t < 12; ++t) {
-            fprintf(stderr, "[trace] %2d |", t);
-            for (int k = 0; k < 6; ++k) fprintf(stderr, " %7lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
-            fprintf(stderr, " |");
-            for (int k = 8; k < 13; ++k) fprintf(stderr, " %7lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
-            fprintf(stderr, "\n");
-        }
-    }
     return 0;
 }
 
