@@ -1,0 +1,54 @@
+"""Double-buffered host->device input feed (SURVEY §8f "input feed" row; the reference does a blocking pageable
+`.to(device)` per micro-batch inside forward_loss, strategies/base.py:282-289).
+
+`DevicePrefetcher` wraps any iterable of TrainBatch-like objects whose tensors live in (ideally pinned) host memory and
+yields the same objects with device tensors.  The copy of batch k+1 is issued on a side stream while step k computes;
+an event hands each batch over to the compute stream, so the step never waits on PCIe unless the feed is behind."""
+from __future__ import annotations
+
+import dataclasses
+from typing import Iterable, Iterator, Optional
+
+import torch
+
+
+class DevicePrefetcher:
+    def __init__(self, batches: Iterable, device: Optional[torch.device] = None, depth: int = 2):
+        self.batches = batches
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.depth = max(1, depth)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def _stage(self, batch):
+        with torch.cuda.stream(self.stream):
+            tensors = {}
+            for k, v in batch.tensors.items():
+                if isinstance(v, torch.Tensor) and not v.is_cuda:
+                    if not v.is_pinned():
+                        v = v.pin_memory()
+                    tensors[k] = v.to(self.device, non_blocking=True)
+                else:
+                    tensors[k] = v
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dataclasses.replace(batch, tensors=tensors), ev
+
+    def __iter__(self) -> Iterator:
+        it = iter(self.batches)
+        queue = []
+        try:
+            for _ in range(self.depth):
+                queue.append(self._stage(next(it)))
+        except StopIteration:
+            pass
+        while queue:
+            batch, ev = queue.pop(0)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            for v in batch.tensors.values():          # the compute stream now owns these buffers
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    v.record_stream(torch.cuda.current_stream(self.device))
+            try:
+                queue.append(self._stage(next(it)))
+            except StopIteration:
+                pass
+            yield batch

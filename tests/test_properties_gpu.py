@@ -1,0 +1,143 @@
+"""Size-independent properties and edge cases of the CUDA step (GPU), including BASELINE config-2 full size:
+determinism (bit-identical reruns), gradient accumulation == sum, loss_scale linearity, eval == train forward,
+ragged / minimal / maximal shapes, fully-masked loss, the public strategy/backend API."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(kw, B, S, T, seed=0, pad_tail=0, lk=None):
+    from oracle import eagle3_oracle as O
+    from specforge_b200.engine import DraftDims, Eagle3Engine
+    cfg = O.Eagle3Config(ttt_length=T, **kw)
+    dims = DraftDims(**{k: v for k, v in kw.items()})
+    eng = Eagle3Engine(dims, batch=B, seq_len=S, ttt_length=T, lk_loss_type=lk)
+    P = O.init_params(cfg, seed=seed)
+    t2d, d2t = O.make_vocab_map(cfg.vocab_size, cfg.draft_vocab_size, seed=seed)
+    head_w = torch.randn(cfg.vocab_size, cfg.target_hidden_size, generator=torch.Generator().manual_seed(5)).bfloat16()
+    eng.load_params(P)
+    eng.set_frozen(embed_tokens=P["embed_tokens.weight"], target_head=head_w, t2d=t2d, d2t=d2t)
+    batch = O.make_batch(cfg, B, S, seed=seed, pad_tail=pad_tail)
+    return eng, cfg, P, batch, head_w, t2d, d2t
+
+
+SMALL = dict(hidden_size=256, intermediate_size=512, num_heads=4, num_kv_heads=2, head_dim=64, vocab_size=1024,
+             draft_vocab_size=256, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=512)
+
+
+def test_deterministic_and_accumulation_and_scale():
+    eng, *_ , batch, _, _, _ = _make(SMALL, 2, 200, 3, pad_tail=13)
+    eng.forward(batch); eng.backward()
+    g1 = eng.grads_f32.clone(); l1 = eng.loss.clone(); m1 = eng.metrics.clone()
+    eng.forward(batch); eng.backward()
+    assert torch.equal(eng.loss, l1) and torch.equal(eng.metrics, m1)
+    assert torch.equal(eng.grads_f32, g1), "the step must be bit-deterministic (no atomics on the GEMM/attention path)"
+    eng.forward(batch); eng.backward(accumulate=True)          # second micro-batch accumulates
+    torch.testing.assert_close(eng.grads_f32, 2 * g1, rtol=1e-6, atol=1e-9)
+    eng.forward(batch); eng.backward(loss_scale=0.25)
+    torch.testing.assert_close(eng.grads_f32, 0.25 * g1, rtol=1e-6, atol=1e-12)
+    # eval forward (no gradient written) reports the same loss
+    eng.forward(batch, need_grad=False)
+    assert torch.equal(eng.loss, l1)
+
+
+@pytest.mark.parametrize("B,S,T,pad", [(1, 64, 1, 0), (1, 65, 2, 3), (3, 130, 9, 70), (2, 448, 4, 0)])
+def test_ragged_and_extreme_shapes_match_oracle(B, S, T, pad):
+    from oracle import eagle3_oracle as O
+    eng, cfg, P, batch, head_w, t2d, d2t = _make(SMALL, B, S, T, pad_tail=pad)
+    loss, metrics = eng.forward(batch); eng.backward()
+    torch.cuda.synchronize()
+    res, grads = O.train_step(P, cfg, batch, head_w, t2d, d2t)
+    ref = torch.stack([p.detach().float() for p in res.plosses])
+    torch.testing.assert_close(metrics[:, 0].cpu(), ref, rtol=1e-3, atol=1e-5)
+    for n in ("lm_head.weight", "midlayer.self_attn.k_proj.weight", "fc.weight"):
+        got = eng.param_view(n, eng.grads_f32).float().cpu()
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), grads[n].float().flatten(), dim=0).item()
+        assert cos >= 0.999, (n, cos)
+
+
+def test_fully_masked_loss_gives_zero_loss_and_zero_grads():
+    eng, cfg, P, batch, *_ = _make(SMALL, 2, 96, 3)
+    batch = dict(batch)
+    batch["loss_mask"] = torch.zeros_like(batch["loss_mask"])
+    loss, metrics = eng.forward(batch); eng.backward()
+    torch.cuda.synchronize()
+    assert float(loss) == 0.0 and float(metrics[:, 1].sum()) == 0.0
+    assert float(eng.grads_f32.abs().max()) == 0.0
+    assert torch.isfinite(metrics).all()           # denominators are clamped (1e-6 / 1e-8) exactly like the reference
+
+
+def test_public_api_strategy_backend_step():
+    """B200Eagle3TrainStrategy.forward_loss -> StepOutput contract (controller.py:216-252) and one backend step."""
+    from oracle import eagle3_oracle as O
+    from specforge_b200.backend import B200TrainingBackend
+    from specforge_b200.contracts import TrainBatch
+    from specforge_b200.draft import B200Eagle3DraftModel
+    from specforge_b200.strategy import B200Eagle3TrainStrategy
+    cfgd = dict(hidden_size=256, intermediate_size=512, num_attention_heads=4, num_key_value_heads=2, head_dim=64, vocab_size=1024,
+                draft_vocab_size=256, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=512)
+    draft = B200Eagle3DraftModel(cfgd)
+    eng = draft.bind_engine(batch=2, seq_len=128, ttt_length=3)
+    t2d, d2t = O.make_vocab_map(1024, 256, seed=0)
+    draft.t2d.copy_(t2d); draft.d2t.copy_(d2t)
+    draft.embed_tokens_weight.data = (torch.randn(1024, 256, device=eng.device) * 0.02).bfloat16()
+    head = torch.randn(1024, 256, device=eng.device).bfloat16()
+    st = B200Eagle3TrainStrategy(draft, target_head_weight=head)
+    be = B200TrainingBackend(lr=1e-3, total_steps=100, warmup_ratio=0.1)
+    be.attach(st); be.prepare_model(st.trainable_module())
+    cfg = O.Eagle3Config(ttt_length=3, **SMALL)
+    tb = TrainBatch(sample_ids=["0", "1"], strategy="eagle3", tensors=O.make_batch(cfg, 2, 128, seed=1), metadata={"target_repr": "hidden_state"})
+    sd0 = {k: v.clone() for k, v in draft.state_dict().items()}
+    out = st.forward_loss(tb)
+    assert out.loss.dim() == 0 and out.loss.requires_grad
+    for k in ("plosses", "acces", "acceptance_rates", "acc_corrects", "acc_denoms", "metric_losses", "metric_loss_denoms"):
+        assert len(out.metrics[k]) == 3 and all(t.dim() == 0 for t in out.metrics[k])
+    weights = [0.8 ** i for i in range(3)]
+    torch.testing.assert_close(out.loss.detach(), sum(w * p for w, p in zip(weights, out.metrics["plosses"])), rtol=1e-6, atol=1e-7)
+    be.backward(out.loss / 2, is_boundary=False)       # accumulation_steps = 2 (controller.py:345)
+    out2 = st.forward_loss(tb)
+    be.backward(out2.loss / 2, is_boundary=True)
+    gn = be.step()
+    assert float(gn) > 0
+    sd1 = draft.state_dict()
+    assert set(sd1) == set(sd0) and "lm_head.weight" in sd1 and "t2d" in sd1 and sd1["fc.weight"].shape == (256, 768)
+    assert not torch.equal(sd1["lm_head.weight"], sd0["lm_head.weight"])
+    with torch.no_grad():                                # evaluation path (controller.py:794-815)
+        ev = st.forward_loss(tb)
+    assert not ev.loss.requires_grad
+    with pytest.raises(ValueError):
+        st.forward_loss(TrainBatch(sample_ids=["0"], strategy="eagle3", tensors={"input_ids": tb.tensors["input_ids"]}))
+    ck = st.checkpoint_state_filter({"draft_model." + k: v for k, v in sd1.items()})
+    assert "embed_tokens.weight" not in ck and "fc.weight" in ck
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 (Qwen3-8B draft, B=8, S=2048, TTT=7): finite, deterministic, and linear in loss_scale."""
+    kw = dict(hidden_size=4096, intermediate_size=12288, num_heads=32, num_kv_heads=8, head_dim=128, vocab_size=151936,
+              draft_vocab_size=32000, rms_norm_eps=1e-6, rope_theta=1000000.0, max_position_embeddings=40960)
+    from specforge_b200.engine import DraftDims, Eagle3Engine
+    dev = torch.device("cuda", 0)
+    eng = Eagle3Engine(DraftDims(**kw), batch=8, seq_len=2048, ttt_length=7)
+    g = torch.Generator(device=dev).manual_seed(0)
+    for n in eng.offsets:
+        v = eng.param_view(n)
+        v.copy_(torch.ones_like(v) if v.dim() == 1 else (torch.randn(v.shape, device=dev, generator=g) * 0.02).bfloat16())
+    V, H, DV = kw["vocab_size"], kw["hidden_size"], kw["draft_vocab_size"]
+    perm = torch.randperm(V, device=dev, generator=g)[:DV].sort().values
+    t2d = torch.zeros(V, dtype=torch.bool, device=dev); t2d[perm] = True
+    eng.set_frozen(embed_tokens=(torch.randn(V, H, device=dev, generator=g) * 0.02).bfloat16(),
+                   target_head=torch.randn(V, H, device=dev, generator=g).bfloat16(), t2d=t2d, d2t=perm - torch.arange(DV, device=dev))
+    batch = {"input_ids": torch.randint(0, V, (8, 2048), device=dev, generator=g), "attention_mask": torch.ones(8, 2048, dtype=torch.long, device=dev),
+             "loss_mask": torch.ones(8, 2048, dtype=torch.long, device=dev), "hidden_state": torch.randn(8, 2048, 3 * H, device=dev, generator=g).bfloat16(),
+             "target": torch.randn(8, 2048, H, device=dev, generator=g).bfloat16()}
+    eng.forward(batch); eng.backward()
+    l1, cs1 = eng.loss.clone(), eng.grads_f32.double().sum().item()
+    n1 = eng.grads_f32.double().pow(2).sum().sqrt().item()
+    assert torch.isfinite(eng.loss).all() and torch.isfinite(eng.metrics).all() and cs1 == cs1 and n1 > 0
+    # uniform-ish logits at init: each step's KL term ~ log(DV) * fraction of rows whose teacher argmax is in the draft vocab
+    frac = eng.metrics[0, 5].item() / (8 * 2048)
+    assert abs(eng.metrics[0, 0].item() / (frac * torch.log(torch.tensor(float(DV))).item()) - 1) < 0.05
+    eng.forward(batch); eng.backward(loss_scale=0.5)
+    assert torch.equal(eng.loss, l1)
+    assert abs(eng.grads_f32.double().sum().item() / (0.5 * cs1) - 1) < 1e-9      # deterministic + linear
