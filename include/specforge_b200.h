@@ -127,8 +127,10 @@ int sf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t
                  const void* R, int64_t ldr, int M, int N, int K, int epi, int cta_group, void* stream);
 int sf_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* out, int64_t ldo, int64_t M, int H, float eps,
                    void* stream);
+/* dw (+)= column sums via per-block partials in `scratch` (sf_rmsnorm_bwd_scratch_bytes(H) bytes): deterministic. */
+int64_t sf_rmsnorm_bwd_scratch_bytes(int H);
 int sf_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const void* dy, int64_t lddy, const void* add, void* dx,
-                   float* dw, int64_t M, int H, float eps, void* stream);
+                   float* dw, float* scratch, int64_t M, int H, float eps, void* stream);
 /* TTT attention at step J over the fused per-step qkv buffers qkv[i] = [B*S, (nh+2nkv)*d] (RoPE already applied). */
 /* key_mask: optional [B,S] bytes (1 = attend); kvlen_ws: 2*B ints of scratch, required with key_mask. */
 int sf_ttt_attention_fwd(const void* const* qkv, int J, void* out, float* lse, float* sd_ws, const uint8_t* key_mask,

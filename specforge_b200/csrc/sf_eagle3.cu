@@ -65,7 +65,7 @@ struct Plan {
     // union region: forward temporaries / backward buffers
     int64_t u_base;
     int64_t tgt_shift, tlogits;                       // forward temporaries
-    int64_t dh_tot, dgu, dhmid, dqkv, d_hf, d_act, d_hn2, d_attn, d_xcat, dh_carry, dk_acc, dv_acc, dq_diag, delta, d_hs3n;
+    int64_t dh_tot, dgu, dhmid, dqkv, d_hf, d_act, d_hn2, d_attn, d_xcat, dh_carry, dk_acc, dv_acc, dq_diag, delta, d_hs3n, norm_ws;
     int64_t total;
 };
 static Plan make_plan(const sf_eagle3_config& c) {
@@ -119,6 +119,7 @@ static Plan make_plan(const sf_eagle3_config& c) {
     p.dv_acc = take(T * M * x.KV * 4);
     p.dq_diag = take(M * x.A * 4);
     p.delta = take((int64_t)x.B * x.nh * x.S * 4);
+    p.norm_ws = take(rmsnorm_bwd_ws_bytes(x.H > x.Ht ? x.H : x.Ht));
     p.d_hs3n = c.fc_norm ? take(M * 3 * x.Ht * 2) : 0;
     p.total = (o > fwd_end ? o : fwd_end) + 1024;
     return p;
@@ -310,7 +311,7 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
         // d(norm(h_{j+1})) = dlogits W_lm ; through the final norm ; + gradient arriving from step j+1
         SF_TRY(mm(c, dlogits, x.DV, MAJOR_K, c.W[SF_P_LM_HEAD], x.H, MAJOR_MN, d_hf, x.H, nullptr, 0, M, x.H, x.DV, EPI_BF16));
         if (cfg.norm_output) {
-            SF_TRY(rmsnorm_bwd(h_out, x.H, nullptr, x.S, 0, c.W[SF_P_NORM], d_hf, x.H, carry_in, nullptr, dh_tot, Gn + off[SF_P_NORM], M, x.H, cfg.rms_eps, st));
+            SF_TRY(rmsnorm_bwd(h_out, x.H, nullptr, x.S, 0, c.W[SF_P_NORM], d_hf, x.H, carry_in, nullptr, dh_tot, Gn + off[SF_P_NORM], c.at<float>(p.norm_ws), M, x.H, cfg.rms_eps, st));
         } else {
             SF_TRY(add_bf16(d_hf, carry_in, dh_tot, M * x.H, st));   // lm_head reads h_{j+1} directly
         }
@@ -322,7 +323,7 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
             SF_TRY(swiglu_bwd(gu, d_act, dgu, M, x.I, st));
         }
         SF_TRY(mm(c, dgu, 2 * x.I, MAJOR_K, c.W[SF_P_GATE], x.H, MAJOR_MN, d_hn2, x.H, nullptr, 0, M, x.H, 2 * x.I, EPI_BF16));
-        SF_TRY(rmsnorm_bwd(hmid, x.H, nullptr, x.S, 0, c.W[SF_P_POST_NORM], d_hn2, x.H, dh_tot, nullptr, dhmid, Gn + off[SF_P_POST_NORM], M, x.H, cfg.rms_eps, st));
+        SF_TRY(rmsnorm_bwd(hmid, x.H, nullptr, x.S, 0, c.W[SF_P_POST_NORM], d_hn2, x.H, dh_tot, nullptr, dhmid, Gn + off[SF_P_POST_NORM], c.at<float>(p.norm_ws), M, x.H, cfg.rms_eps, st));
         // attention
         SF_TRY(mm(c, dhmid, x.H, MAJOR_K, c.W[SF_P_O], x.A, MAJOR_MN, d_attn, x.A, nullptr, 0, M, x.A, x.H, EPI_BF16));
         AttnDesc a{};
@@ -346,8 +347,8 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
         SF_TRY(cvt_f32_bf16(a.dv_acc[j], x.KV, dqkv + x.A + x.KV, x.QKV, M, (int)x.KV, 1.0f, st));
         // through the fused q/k/v projection and the two input norms
         SF_TRY(mm(c, dqkv, x.QKV, MAJOR_K, c.W[SF_P_Q], 2 * x.H, MAJOR_MN, d_xcat, 2 * x.H, nullptr, 0, M, 2 * x.H, x.QKV, EPI_BF16));
-        SF_TRY(rmsnorm_bwd(fz.embed_tokens, x.H, bt.input_ids, x.S, 1 + j, c.W[SF_P_INPUT_NORM], d_xcat, 2 * x.H, nullptr, nullptr, nullptr, Gn + off[SF_P_INPUT_NORM], M, x.H, cfg.rms_eps, st));
-        SF_TRY(rmsnorm_bwd(h_in, x.H, nullptr, x.S, 0, c.W[SF_P_HIDDEN_NORM], d_xcat + x.H, 2 * x.H, dhmid, nullptr, dh_carry, Gn + off[SF_P_HIDDEN_NORM], M, x.H, cfg.rms_eps, st));
+        SF_TRY(rmsnorm_bwd(fz.embed_tokens, x.H, bt.input_ids, x.S, 1 + j, c.W[SF_P_INPUT_NORM], d_xcat, 2 * x.H, nullptr, nullptr, nullptr, Gn + off[SF_P_INPUT_NORM], c.at<float>(p.norm_ws), M, x.H, cfg.rms_eps, st));
+        SF_TRY(rmsnorm_bwd(h_in, x.H, nullptr, x.S, 0, c.W[SF_P_HIDDEN_NORM], d_xcat + x.H, 2 * x.H, dhmid, nullptr, dh_carry, Gn + off[SF_P_HIDDEN_NORM], c.at<float>(p.norm_ws), M, x.H, cfg.rms_eps, st));
     }
     // ---- weight gradients: one GEMM per weight, contracting over all T*M tokens (fp32 accumulation in TMEM)
     const int64_t TM = (int64_t)T * M;
@@ -363,7 +364,7 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
         const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(bt.hidden_state);
         SF_TRY(mm(c, c.bf(p.dh_carry), x.H, MAJOR_K, c.W[SF_P_FC], 3 * x.Ht, MAJOR_MN, c.bf(p.d_hs3n), 3 * x.Ht, nullptr, 0, M, 3 * x.Ht, x.H, EPI_BF16));
         for (int i = 0; i < 3; ++i)
-            SF_TRY(rmsnorm_bwd(hs + i * x.Ht, 3 * x.Ht, nullptr, x.S, 0, c.W[SF_P_FC_NORM0 + i], c.bf(p.d_hs3n) + i * x.Ht, 3 * x.Ht, nullptr, nullptr, nullptr, Gn + off[SF_P_FC_NORM0 + i], M, x.Ht, cfg.rms_eps, st));
+            SF_TRY(rmsnorm_bwd(hs + i * x.Ht, 3 * x.Ht, nullptr, x.S, 0, c.W[SF_P_FC_NORM0 + i], c.bf(p.d_hs3n) + i * x.Ht, 3 * x.Ht, nullptr, nullptr, nullptr, Gn + off[SF_P_FC_NORM0 + i], c.at<float>(p.norm_ws), M, x.Ht, cfg.rms_eps, st));
     }
     SF_TRY(mm(c, c.bf(p.dh_carry), x.H, MAJOR_MN, fc_in, 3 * x.Ht, MAJOR_MN, Gn + off[SF_P_FC], 3 * x.Ht, nullptr, 0, x.H, 3 * x.Ht, M, EPI_F32_ACCUM));
     return 0;
@@ -428,9 +429,10 @@ extern "C" int sf_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* o
     return rmsnorm_fwd(x, ldx, nullptr, 1, 0, w, out, ldo, M, H, eps, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int sf_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const void* dy, int64_t lddy, const void* add, void* dx,
-                              float* dw, int64_t M, int H, float eps, void* stream) {
-    return rmsnorm_bwd(x, ldx, nullptr, 1, 0, w, dy, lddy, add, nullptr, dx, dw, M, H, eps, reinterpret_cast<cudaStream_t>(stream));
+                              float* dw, float* scratch, int64_t M, int H, float eps, void* stream) {
+    return rmsnorm_bwd(x, ldx, nullptr, 1, 0, w, dy, lddy, add, nullptr, dx, dw, scratch, M, H, eps, reinterpret_cast<cudaStream_t>(stream));
 }
+extern "C" int64_t sf_rmsnorm_bwd_scratch_bytes(int H) { return rmsnorm_bwd_ws_bytes(H); }
 extern "C" int sf_swiglu_fwd(const void* gu, void* act, int64_t M, int I, void* stream) {
     return swiglu_fwd(gu, act, M, I, reinterpret_cast<cudaStream_t>(stream));
 }

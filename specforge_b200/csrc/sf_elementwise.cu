@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kThreads)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64_t* __restrict__ ids, int S, int shift,
                    const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ dy, int64_t lddy,
                    const __nv_bfloat16* __restrict__ add1, const __nv_bfloat16* __restrict__ add2,
-                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int64_t M, int H, float eps) {
+                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_partial, int64_t M, int H, float eps) {
     __shared__ float2 red[32];
     const int nchunks = H / 8;
     float dwacc[kChunks][8];
@@ -176,14 +176,24 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
             }
         }
     }
+    // per-block partial column sums; a second kernel adds them in block order (deterministic, no atomics)
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
         const int ch = threadIdx.x + c * kThreads;
         if (ch < nchunks) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(dw + ch * 8 + i, dwacc[c][i]);
+            float4* dst = reinterpret_cast<float4*>(dw_partial + (int64_t)blockIdx.x * H + ch * 8);
+            dst[0] = make_float4(dwacc[c][0], dwacc[c][1], dwacc[c][2], dwacc[c][3]);
+            dst[1] = make_float4(dwacc[c][4], dwacc[c][5], dwacc[c][6], dwacc[c][7]);
         }
     }
+}
+// dw[c] += sum_b partial[b][c]   (fixed summation order)
+__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ partial, int nblocks, int H, float* __restrict__ dw) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H) return;
+    float acc = 0.f;
+    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * H + c];
+    dw[c] += acc;
 }
 
 // ------------------------------------------------------------------ RoPE (in place on the fused qkv buffer)
@@ -334,18 +344,23 @@ int rmsnorm_fwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift
     SF_CUDA_CHECK_LAUNCH("rmsnorm_fwd");
     return 0;
 }
+int64_t rmsnorm_bwd_ws_bytes(int H) { return (int64_t)148 * 12 * H * 4; }
+
 int rmsnorm_bwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift, const void* w, const void* dy,
-                int64_t lddy, const void* add1, const void* add2, void* dx, float* dw, int64_t M, int H, float eps,
-                cudaStream_t st) {
+                int64_t lddy, const void* add1, const void* add2, void* dx, float* dw, float* partial_ws, int64_t M, int H,
+                float eps, cudaStream_t st) {
+    if (!partial_ws) return set_error(-22, "rmsnorm_bwd: partial-sum workspace missing");
+    int launched_blocks = 0;
     if (H % 8 || H > kRowThreads * kMaxChunks * 8) return set_error(-22, "rmsnorm: H=%d must be a multiple of 8 and <= 8192", H);
     const int nch = H / 8;
 #define SF_RMS_BWD(CH, TH, BPS)                                                                                        \
     do {                                                                                                               \
         int blocks = 148 * BPS;                                                                                        \
         if (blocks > M) blocks = (int)M;                                                                               \
+        launched_blocks = blocks;                                                                                      \
         rmsnorm_bwd_kernel<CH, TH><<<blocks, TH, 0, st>>>((const __nv_bfloat16*)x, ldx, ids, S, shift,                 \
             (const __nv_bfloat16*)w, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)add1,                        \
-            (const __nv_bfloat16*)add2, (__nv_bfloat16*)dx, dw, M, H, eps);                                            \
+            (const __nv_bfloat16*)add2, (__nv_bfloat16*)dx, partial_ws, M, H, eps);                                    \
     } while (0)
     if (nch <= 128) SF_RMS_BWD(1, 128, 12);
     else if (nch <= 256) SF_RMS_BWD(1, 256, 8);
@@ -353,6 +368,8 @@ int rmsnorm_bwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift
     else SF_RMS_BWD(2, 512, 3);
 #undef SF_RMS_BWD
     SF_CUDA_CHECK_LAUNCH("rmsnorm_bwd");
+    colsum_partials_kernel<<<(H + 255) / 256, 256, 0, st>>>(partial_ws, launched_blocks, H, dw);
+    SF_CUDA_CHECK_LAUNCH("rmsnorm_bwd_colsum");
     return 0;
 }
 int rope(void* x, const float* src32, int64_t ld, int64_t ld32, int n_heads, int head_dim, const void* cos_t,

@@ -53,9 +53,10 @@ int attn_bwd(const AttnDesc& a, cudaStream_t st);
 
 int rmsnorm_fwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift, const void* w, void* out, int64_t ldo,
                 int64_t M, int H, float eps, float* rstd, cudaStream_t st);
+int64_t rmsnorm_bwd_ws_bytes(int H);
 int rmsnorm_bwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift, const void* w, const void* dy,
-                int64_t lddy, const void* add1, const void* add2, void* dx, float* dw, int64_t M, int H, float eps,
-                cudaStream_t st);
+                int64_t lddy, const void* add1, const void* add2, void* dx, float* dw, float* partial_ws, int64_t M, int H,
+                float eps, cudaStream_t st);
 int rope(void* x, const float* src32, int64_t ld, int64_t ld32, int n_heads, int head_dim, const void* cos_t,
          const void* sin_t, int S, int pos_offset, int64_t M, int inverse, cudaStream_t st);
 int cvt_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t M, int cols, float scale, cudaStream_t st);

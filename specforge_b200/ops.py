@@ -43,8 +43,10 @@ def _declare_ops():
     l.sf_rmsnorm_fwd.restype = c_int
     l.sf_rmsnorm_fwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p]
     l.sf_rmsnorm_bwd.restype = c_int
-    l.sf_rmsnorm_bwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
-                                 c_int, c_float, c_void_p]
+    l.sf_rmsnorm_bwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_int, c_float, c_void_p]
+    l.sf_rmsnorm_bwd_scratch_bytes.restype = c_int64
+    l.sf_rmsnorm_bwd_scratch_bytes.argtypes = [c_int]
     l.sf_swiglu_fwd.restype = c_int
     l.sf_swiglu_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p]
     l.sf_swiglu_bwd.restype = c_int
@@ -74,8 +76,9 @@ def rmsnorm_bwd(x, w, dy, eps, add=None):
     l = _declare_ops()
     dx = torch.empty_like(x)
     dw = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
+    scratch = torch.empty(l.sf_rmsnorm_bwd_scratch_bytes(x.shape[1]) // 4, dtype=torch.float32, device=x.device)
     check(l.sf_rmsnorm_bwd(x.data_ptr(), x.stride(0), w.data_ptr(), dy.data_ptr(), dy.stride(0), _ptr(add), dx.data_ptr(),
-                           dw.data_ptr(), x.shape[0], x.shape[1], eps, _stream()), "sf_rmsnorm_bwd")
+                           dw.data_ptr(), scratch.data_ptr(), x.shape[0], x.shape[1], eps, _stream()), "sf_rmsnorm_bwd")
     return dx, dw
 
 

@@ -135,9 +135,11 @@ def test_config2_full_size_properties():
     l1, cs1 = eng.loss.clone(), eng.grads_f32.double().sum().item()
     n1 = eng.grads_f32.double().pow(2).sum().sqrt().item()
     assert torch.isfinite(eng.loss).all() and torch.isfinite(eng.metrics).all() and cs1 == cs1 and n1 > 0
-    # uniform-ish logits at init: each step's KL term ~ log(DV) * fraction of rows whose teacher argmax is in the draft vocab
+    # near-uniform draft logits at init: each step's KL term ~ (log DV + O(logit variance)) x the fraction of rows whose
+    # teacher argmax is in the draft vocab (loss is a mean over ALL rows, core/loss.py:201)
     frac = eng.metrics[0, 5].item() / (8 * 2048)
-    assert abs(eng.metrics[0, 0].item() / (frac * torch.log(torch.tensor(float(DV))).item()) - 1) < 0.05
+    ratio = eng.metrics[0, 0].item() / (frac * torch.log(torch.tensor(float(DV))).item())
+    assert 0.95 < ratio < 1.3, ratio
     eng.forward(batch); eng.backward(loss_scale=0.5)
     assert torch.equal(eng.loss, l1)
     assert abs(eng.grads_f32.double().sum().item() / (0.5 * cs1) - 1) < 1e-9      # deterministic + linear
