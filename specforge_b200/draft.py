@@ -37,8 +37,15 @@ def dims_from_config(config: Any) -> DraftDims:
                      norm_output=bool(get("norm_output", True)), rope_scaling=dict(scaling) if scaling else None)
 
 
+try:  # the reference's registry requires `config_class` (registry.py:38-41); LlamaConfig is what its drafts use
+    from transformers import LlamaConfig as _LlamaConfig
+except Exception:  # pragma: no cover
+    _LlamaConfig = None
+
+
 class B200Eagle3DraftModel(nn.Module):
     architectures = ["LlamaForCausalLMEagle3"]  # what the draft JSON names; kept for export parity
+    config_class = _LlamaConfig
 
     def __init__(self, config: Any, quant_config=None, attention_backend: str = "b200"):
         super().__init__()
@@ -58,6 +65,33 @@ class B200Eagle3DraftModel(nn.Module):
         self.register_buffer("d2t", torch.zeros(d.draft_vocab_size, dtype=torch.int64))
         self._flat_params: Dict[str, nn.Parameter] = {}
         self.vocab_mapping_loaded = False
+
+    def state_dict_spec(self) -> Dict[str, tuple]:
+        """name -> shape of everything state_dict() will hold (the reference LlamaForCausalLMEagle3 contract)."""
+        d = self.dims
+        H, I, hd, Ht = d.hidden_size, d.intermediate_size, d.head_dim, d.target_hidden_size
+        spec = {
+            "embed_tokens.weight": (d.vocab_size, H),
+            "fc.weight": (H, 3 * Ht),
+            "midlayer.self_attn.q_proj.weight": (d.num_heads * hd, 2 * H),
+            "midlayer.self_attn.k_proj.weight": (d.num_kv_heads * hd, 2 * H),
+            "midlayer.self_attn.v_proj.weight": (d.num_kv_heads * hd, 2 * H),
+            "midlayer.self_attn.o_proj.weight": (H, d.num_heads * hd),
+            "midlayer.mlp.gate_proj.weight": (I, H),
+            "midlayer.mlp.up_proj.weight": (I, H),
+            "midlayer.mlp.down_proj.weight": (H, I),
+            "midlayer.hidden_norm.weight": (H,),
+            "midlayer.input_layernorm.weight": (H,),
+            "midlayer.post_attention_layernorm.weight": (H,),
+            "norm.weight": (H,),
+            "lm_head.weight": (d.draft_vocab_size, H),
+            "t2d": (d.vocab_size,),
+            "d2t": (d.draft_vocab_size,),
+        }
+        if d.fc_norm:
+            for i in range(3):
+                spec[f"fc_norm.{i}.weight"] = (Ht,)
+        return spec
 
     # ---- engine binding -------------------------------------------------------------------------------
     def bind_engine(self, batch: int, seq_len: int, ttt_length: int, ploss_decay: float = 0.8, device=None,

@@ -1,0 +1,42 @@
+"""Seam 1 (draft registry) against the REAL reference package, when it is present (/root/reference exists only in the
+build container; on the GPU box this module is skipped).  CPU only: checks that our draft class can be bound into the
+reference's DRAFT_REGISTRY, resolved by AutoDraftModelConfig / AutoDraftModel from the reference's own draft JSONs, and
+that its state-dict contract (names + shapes) equals the reference class's, incl. EAGLE3.1 fc_norm."""
+import os
+import sys
+
+import pytest
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "specforge")), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import specforge.modeling.draft.llama3_eagle as le
+    from specforge.modeling.auto import AutoDraftModel, AutoDraftModelConfig
+    from specforge.modeling.draft.registry import DRAFT_REGISTRY
+    return le, AutoDraftModel, AutoDraftModelConfig, DRAFT_REGISTRY
+
+
+@pytest.mark.parametrize("cfg_name", ["qwen2.5-0.5b-eagle3.json", "qwen3-30B-A3B-eagle3.1.json"])
+def test_registry_binding_and_state_dict_contract(ref, cfg_name, monkeypatch):
+    le, AutoDraftModel, AutoDraftModelConfig, DRAFT_REGISTRY = ref
+    from specforge_b200.draft import B200Eagle3DraftModel
+    ref_cls = le.LlamaForCausalLMEagle3
+    path = os.path.join(REF, "configs", cfg_name)
+    config = AutoDraftModelConfig.from_file(path)
+    # shrink the tables so the reference module instantiates quickly on CPU (shapes scale with these fields only)
+    config.vocab_size, config.draft_vocab_size = 2048, 512
+    ref_model = ref_cls(config, attention_backend="sdpa")
+    ref_sd = {k: tuple(v.shape) for k, v in ref_model.state_dict().items()}
+    monkeypatch.setitem(DRAFT_REGISTRY, "LlamaForCausalLMEagle3", B200Eagle3DraftModel)   # INTEGRATION.md seam 1
+    config2 = AutoDraftModelConfig.from_file(path)                    # resolves config_class through OUR class
+    config2.vocab_size, config2.draft_vocab_size = 2048, 512
+    ours = AutoDraftModel.from_config(config2, attention_backend="b200")
+    assert isinstance(ours, B200Eagle3DraftModel)
+    assert ours.state_dict_spec() == ref_sd
+    assert ours.dims.fc_norm == bool(getattr(config, "fc_norm", False))
