@@ -147,6 +147,27 @@ __global__ void total_loss_kernel(const float* __restrict__ metrics, int T, floa
         for (int i = threadIdx.x; i < T * 8; i += blockDim.x) metrics_out[i] = metrics[i];
 }
 
+// Side stream for the work that is OFF the draft's critical path: the teacher distribution (needed only by the first
+// loss) and every step's loss/metrics kernel (needed only by backward).  Their blocks use no dynamic smem, so they
+// co-reside with the persistent tcgen05 GEMM CTAs of the next ops and soak up the HBM bandwidth the GEMMs leave idle.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork[12] = {nullptr};
+    cudaEvent_t join = nullptr;
+    bool init() {
+        if (stream) return true;
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (auto& e : fork) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+        return cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
+    }
+};
+static SideStream g_side[16];
+static bool overlap_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SF_NO_OVERLAP"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
 struct Ctx {
     const sf_eagle3_config* cfg; Dims x; Plan p; uint8_t* ws; cudaStream_t st;
     const __nv_bfloat16* W[SF_P_COUNT];
@@ -198,8 +219,17 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
     // ---- teacher: shift, frozen target head GEMM, distribution  (strategies/base.py:116-120, eagle3/model.py:445-501)
     SF_TRY(shift_left(bt.target, c.bf(p.tgt_shift), x.B, x.S, x.Ht, st));
     SF_TRY(mm(c, c.bf(p.tgt_shift), x.Ht, MAJOR_K, fz.target_head, x.Ht, MAJOR_K, c.bf(p.tlogits), x.V, nullptr, 0, M, x.V, x.Ht, EPI_BF16));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStream* side = (overlap_enabled() && dev < 16 && g_side[dev].init()) ? &g_side[dev] : nullptr;
+    cudaStream_t ls = st;   // stream of the loss-side work
+    if (side) {
+        ls = side->stream;
+        if (cudaEventRecord(side->fork[0], st) != cudaSuccess || cudaStreamWaitEvent(ls, side->fork[0], 0) != cudaSuccess)
+            return set_error(-5, "side-stream fork failed");
+    }
     SF_TRY(teacher(c.bf(p.tlogits), x.V, c.at<int>(p.d2t_idx), fz.t2d, c.at<int>(p.loss_mask32), c.at<float>(p.target_p),
-                   c.at<float>(p.pod), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask), x.B, x.S, T, x.V, x.DV, st));
+                   c.at<float>(p.pod), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask), x.B, x.S, T, x.V, x.DV, ls));
     // ---- fc: h_0 = [fc_norm_i(chunk_i)] W_fc^T   (llama3_eagle.py:1762-1770; per-third RMSNorm = EAGLE3.1)
     const void* fc_in = bt.hidden_state;
     if (cfg.fc_norm) {
@@ -257,9 +287,17 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         SF_TRY(mm(c, hf, x.H, MAJOR_K, c.W[SF_P_LM_HEAD], x.H, MAJOR_K, logits, x.DV, nullptr, 0, M, x.DV, x.H, EPI_BF16));
         // loss / metrics / d(logits) in place   (eagle3/model.py:142-199, core/loss.py, core/lk_loss.py)
         const float step_weight = powf(cfg.ploss_decay, (float)j);
+        if (side) {
+            if (cudaEventRecord(side->fork[1 + j], st) != cudaSuccess || cudaStreamWaitEvent(ls, side->fork[1 + j], 0) != cudaSuccess)
+                return set_error(-5, "side-stream fork failed");
+        }
         SF_TRY(loss_step(logits, x.DV, c.at<float>(p.target_p), c.at<float>(p.pod), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask),
                          c.at<int>(p.loss_mask32), fz.d2t, x.B, x.S, T, x.DV, j, step_weight, need_grad, cfg.lk_loss_type,
-                         cfg.kl_scale, cfg.kl_decay, c.at<float>(p.row_ws), c.at<float>(p.metrics), st));
+                         cfg.kl_scale, cfg.kl_decay, c.at<float>(p.row_ws), c.at<float>(p.metrics), side ? 1 : 0, ls));
+    }
+    if (side) {
+        if (cudaEventRecord(side->join, ls) != cudaSuccess || cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess)
+            return set_error(-5, "side-stream join failed");
     }
     total_loss_kernel<<<1, 64, 0, st>>>(c.at<float>(p.metrics), T, cfg.ploss_decay, loss_out ? loss_out : c.at<float>(p.misc), metrics_out);
     SF_CUDA_CHECK_LAUNCH("total_loss");

@@ -70,7 +70,7 @@ int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, 
 int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod, const int64_t* tgt_ids,
               const int* position_mask, const int* loss_mask, const int64_t* d2t, int B, int S, int T, int DV, int step,
               float step_weight, int write_grad, int lk_type, float kl_scale, float kl_decay, float* row_ws, float* metrics,
-              cudaStream_t st);
+              int no_smem, cudaStream_t st);
 int grad_norm(const void* g, int64_t n, float gscale, float* partials_ws, float* out, cudaStream_t st);
 int adamw(const void* g, float* master, float* m1, float* m2, void* param, int64_t n, const float* gnorm, float max_norm,
           float gscale, float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st);

@@ -122,6 +122,82 @@ teacher_kernel(const __nv_bfloat16* __restrict__ tl, int64_t ld, const int* __re
         position_mask[r] = (t2d[mi.i] ? 1 : 0) * loss_mask[r];
     }
 }
+// Same kernel with the gathered draft logits held in registers (no dynamic smem): a block then fits next to a
+// resident tcgen05 GEMM CTA, which is what lets the teacher run on a side stream under the draft's first GEMMs.
+template <int kItems>
+__global__ void __launch_bounds__(512, 2)
+teacher_reg_kernel(const __nv_bfloat16* __restrict__ tl, int64_t ld, const int* __restrict__ d2t_idx,
+                   const uint8_t* __restrict__ t2d, const int* __restrict__ loss_mask, float* __restrict__ target_p,
+                   float* __restrict__ pod, int64_t* __restrict__ ids, int* __restrict__ position_mask, int S, int T, int V,
+                   int DV) {
+    __shared__ float redv[32];
+    __shared__ int redi[32];
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / S), s = (int)(r % S);
+    const __nv_bfloat16* row = tl + r * ld;
+    MaxIdx mi{-INFINITY, 0x7fffffff};
+    float d = 0.f;
+    const int nch = V / 8;
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(row) + c), f);
+        float cm = f[0]; int ci = 0;
+#pragma unroll
+        for (int e = 1; e < 8; ++e)
+            if (f[e] > cm) { cm = f[e]; ci = e; }
+        if (cm > mi.v) { d *= __expf(mi.v - cm); mi.v = cm; mi.i = c * 8 + ci; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d += __expf(f[e] - mi.v);
+    }
+    for (int e = nch * 8 + threadIdx.x; e < V; e += blockDim.x) {
+        const float f = __bfloat162float(row[e]);
+        if (f > mi.v) { d *= __expf(mi.v - f); mi.v = f; mi.i = e; }
+        d += __expf(f - mi.v);
+    }
+    const float my_m = mi.v;
+    mi = block_argmax(mi, redv, redi);
+    const float m = mi.v;
+    d = block_sum_f(my_m == -INFINITY ? 0.f : d * __expf(my_m - m), redv);
+    const float lse = m + logf(d);
+    // gathered draft logits stay in registers as raw bf16 pairs (lossless): 512 x ~60 registers fit beside a GEMM CTA
+    uint32_t xp[kItems / 2];
+    float md = -INFINITY;
+    const __nv_bfloat16 ninf = __float2bfloat16_rn(-INFINITY);
+#pragma unroll
+    for (int k = 0; k < kItems; k += 2) {
+        const int i0 = threadIdx.x + k * 512, i1 = i0 + 512;
+        const __nv_bfloat16 a = (i0 < DV) ? row[d2t_idx[i0]] : ninf;
+        const __nv_bfloat16 bq = (i1 < DV) ? row[d2t_idx[i1]] : ninf;
+        __nv_bfloat162 pr; pr.x = a; pr.y = bq;
+        xp[k / 2] = *reinterpret_cast<uint32_t*>(&pr);
+        md = fmaxf(md, fmaxf(__bfloat162float(a), __bfloat162float(bq)));
+    }
+    md = block_max_f(md, redv);
+    float dd = 0.f;
+#pragma unroll
+    for (int k = 0; k < kItems / 2; ++k) {
+        const __nv_bfloat162 pr = *reinterpret_cast<const __nv_bfloat162*>(&xp[k]);
+        dd += __expf(__bfloat162float(pr.x) - md) + __expf(__bfloat162float(pr.y) - md);   // exp(-inf) = 0 for padding slots
+    }
+    dd = block_sum_f(dd, redv);
+    const float inv = 1.f / dd;
+    const int64_t orow = (int64_t)b * (S + T) + s;
+    float* tp = target_p + orow * DV;
+    float* pp = pod + orow * DV;
+#pragma unroll
+    for (int k = 0; k < kItems; k += 2) {
+        const __nv_bfloat162 pr = *reinterpret_cast<const __nv_bfloat162*>(&xp[k / 2]);
+        const int i0 = threadIdx.x + k * 512, i1 = i0 + 512;
+        const float x0 = __bfloat162float(pr.x), x1 = __bfloat162float(pr.y);
+        if (i0 < DV) { tp[i0] = __expf(x0 - md) * inv; pp[i0] = __expf(x0 - lse); }
+        if (i1 < DV) { tp[i1] = __expf(x1 - md) * inv; pp[i1] = __expf(x1 - lse); }
+    }
+    if (threadIdx.x == 0) {
+        ids[orow] = mi.i;
+        position_mask[r] = (t2d[mi.i] ? 1 : 0) * loss_mask[r];
+    }
+}
+
 // padded tail rows: target_p = 1/DV, p_on_draft = 0, ids = 0   (eagle3/model.py:459-477)
 __global__ void __launch_bounds__(256)
 teacher_pad_kernel(float* __restrict__ target_p, float* __restrict__ pod, int64_t* __restrict__ ids, int B, int S, int T,
@@ -456,12 +532,21 @@ __global__ void __launch_bounds__(256) cvt_flat_f32_bf16_kernel(const float* __r
 int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, const int* loss_mask, float* target_p,
             float* pod, int64_t* ids, int* position_mask, int B, int S, int T, int V, int DV, cudaStream_t st) {
     if (V % 8) return set_error(-22, "teacher: target vocab %d must be a multiple of 8", V);
-    const int smem = DV * 2;
-    if (smem > 200 * 1024) return set_error(-22, "teacher: draft vocab %d too large for the smem-staged path", DV);
-    static int smem_set = 0;
-    if (smem > smem_set) { cudaFuncSetAttribute(teacher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
-    teacher_kernel<<<(unsigned)((int64_t)B * S), 512, smem, st>>>((const __nv_bfloat16*)tl, ld, d2t_idx, t2d, loss_mask,
-                                                                 target_p, pod, ids, position_mask, S, T, V, DV);
+    const unsigned rows = (unsigned)((int64_t)B * S);
+#define SF_TEACHER_REG(K) teacher_reg_kernel<K><<<rows, 512, 0, st>>>((const __nv_bfloat16*)tl, ld, d2t_idx, t2d, loss_mask, \
+                                                                    target_p, pod, ids, position_mask, S, T, V, DV)
+    if (DV <= 512 * 8) SF_TEACHER_REG(8);
+    else if (DV <= 512 * 32) SF_TEACHER_REG(32);
+    else if (DV <= 512 * 64) SF_TEACHER_REG(64);
+    else {
+        const int smem = DV * 2;
+        if (smem > 200 * 1024) return set_error(-22, "teacher: draft vocab %d too large for the smem-staged path", DV);
+        static int smem_set = 0;
+        if (smem > smem_set) { cudaFuncSetAttribute(teacher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
+        teacher_kernel<<<rows, 512, smem, st>>>((const __nv_bfloat16*)tl, ld, d2t_idx, t2d, loss_mask, target_p, pod, ids,
+                                                position_mask, S, T, V, DV);
+    }
+#undef SF_TEACHER_REG
     SF_CUDA_CHECK_LAUNCH("teacher");
     if (T > 0) {
         teacher_pad_kernel<<<148 * 4, 256, 0, st>>>(target_p, pod, ids, B, S, T, DV);
@@ -473,7 +558,7 @@ int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, 
 int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod, const int64_t* tgt_ids,
               const int* position_mask, const int* loss_mask, const int64_t* d2t, int B, int S, int T, int DV, int step,
               float step_weight, int write_grad, int lk_type, float kl_scale, float kl_decay, float* row_ws, float* metrics,
-              cudaStream_t st) {
+              int no_smem, cudaStream_t st) {
     if (DV % 8 || ld % 8) return set_error(-22, "loss: draft vocab %d / ld must be multiples of 8", DV);
     LossParams p;
     p.logits = (__nv_bfloat16*)logits; p.ld = ld; p.target_p = target_p; p.pod = pod; p.tgt_ids = tgt_ids;
@@ -482,7 +567,7 @@ int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod,
     p.grad_coef = step_weight / (float)M; p.write_grad = (lk_type == 0) ? write_grad : 0;
     p.row_loss = row_ws; p.row_accept = row_ws + M; p.row_correct = row_ws + 2 * M;
     int smem = DV * 2;
-    p.use_smem = smem <= 100 * 1024;
+    p.use_smem = !no_smem && smem <= 100 * 1024;
     if (!p.use_smem) smem = 0;
     static int smem_set = 0;
     if (smem > smem_set) { cudaFuncSetAttribute(loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
