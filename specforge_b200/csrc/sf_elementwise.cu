@@ -187,13 +187,22 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
         }
     }
 }
-// dw[c] += sum_b partial[b][c]   (fixed summation order)
+// dw[c] += sum_b partial[b][c]   (fixed summation order: 8 interleaved row groups, then an ordered smem add)
 __global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ partial, int nblocks, int H, float* __restrict__ dw) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= H) return;
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
     float acc = 0.f;
-    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * H + c];
-    dw[c] += acc;
+    if (c < H)
+        for (int b = ry; b < nblocks; b += 8) acc += partial[(int64_t)b * H + c];
+    red[ry][cx] = acc;
+    __syncthreads();
+    if (ry == 0 && c < H) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][cx];
+        dw[c] += t;
+    }
 }
 
 // ------------------------------------------------------------------ RoPE (in place on the fused qkv buffer)
@@ -368,7 +377,7 @@ int rmsnorm_bwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift
     else SF_RMS_BWD(2, 512, 3);
 #undef SF_RMS_BWD
     SF_CUDA_CHECK_LAUNCH("rmsnorm_bwd");
-    colsum_partials_kernel<<<(H + 255) / 256, 256, 0, st>>>(partial_ws, launched_blocks, H, dw);
+    colsum_partials_kernel<<<(H + 31) / 32, 256, 0, st>>>(partial_ws, launched_blocks, H, dw);
     SF_CUDA_CHECK_LAUNCH("rmsnorm_bwd_colsum");
     return 0;
 }
