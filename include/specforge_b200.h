@@ -108,6 +108,15 @@ int sf_eagle3_backward(const sf_eagle3_config* cfg, const void* params_flat, con
                        const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float loss_scale,
                        float* grads_flat_f32, int accumulate, void* stream);
 
+/* Same, with a host callback invoked right after the LAST kernel producing a group of adjacent parameters'
+ * gradients has been enqueued (norm weights first, then lm_head, down, gate+up, o, q+k+v, fc[+fc_norm]): the caller
+ * can record an event and start the data-parallel all-reduce of that slice on another stream while the remaining
+ * weight-gradient GEMMs still run.  first_param indexes the SF_P_* enum; the slice is n_params adjacent entries. */
+typedef void (*sf_grad_ready_fn)(int32_t first_param, int32_t n_params, void* user);
+int sf_eagle3_backward_ex(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,
+                          const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float loss_scale,
+                          float* grads_flat_f32, int accumulate, sf_grad_ready_fn on_ready, void* user, void* stream);
+
 /* grads_bf16[i] = bf16(grads_f32[i] * (scale_dev ? *scale_dev : 1))  — the bf16 gradient buffer DDP all-reduces
  * (backend.py:233-253).  scale_dev is an optional DEVICE float (e.g. the 1/accumulation_steps that autograd hands
  * to backward), so applying it needs no host synchronisation. */

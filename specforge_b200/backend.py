@@ -51,6 +51,8 @@ class B200TrainingBackend:
         self.module: Optional[nn.Module] = None
         self._step = 0
         self._comm_stream: Optional[torch.cuda.Stream] = None
+        self._reduced_elems = 0
+        self.overlap_allreduce = True
 
     @property
     def world_size(self) -> int:
@@ -59,6 +61,25 @@ class B200TrainingBackend:
     def attach(self, strategy) -> None:
         self.strategy = strategy
         self.engine = strategy.engine
+        strategy.grad_ready_hook = self._on_grad_slice_ready
+
+    # ---- overlapped gradient all-reduce ---------------------------------------------------------------
+    # On the boundary micro-step the C library reports each contiguous slice of the flat gradient as soon as the last
+    # kernel writing it has been enqueued (norms, lm_head, down, gate+up, o, qkv, fc).  Each slice is converted to
+    # bf16 and all-reduced on a communication stream while the remaining weight-gradient GEMMs still run.
+    def _on_grad_slice_ready(self, first: int, count: int) -> None:
+        if self.world_size == 1 or not self.overlap_allreduce:
+            return
+        eng = self.engine
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=eng.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ev)
+            eng.grads_to_bf16(scale=self.strategy._last_grad_out, first=first, count=count)
+            dist.all_reduce(eng.grads_bf16[first:first + count], op=dist.ReduceOp.SUM, group=self.process_group)
+        self._reduced_elems += count
 
     def prepare_model(self, model: nn.Module, *, wrap: bool = True, optimizer_target=None) -> nn.Module:
         self.module = model
@@ -67,17 +88,24 @@ class B200TrainingBackend:
         return model
 
     def backward(self, loss: torch.Tensor, *, is_boundary: bool = True) -> None:
-        loss.backward()  # -> _Eagle3StepFn.backward -> sf_eagle3_backward (accumulates into the fp32 flat buffer)
+        self.strategy._is_boundary = is_boundary
+        self._reduced_elems = 0
+        loss.backward()  # -> _Eagle3StepFn.backward -> sf_eagle3_backward(_ex) (accumulates into the fp32 flat buffer)
 
     def scale_gradients(self, factor: torch.Tensor) -> None:
         self.engine.grads_f32.mul_(factor)
 
     def step(self) -> torch.Tensor:
         eng, st = self.engine, self.strategy
-        g = eng.grads_to_bf16(scale=st._last_grad_out)   # x (1/accumulation_steps) from autograd, on device
         world = self.world_size
-        if world > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.process_group)
+        if world > 1 and self._reduced_elems == eng.n_params:
+            # every slice was converted + all-reduced on the comm stream during backward: just join it
+            torch.cuda.current_stream(eng.device).wait_stream(self._comm_stream)
+        else:
+            g = eng.grads_to_bf16(scale=st._last_grad_out)   # x (1/accumulation_steps) from autograd, on device
+            if world > 1:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.process_group)
+        self._reduced_elems = 0
         lr = self.schedule.lr_at(self._step)
         gn = eng.optimizer_step(lr, grad_scale=1.0 / world, max_grad_norm=self.max_grad_norm,
                                 weight_decay=self.weight_decay)

@@ -309,7 +309,8 @@ __global__ void scale_f32_kernel(float* __restrict__ g, int64_t n, float s) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) g[i] *= s;
 }
 
-static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt, float loss_scale, float* G, int accumulate) {
+static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt, float loss_scale, float* G, int accumulate,
+                    sf_grad_ready_fn on_ready, void* user) {
     const Dims& x = c.x; const Plan& p = c.p; const sf_eagle3_config& cfg = *c.cfg;
     const int64_t M = x.M; const int T = x.T;
     cudaStream_t st = c.st;
@@ -388,13 +389,21 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
         SF_TRY(rmsnorm_bwd(fz.embed_tokens, x.H, bt.input_ids, x.S, 1 + j, c.W[SF_P_INPUT_NORM], d_xcat, 2 * x.H, nullptr, nullptr, nullptr, Gn + off[SF_P_INPUT_NORM], c.at<float>(p.norm_ws), M, x.H, cfg.rms_eps, st));
         SF_TRY(rmsnorm_bwd(h_in, x.H, nullptr, x.S, 0, c.W[SF_P_HIDDEN_NORM], d_xcat + x.H, 2 * x.H, dhmid, nullptr, dh_carry, Gn + off[SF_P_HIDDEN_NORM], c.at<float>(p.norm_ws), M, x.H, cfg.rms_eps, st));
     }
-    // ---- weight gradients: one GEMM per weight, contracting over all T*M tokens (fp32 accumulation in TMEM)
+    // ---- weight gradients: one GEMM per weight, contracting over all T*M tokens (fp32 accumulation in TMEM).
+    // `on_ready` fires after each group of adjacent parameters is complete so the caller can overlap its all-reduce.
+    auto ready = [&](int first, int n) { if (on_ready) on_ready(first, n, user); };
     const int64_t TM = (int64_t)T * M;
+    ready(SF_P_HIDDEN_NORM, 4);     // the four norm-weight gradients were finished inside the TTT loop
     SF_TRY(mm(c, c.bf(p.logits), x.DV, MAJOR_MN, c.bf(p.hf), x.H, MAJOR_MN, Gn + off[SF_P_LM_HEAD], x.H, nullptr, 0, x.DV, x.H, TM, EPI_F32_ACCUM));
+    ready(SF_P_LM_HEAD, 1);
     SF_TRY(mm(c, c.bf(p.dh_tot), x.H, MAJOR_MN, c.bf(p.act), x.I, MAJOR_MN, Gn + off[SF_P_DOWN], x.I, nullptr, 0, x.H, x.I, TM, EPI_F32_ACCUM));
+    ready(SF_P_DOWN, 1);
     SF_TRY(mm(c, c.bf(p.dgu), 2 * x.I, MAJOR_MN, c.bf(p.hn2), x.H, MAJOR_MN, Gn + off[SF_P_GATE], x.H, nullptr, 0, 2 * x.I, x.H, TM, EPI_F32_ACCUM));
+    ready(SF_P_GATE, 2);
     SF_TRY(mm(c, c.bf(p.dhmid), x.H, MAJOR_MN, c.bf(p.attn), x.A, MAJOR_MN, Gn + off[SF_P_O], x.A, nullptr, 0, x.H, x.A, TM, EPI_F32_ACCUM));
+    ready(SF_P_O, 1);
     SF_TRY(mm(c, c.bf(p.dqkv), x.QKV, MAJOR_MN, c.bf(p.xcat), 2 * x.H, MAJOR_MN, Gn + off[SF_P_Q], 2 * x.H, nullptr, 0, x.QKV, 2 * x.H, TM, EPI_F32_ACCUM));
+    ready(SF_P_Q, 3);
     // fc: dW_fc = d(h_0)^T fc_in ; with fc_norm also the three norm-weight gradients through d(fc_in) = d(h_0) W_fc
     const void* fc_in = bt.hidden_state;
     if (cfg.fc_norm) {
@@ -403,8 +412,10 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
         SF_TRY(mm(c, c.bf(p.dh_carry), x.H, MAJOR_K, c.W[SF_P_FC], 3 * x.Ht, MAJOR_MN, c.bf(p.d_hs3n), 3 * x.Ht, nullptr, 0, M, 3 * x.Ht, x.H, EPI_BF16));
         for (int i = 0; i < 3; ++i)
             SF_TRY(rmsnorm_bwd(hs + i * x.Ht, 3 * x.Ht, nullptr, x.S, 0, c.W[SF_P_FC_NORM0 + i], c.bf(p.d_hs3n) + i * x.Ht, 3 * x.Ht, nullptr, nullptr, nullptr, Gn + off[SF_P_FC_NORM0 + i], c.at<float>(p.norm_ws), M, x.Ht, cfg.rms_eps, st));
+        ready(SF_P_FC_NORM0, 3);
     }
     SF_TRY(mm(c, c.bf(p.dh_carry), x.H, MAJOR_MN, fc_in, 3 * x.Ht, MAJOR_MN, Gn + off[SF_P_FC], 3 * x.Ht, nullptr, 0, x.H, 3 * x.Ht, M, EPI_F32_ACCUM));
+    ready(SF_P_FC, 1);
     return 0;
 }
 
@@ -431,14 +442,15 @@ extern "C" int sf_eagle3_forward(const sf_eagle3_config* cfg, const void* params
     SF_TRY(setup(c, cfg, params_flat, workspace, workspace_bytes, stream));
     return forward(c, *frozen, *batch, metrics, loss, need_grad);
 }
-extern "C" int sf_eagle3_backward(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,
-                                  const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float loss_scale,
-                                  float* grads_flat_f32, int accumulate, void* stream) {
+extern "C" int sf_eagle3_backward_ex(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,
+                                     const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float loss_scale,
+                                     float* grads_flat_f32, int accumulate, sf_grad_ready_fn on_ready, void* user, void* stream) {
     if (!frozen || !batch || !grads_flat_f32) return set_error(-22, "null argument");
     Ctx c;
     SF_TRY(setup(c, cfg, params_flat, workspace, workspace_bytes, stream));
     if (loss_scale != 1.0f && accumulate) return set_error(-22, "loss_scale != 1 with accumulate is unsupported: scale the loss via grads_to_bf16 / optimizer grad_scale");
-    SF_TRY(backward(c, *frozen, *batch, loss_scale, grads_flat_f32, accumulate));
+    if (loss_scale != 1.0f && on_ready) return set_error(-22, "loss_scale != 1 cannot be combined with the gradient-ready callback");
+    SF_TRY(backward(c, *frozen, *batch, loss_scale, grads_flat_f32, accumulate, on_ready, user));
     if (loss_scale != 1.0f) {
         int64_t off[SF_P_COUNT], sz[SF_P_COUNT], total;
         layout(*cfg, off, sz, &total);
@@ -446,6 +458,12 @@ extern "C" int sf_eagle3_backward(const sf_eagle3_config* cfg, const void* param
         SF_CUDA_CHECK_LAUNCH("scale_grads");
     }
     return 0;
+}
+extern "C" int sf_eagle3_backward(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,
+                                  const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float loss_scale,
+                                  float* grads_flat_f32, int accumulate, void* stream) {
+    return sf_eagle3_backward_ex(cfg, params_flat, frozen, batch, workspace, workspace_bytes, loss_scale, grads_flat_f32,
+                                 accumulate, nullptr, nullptr, stream);
 }
 extern "C" int sf_grads_to_bf16(const float* grads_f32, void* grads_bf16, int64_t n, const float* scale_dev, void* stream) {
     return cvt_flat_f32_bf16(grads_f32, grads_bf16, n, scale_dev, reinterpret_cast<cudaStream_t>(stream));

@@ -60,6 +60,8 @@ class SfBatch(Structure):
                 ("hidden_state", c_void_p), ("target", c_void_p)]
 
 
+GRAD_READY_FN = ctypes.CFUNCTYPE(None, c_int32, c_int32, c_void_p)
+
 _declared = False
 
 
@@ -78,6 +80,9 @@ def _declare():
     l.sf_eagle3_backward.restype = ctypes.c_int
     l.sf_eagle3_backward.argtypes = [POINTER(SfConfig), c_void_p, POINTER(SfFrozen), POINTER(SfBatch), c_void_p, c_size_t,
                                      c_float, c_void_p, ctypes.c_int, c_void_p]
+    l.sf_eagle3_backward_ex.restype = ctypes.c_int
+    l.sf_eagle3_backward_ex.argtypes = [POINTER(SfConfig), c_void_p, POINTER(SfFrozen), POINTER(SfBatch), c_void_p, c_size_t,
+                                        c_float, c_void_p, ctypes.c_int, GRAD_READY_FN, c_void_p, c_void_p]
     l.sf_grads_to_bf16.restype = ctypes.c_int
     l.sf_grads_to_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     l.sf_optimizer_step.restype = ctypes.c_int
@@ -318,23 +323,46 @@ class Eagle3Engine:
                                       self._stream()), "sf_eagle3_forward")
         return self.loss, self.metrics
 
-    def backward(self, loss_scale: float = 1.0, accumulate: bool = False) -> None:
+    def backward(self, loss_scale: float = 1.0, accumulate: bool = False, on_ready=None) -> None:
+        """Full backward.  on_ready(first_elem, n_elems) is called (on the host, in stream order of the producing
+        kernels) as soon as each contiguous slice [first_elem, first_elem + n_elems) of the flat gradient is complete."""
         if self._batch is None:
             raise RuntimeError("backward() without a preceding forward(need_grad=True)")
-        check(lib().sf_eagle3_backward(self.cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
-                                       self.workspace_bytes, loss_scale, self.grads_f32.data_ptr(), int(accumulate),
-                                       self._stream()), "sf_eagle3_backward")
+        if on_ready is None:
+            check(lib().sf_eagle3_backward(self.cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
+                                           self.workspace_bytes, loss_scale, self.grads_f32.data_ptr(), int(accumulate),
+                                           self._stream()), "sf_eagle3_backward")
+        else:
+            names = P_NAMES
+            errors = []
+
+            def _cb(first, n, _user):
+                try:
+                    lo = self.offsets[names[first]]
+                    hi = self.offsets[names[first + n - 1]] + self.sizes[names[first + n - 1]]
+                    on_ready(lo, hi - lo)
+                except Exception as exc:  # never let an exception cross the C boundary
+                    errors.append(exc)
+
+            cb = GRAD_READY_FN(_cb)
+            check(lib().sf_eagle3_backward_ex(self.cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
+                                              self.workspace_bytes, loss_scale, self.grads_f32.data_ptr(), int(accumulate),
+                                              cb, None, self._stream()), "sf_eagle3_backward_ex")
+            if errors:
+                raise errors[0]
         self._grads_dirty = True
 
-    def grads_to_bf16(self, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """fp32 accumulators -> the bf16 gradient buffer (optionally times a DEVICE scalar, no host sync)."""
+    def grads_to_bf16(self, scale: Optional[torch.Tensor] = None, first: int = 0, count: Optional[int] = None) -> torch.Tensor:
+        """fp32 accumulators -> the bf16 gradient buffer (optionally times a DEVICE scalar, no host sync); `first`/`count`
+        restrict the conversion to a slice (used when slices are all-reduced as they become ready)."""
         sp = 0
         if scale is not None:
             scale = scale.detach().to(self.device, torch.float32).reshape(1)
             self._scale_keep = scale
             sp = scale.data_ptr()
-        check(lib().sf_grads_to_bf16(self.grads_f32.data_ptr(), self.grads_bf16.data_ptr(), self.n_params, sp, self._stream()),
-              "sf_grads_to_bf16")
+        count = self.n_params - first if count is None else count
+        check(lib().sf_grads_to_bf16(self.grads_f32.data_ptr() + 4 * first, self.grads_bf16.data_ptr() + 2 * first, count, sp,
+                                     self._stream()), "sf_grads_to_bf16")
         return self.grads_bf16
 
     def optimizer_step(self, lr: float, *, grad_scale: float = 1.0, max_grad_norm: float = 0.5, betas=(0.9, 0.999),

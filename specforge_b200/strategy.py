@@ -30,9 +30,10 @@ class _Eagle3StepFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         strategy = ctx.strategy
         eng = strategy.engine
-        eng.backward(loss_scale=1.0, accumulate=strategy._micro_in_window > 0)
-        strategy._micro_in_window += 1
         strategy._last_grad_out = grad_out.detach()
+        hook = strategy.grad_ready_hook if strategy._is_boundary else None
+        eng.backward(loss_scale=1.0, accumulate=strategy._micro_in_window > 0, on_ready=hook)
+        strategy._micro_in_window += 1
         if strategy.return_autograd_grads:
             g = eng.grads_to_bf16(scale=grad_out)
             return g.clone(), None, None, None
@@ -64,6 +65,8 @@ class B200Eagle3TrainStrategy:
         self._module = _Trainable(draft_model)
         self._micro_in_window = 0
         self._last_grad_out: Optional[torch.Tensor] = None
+        self._is_boundary = True            # set by the backend before loss.backward()
+        self.grad_ready_hook = None         # backend: called with (first_elem, n_elems) as gradient slices complete
         draft_model.sync_frozen(target_head_weight)
 
     def trainable_module(self) -> nn.Module:

@@ -16,6 +16,7 @@ class _FakeEngine:
 
     def __init__(self, n, rank):
         self.device = torch.device("cpu")
+        self.n_params = n
         self.params = torch.full((n,), float(rank + 1), dtype=torch.bfloat16)   # ranks start DIFFERENT on purpose
         self.grads_f32 = torch.zeros(n)
         self.grads_bf16 = torch.zeros(n, dtype=torch.bfloat16)
