@@ -131,6 +131,64 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def kernel_timeline(step_fn, out_path, steps=2):
+    """CUPTI kernel timeline of `steps` steps (torch.profiler, CUDA activities only): per-stream busy time, idle gaps on
+    the busiest stream, time per kernel name.  Diagnostic only — nothing measured under the profiler is a bench value."""
+    import gzip, tempfile, collections
+    import torch
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            step_fn()
+        torch.cuda.synchronize()
+    tmp = tempfile.mktemp(suffix=".json")
+    prof.export_chrome_trace(tmp)
+    ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+    os.remove(tmp)
+    ev.sort(key=lambda e: e["ts"])
+    t0, t1 = ev[0]["ts"], max(e["ts"] + e["dur"] for e in ev)
+    streams = collections.defaultdict(list)
+    for e in ev:
+        streams[e["args"].get("stream")].append(e)
+    main = max(streams, key=lambda k: sum(e["dur"] for e in streams[k]))
+    by_name = collections.defaultdict(lambda: [0, 0.0])
+    for e in ev:
+        k = (e["name"][:90], "main" if e["args"].get("stream") == main else "side")
+        by_name[k][0] += 1
+        by_name[k][1] += e["dur"]
+    gaps = []
+    m = streams[main]
+    for a, b in zip(m, m[1:]):
+        g = b["ts"] - (a["ts"] + a["dur"])
+        if g > 3.0:
+            gaps.append({"gap_us": round(g, 1), "after": a["name"][:60], "before": b["name"][:60]})
+    # union busy time over all streams
+    busy, cur_s, cur_e = 0.0, None, None
+    for e in ev:
+        s, en = e["ts"], e["ts"] + e["dur"]
+        if cur_e is None or s > cur_e:
+            if cur_e is not None:
+                busy += cur_e - cur_s
+            cur_s, cur_e = s, en
+        else:
+            cur_e = max(cur_e, en)
+    busy += cur_e - cur_s
+    out = {
+        "steps": steps, "span_ms": (t1 - t0) / 1e3, "any_stream_busy_ms": busy / 1e3, "idle_ms": (t1 - t0 - busy) / 1e3,
+        "streams": {str(k): {"kernels": len(v), "busy_ms": sum(e["dur"] for e in v) / 1e3} for k, v in streams.items()},
+        "main_stream": str(main), "main_gaps_over_3us": len(gaps), "main_gap_total_ms": sum(g["gap_us"] for g in gaps) / 1e3,
+        "largest_gaps": sorted(gaps, key=lambda g: -g["gap_us"])[:40],
+        "by_kernel_ms": [{"name": k[0], "stream": k[1], "n": v[0], "ms": round(v[1] / 1e3, 3)}
+                         for k, v in sorted(by_name.items(), key=lambda kv: -kv[1][1])],
+    }
+    os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
+    with open(out_path, "w") as f:
+        json.dump(out, f, indent=1)
+    with gzip.open(out_path + ".events.gz", "wt") as f:
+        json.dump([[e["name"][:60], e["args"].get("stream"), e["ts"] - t0, e["dur"]] for e in ev], f)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -256,6 +314,9 @@ def run_ours(args):
     ms_e2e, last_loss = timed_e2e(args.steps)
     e2e = world * B / (ms_e2e / args.steps / 1e3)
 
+    if args.timeline and rank == 0:
+        kernel_timeline(lambda: step(dev_batch, False), args.timeline)
+
     sustained, burst, peak_src = peaks()
     flops_step = eng.flops_per_step()
     achieved = (gfl.value / 1e12) / (gms.value / 1e3) if gms.value > 0 else 0.0
@@ -294,8 +355,13 @@ def run_ours(args):
 
 
 def main():
+    wd = int(os.environ.get("SF_BENCH_WATCHDOG", "0"))
+    if wd > 0:   # diagnostic: dump every thread's Python stack and exit if the run takes longer than `wd` seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--timeline", default=None, help="also write a CUPTI kernel-timeline summary of 2 steps to this path")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -61,7 +61,7 @@ static void layout(const sf_eagle3_config& c, int64_t* off, int64_t* sz, int64_t
 struct Plan {
     // persistent forward -> backward
     int64_t h, xcat, qkv, attn, lse, hmid, hn2, gu, act, hf, logits, hs3n;
-    int64_t target_p, pod, ids, pos_mask, loss_mask32, key_mask, kvlen, d2t_idx, row_ws, sd_ws, metrics, misc;
+    int64_t xg, tstats, ids, pos_mask, loss_mask32, key_mask, kvlen, d2t_idx, row_ws, sd_ws, metrics, misc;
     // union region: forward temporaries / backward buffers
     int64_t u_base;
     int64_t tgt_shift, tlogits;                       // forward temporaries
@@ -86,8 +86,8 @@ static Plan make_plan(const sf_eagle3_config& c) {
     p.hf = c.norm_output ? take(T * M * x.H * 2) : p.h + M * x.H * 2;
     p.logits = take(T * M * x.DV * 2);
     p.hs3n = c.fc_norm ? take(M * 3 * x.Ht * 2) : 0;
-    p.target_p = take((int64_t)x.B * (x.S + T) * x.DV * 4);
-    p.pod = take((int64_t)x.B * (x.S + T) * x.DV * 4);
+    p.xg = take((int64_t)x.B * (x.S + T) * x.DV * 2);       // gathered bf16 teacher logits, padded rows
+    p.tstats = take((int64_t)x.B * (x.S + T) * 16);         // {md, 1/dd, p_on_draft scale, 0} per padded row
     p.ids = take((int64_t)x.B * (x.S + T) * 8);
     p.pos_mask = take(M * 4);
     p.loss_mask32 = take(M * 4);
@@ -162,6 +162,11 @@ struct SideStream {
     }
 };
 static SideStream g_side[16];
+static bool loss_on_side() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SF_LOSS_SIDE"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
 static bool overlap_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SF_NO_OVERLAP"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -218,18 +223,25 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
     SF_CUDA_CHECK_LAUNCH("d2t_idx");
     // ---- teacher: shift, frozen target head GEMM, distribution  (strategies/base.py:116-120, eagle3/model.py:445-501)
     SF_TRY(shift_left(bt.target, c.bf(p.tgt_shift), x.B, x.S, x.Ht, st));
-    SF_TRY(mm(c, c.bf(p.tgt_shift), x.Ht, MAJOR_K, fz.target_head, x.Ht, MAJOR_K, c.bf(p.tlogits), x.V, nullptr, 0, M, x.V, x.Ht, EPI_BF16));
     int dev = 0;
     cudaGetDevice(&dev);
     SideStream* side = (overlap_enabled() && dev < 16 && g_side[dev].init()) ? &g_side[dev] : nullptr;
     cudaStream_t ls = st;   // stream of the loss-side work
-    if (side) {
-        ls = side->stream;
-        if (cudaEventRecord(side->fork[0], st) != cudaSuccess || cudaStreamWaitEvent(ls, side->fork[0], 0) != cudaSuccess)
-            return set_error(-5, "side-stream fork failed");
+    if (side) ls = side->stream;
+    // The target-head GEMM is issued in two row halves: the teacher statistics of the first half run on the side stream
+    // under the second half's GEMM, those of the second half under the draft's fc / QKV GEMMs.
+    const int64_t Mh = (side && M >= 1024) ? (M / 2) / 256 * 256 : M;
+    for (int half = 0; half < (Mh < M ? 2 : 1); ++half) {
+        const int64_t r0 = half ? Mh : 0, nr = half ? M - Mh : Mh;
+        SF_TRY(mm(c, c.bf(p.tgt_shift, r0 * x.Ht), x.Ht, MAJOR_K, fz.target_head, x.Ht, MAJOR_K, c.bf(p.tlogits, r0 * x.V), x.V,
+                  nullptr, 0, nr, x.V, x.Ht, EPI_BF16));
+        if (side) {
+            if (cudaEventRecord(side->fork[10 + half], st) != cudaSuccess || cudaStreamWaitEvent(ls, side->fork[10 + half], 0) != cudaSuccess)
+                return set_error(-5, "side-stream fork failed");
+        }
+        SF_TRY(teacher(c.bf(p.tlogits), x.V, c.at<int>(p.d2t_idx), fz.t2d, c.at<int>(p.loss_mask32), c.bf(p.xg), c.at<float>(p.tstats),
+                       c.at<int64_t>(p.ids), c.at<int>(p.pos_mask), x.B, x.S, T, x.V, x.DV, r0, nr, half == 0, side ? 1 : 0, ls));
     }
-    SF_TRY(teacher(c.bf(p.tlogits), x.V, c.at<int>(p.d2t_idx), fz.t2d, c.at<int>(p.loss_mask32), c.at<float>(p.target_p),
-                   c.at<float>(p.pod), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask), x.B, x.S, T, x.V, x.DV, ls));
     // ---- fc: h_0 = [fc_norm_i(chunk_i)] W_fc^T   (llama3_eagle.py:1762-1770; per-third RMSNorm = EAGLE3.1)
     const void* fc_in = bt.hidden_state;
     if (cfg.fc_norm) {
@@ -239,6 +251,7 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         fc_in = c.bf(p.hs3n);
     }
     SF_TRY(mm(c, fc_in, 3 * x.Ht, MAJOR_K, c.W[SF_P_FC], 3 * x.Ht, MAJOR_K, c.bf(p.h), x.H, nullptr, 0, M, x.H, 3 * x.Ht, EPI_BF16));
+    bool side_dirty = side != nullptr;   // the teacher kernels are in flight on the side stream
     const uint8_t* key_mask = bt.attention_mask ? c.at<uint8_t>(p.key_mask) : nullptr;
     if (key_mask) SF_TRY(mask_prefix(key_mask, x.B, x.S, c.at<int>(p.kvlen), c.at<int>(p.kvlen) + x.B, st));
     for (int j = 0; j < T; ++j) {
@@ -287,17 +300,22 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         SF_TRY(mm(c, hf, x.H, MAJOR_K, c.W[SF_P_LM_HEAD], x.H, MAJOR_K, logits, x.DV, nullptr, 0, M, x.DV, x.H, EPI_BF16));
         // loss / metrics / d(logits) in place   (eagle3/model.py:142-199, core/loss.py, core/lk_loss.py)
         const float step_weight = powf(cfg.ploss_decay, (float)j);
-        if (side) {
-            if (cudaEventRecord(side->fork[1 + j], st) != cudaSuccess || cudaStreamWaitEvent(ls, side->fork[1 + j], 0) != cudaSuccess)
+        // The loss runs on the main stream: it is issue- and power-hungry enough that co-running it with a GEMM slows
+        // the GEMM by as much as it saves (measured; SF_LOSS_SIDE=1 re-enables the side-stream placement for A/B runs).
+        // The teacher statistics it consumes come from the side stream, hence the join before the first use.
+        const bool on_side = side && loss_on_side() && j + 1 < T;
+        if (on_side) {
+            if (cudaEventRecord(side->fork[j], st) != cudaSuccess || cudaStreamWaitEvent(ls, side->fork[j], 0) != cudaSuccess)
                 return set_error(-5, "side-stream fork failed");
+            side_dirty = true;
+        } else if (side && side_dirty) {
+            if (cudaEventRecord(side->join, ls) != cudaSuccess || cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess)
+                return set_error(-5, "side-stream join failed");
+            side_dirty = false;
         }
-        SF_TRY(loss_step(logits, x.DV, c.at<float>(p.target_p), c.at<float>(p.pod), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask),
+        SF_TRY(loss_step(logits, x.DV, c.bf(p.xg), c.at<float>(p.tstats), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask),
                          c.at<int>(p.loss_mask32), fz.d2t, x.B, x.S, T, x.DV, j, step_weight, need_grad, cfg.lk_loss_type,
-                         cfg.kl_scale, cfg.kl_decay, c.at<float>(p.row_ws), c.at<float>(p.metrics), side ? 1 : 0, ls));
-    }
-    if (side) {
-        if (cudaEventRecord(side->join, ls) != cudaSuccess || cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess)
-            return set_error(-5, "side-stream join failed");
+                         cfg.kl_scale, cfg.kl_decay, c.at<float>(p.row_ws), c.at<float>(p.metrics), on_side ? 1 : 0, on_side ? ls : st));
     }
     total_loss_kernel<<<1, 64, 0, st>>>(c.at<float>(p.metrics), T, cfg.ploss_decay, loss_out ? loss_out : c.at<float>(p.misc), metrics_out);
     SF_CUDA_CHECK_LAUNCH("total_loss");

@@ -45,6 +45,7 @@ struct GemmParams {
     int num_m_blocks, num_n_blocks;
     void* D2; int ldd2;   // EPI_SWIGLU: act output
     int n_half;           // EPI_SWIGLU / EPI_SWIGLU_BWD: I (columns of gate == columns of up)
+    int group_m;          // M-blocks per raster group (L2 reuse window of the A operand)
 };
 
 template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN>
@@ -116,7 +117,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
     const int cluster_id = blockIdx.x / kCtaGroup;
     const int num_clusters = gridDim.x / kCtaGroup;
-    constexpr int kGroupM = 8;
+    const int kGroupM = p.group_m;
 
     auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
         const int per_group = kGroupM * p.num_n_blocks;

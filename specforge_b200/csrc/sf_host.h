@@ -65,12 +65,13 @@ int swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t M, int I, cu
 int shift_left(const void* src, void* dst, int64_t B, int S, int H, cudaStream_t st);
 int add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t st);
 
-int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, const int* loss_mask, float* target_p,
-            float* pod, int64_t* ids, int* position_mask, int B, int S, int T, int V, int DV, cudaStream_t st);
-int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod, const int64_t* tgt_ids,
+int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, const int* loss_mask, void* xg, float* tstats,
+            int64_t* ids, int* position_mask, int B, int S, int T, int V, int DV, int64_t row0, int64_t nrows, int pad,
+            int lean, cudaStream_t st);
+int loss_step(void* logits, int64_t ld, const void* xg, const float* tstats, const int64_t* tgt_ids,
               const int* position_mask, const int* loss_mask, const int64_t* d2t, int B, int S, int T, int DV, int step,
               float step_weight, int write_grad, int lk_type, float kl_scale, float kl_decay, float* row_ws, float* metrics,
-              int no_smem, cudaStream_t st);
+              int lean, cudaStream_t st);
 int grad_norm(const void* g, int64_t n, float gscale, float* partials_ws, float* out, cudaStream_t st);
 int adamw(const void* g, float* master, float* m1, float* m2, void* param, int64_t n, const float* gnorm, float max_norm,
           float gscale, float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st);

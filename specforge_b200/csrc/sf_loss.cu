@@ -57,269 +57,218 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 
 // ------------------------------------------------------------------ teacher
 // Reference: algorithms/eagle3/model.py:487-501 (_compute_target_p) + :445-484 (padding).
-// One block per (b, s): argmax / logsumexp over the full target vocab, gather of the draft-vocab logits,
-// softmax over the draft vocab.  Output rows live in the [B, S+T, DV] padded layout so that TTT step j
-// reads row (b, s + j) without the reference's per-step `.contiguous()` copies.
-__global__ void __launch_bounds__(512)
-teacher_kernel(const __nv_bfloat16* __restrict__ tl, int64_t ld, const int* __restrict__ d2t_idx,
-               const uint8_t* __restrict__ t2d, const int* __restrict__ loss_mask, float* __restrict__ target_p,
-               float* __restrict__ pod, int64_t* __restrict__ ids, int* __restrict__ position_mask, int S, int T, int V,
-               int DV) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // gathered draft logits (bf16: lossless)
-    __shared__ float redv[32];
-    __shared__ int redi[32];
-    const int64_t r = blockIdx.x;
-    const int b = (int)(r / S), s = (int)(r % S);
-    const __nv_bfloat16* row = tl + r * ld;
-    // pass 1 (single read of the 2*V-byte row): per-thread online (max, argmax, sum exp), then a block merge
-    MaxIdx mi{-INFINITY, 0x7fffffff};
-    float d = 0.f;
-    const int nch = V / 8;
-    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(row) + c), f);
-        float cm = f[0]; int ci = 0;
-#pragma unroll
-        for (int e = 1; e < 8; ++e)
-            if (f[e] > cm) { cm = f[e]; ci = e; }
-        if (cm > mi.v) { d *= __expf(mi.v - cm); mi.v = cm; mi.i = c * 8 + ci; }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d += __expf(f[e] - mi.v);
-    }
-    for (int e = nch * 8 + threadIdx.x; e < V; e += blockDim.x) {
-        const float f = __bfloat162float(row[e]);
-        if (f > mi.v) { d *= __expf(mi.v - f); mi.v = f; mi.i = e; }
-        d += __expf(f - mi.v);
-    }
-    const float my_m = mi.v;
-    mi = block_argmax(mi, redv, redi);
-    const float m = mi.v;
-    d = block_sum_f(my_m == -INFINITY ? 0.f : d * __expf(my_m - m), redv);
-    const float lse = m + logf(d);
-    // pass 2: gather the draft-vocab logits
-    float md = -INFINITY;
-    for (int i = threadIdx.x; i < DV; i += blockDim.x) {
-        const __nv_bfloat16 x = row[d2t_idx[i]];
-        xs[i] = x;
-        md = fmaxf(md, __bfloat162float(x));
-    }
-    md = block_max_f(md, redv);
-    float dd = 0.f;
-    for (int i = threadIdx.x; i < DV; i += blockDim.x) dd += __expf(__bfloat162float(xs[i]) - md);
-    dd = block_sum_f(dd, redv);
-    const float inv = 1.f / dd;
-    const int64_t orow = (int64_t)b * (S + T) + s;
-    float* tp = target_p + orow * DV;
-    float* pp = pod + orow * DV;
-    for (int i = threadIdx.x; i < DV; i += blockDim.x) {
-        const float x = __bfloat162float(xs[i]);
-        tp[i] = __expf(x - md) * inv;
-        pp[i] = __expf(x - lse);
-    }
-    if (threadIdx.x == 0) {
-        ids[orow] = mi.i;
-        position_mask[r] = (t2d[mi.i] ? 1 : 0) * loss_mask[r];
-    }
-}
-// Same kernel with the gathered draft logits held in registers (no dynamic smem): a block then fits next to a
-// resident tcgen05 GEMM CTA, which is what lets the teacher run on a side stream under the draft's first GEMMs.
-template <int kItems>
+// Per (b, s) row: argmax / logsumexp over the full target vocab, gather of the draft-vocab logits, softmax statistics
+// over the draft vocab.  The reference materialises two fp32 [B, S, DV] tensors (target_p and p_on_draft); both are
+// pure functions of the gathered bf16 logits x and three row scalars, so this kernel stores only
+//     xg[row, i]   = x_i (bf16, lossless)                         tstats[row] = {md, inv, cs, 0}
+//     target_p_i   = exp(x_i - md) * inv          (softmax over the draft vocab, fp32, as the reference computes it)
+//     p_on_draft_i = exp(x_i - lse_full) = target_p_i * cs,   cs = dd * exp(md - lse_full)
+// and the loss kernel re-evaluates them: 64 KB of HBM per row instead of 256 KB.  Rows live in the [B, S+T, DV] padded
+// layout so that TTT step j reads row (b, s + j) without the reference's per-step `.contiguous()` copies.
+//
+// Persistent, one 512-thread block per SM, no dynamic smem and <= 72 registers/thread: the block fits NEXT TO a resident
+// tcgen05 GEMM CTA (256 threads x 112 registers, 197 KB smem), which is what lets it run on the side stream under the
+// draft's first GEMMs instead of serialising with them.
 __global__ void __launch_bounds__(512, 2)
-teacher_reg_kernel(const __nv_bfloat16* __restrict__ tl, int64_t ld, const int* __restrict__ d2t_idx,
-                   const uint8_t* __restrict__ t2d, const int* __restrict__ loss_mask, float* __restrict__ target_p,
-                   float* __restrict__ pod, int64_t* __restrict__ ids, int* __restrict__ position_mask, int S, int T, int V,
-                   int DV) {
+teacher_kernel(const __nv_bfloat16* __restrict__ tl, int64_t ld, const int* __restrict__ d2t_idx,
+               const uint8_t* __restrict__ t2d, const int* __restrict__ loss_mask, __nv_bfloat16* __restrict__ xg,
+               float4* __restrict__ tstats, int64_t* __restrict__ ids, int* __restrict__ position_mask, int S, int T, int V,
+               int DV, int64_t row0, int64_t nrows) {
     __shared__ float redv[32];
     __shared__ int redi[32];
-    const int64_t r = blockIdx.x;
-    const int b = (int)(r / S), s = (int)(r % S);
-    const __nv_bfloat16* row = tl + r * ld;
-    MaxIdx mi{-INFINITY, 0x7fffffff};
-    float d = 0.f;
     const int nch = V / 8;
-    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(row) + c), f);
-        float cm = f[0]; int ci = 0;
+    for (int64_t r = row0 + blockIdx.x; r < row0 + nrows; r += gridDim.x) {
+        const int b = (int)(r / S), s = (int)(r % S);
+        const __nv_bfloat16* row = tl + r * ld;
+        // pass 1: one streaming pass over the full vocab with an online max / sum-exp (and first-index argmax)
+        MaxIdx mi{-INFINITY, 0x7fffffff};
+        float d = 0.f;
+#pragma unroll 4
+        for (int c = threadIdx.x; c < nch; c += 512) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(row) + c), f);
+            float cm = f[0]; int ci = 0;
 #pragma unroll
-        for (int e = 1; e < 8; ++e)
-            if (f[e] > cm) { cm = f[e]; ci = e; }
-        if (cm > mi.v) { d *= __expf(mi.v - cm); mi.v = cm; mi.i = c * 8 + ci; }
+            for (int e = 1; e < 8; ++e)
+                if (f[e] > cm) { cm = f[e]; ci = e; }
+            if (cm > mi.v) { d *= __expf(mi.v - cm); mi.v = cm; mi.i = c * 8 + ci; }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d += __expf(f[e] - mi.v);
-    }
-    for (int e = nch * 8 + threadIdx.x; e < V; e += blockDim.x) {
-        const float f = __bfloat162float(row[e]);
-        if (f > mi.v) { d *= __expf(mi.v - f); mi.v = f; mi.i = e; }
-        d += __expf(f - mi.v);
-    }
-    const float my_m = mi.v;
-    mi = block_argmax(mi, redv, redi);
-    const float m = mi.v;
-    d = block_sum_f(my_m == -INFINITY ? 0.f : d * __expf(my_m - m), redv);
-    const float lse = m + logf(d);
-    // gathered draft logits stay in registers as raw bf16 pairs (lossless): 512 x ~60 registers fit beside a GEMM CTA
-    uint32_t xp[kItems / 2];
-    float md = -INFINITY;
-    const __nv_bfloat16 ninf = __float2bfloat16_rn(-INFINITY);
-#pragma unroll
-    for (int k = 0; k < kItems; k += 2) {
-        const int i0 = threadIdx.x + k * 512, i1 = i0 + 512;
-        const __nv_bfloat16 a = (i0 < DV) ? row[d2t_idx[i0]] : ninf;
-        const __nv_bfloat16 bq = (i1 < DV) ? row[d2t_idx[i1]] : ninf;
-        __nv_bfloat162 pr; pr.x = a; pr.y = bq;
-        xp[k / 2] = *reinterpret_cast<uint32_t*>(&pr);
-        md = fmaxf(md, fmaxf(__bfloat162float(a), __bfloat162float(bq)));
-    }
-    md = block_max_f(md, redv);
-    float dd = 0.f;
-#pragma unroll
-    for (int k = 0; k < kItems / 2; ++k) {
-        const __nv_bfloat162 pr = *reinterpret_cast<const __nv_bfloat162*>(&xp[k]);
-        dd += __expf(__bfloat162float(pr.x) - md) + __expf(__bfloat162float(pr.y) - md);   // exp(-inf) = 0 for padding slots
-    }
-    dd = block_sum_f(dd, redv);
-    const float inv = 1.f / dd;
-    const int64_t orow = (int64_t)b * (S + T) + s;
-    float* tp = target_p + orow * DV;
-    float* pp = pod + orow * DV;
-#pragma unroll
-    for (int k = 0; k < kItems; k += 2) {
-        const __nv_bfloat162 pr = *reinterpret_cast<const __nv_bfloat162*>(&xp[k / 2]);
-        const int i0 = threadIdx.x + k * 512, i1 = i0 + 512;
-        const float x0 = __bfloat162float(pr.x), x1 = __bfloat162float(pr.y);
-        if (i0 < DV) { tp[i0] = __expf(x0 - md) * inv; pp[i0] = __expf(x0 - lse); }
-        if (i1 < DV) { tp[i1] = __expf(x1 - md) * inv; pp[i1] = __expf(x1 - lse); }
-    }
-    if (threadIdx.x == 0) {
-        ids[orow] = mi.i;
-        position_mask[r] = (t2d[mi.i] ? 1 : 0) * loss_mask[r];
+            for (int e = 0; e < 8; ++e) d += __expf(f[e] - mi.v);
+        }
+        for (int e = nch * 8 + threadIdx.x; e < V; e += 512) {
+            const float f = __bfloat162float(row[e]);
+            if (f > mi.v) { d *= __expf(mi.v - f); mi.v = f; mi.i = e; }
+            d += __expf(f - mi.v);
+        }
+        const float my_m = mi.v;
+        mi = block_argmax(mi, redv, redi);
+        const float m = mi.v;
+        d = block_sum_f(my_m == -INFINITY ? 0.f : d * __expf(my_m - m), redv);
+        const float lse = m + logf(d);
+        // pass 2: gather the draft-vocab logits (row is L2-hot), store them, online max / sum-exp over the draft vocab
+        const int64_t orow = (int64_t)b * (S + T) + s;
+        __nv_bfloat16* xo = xg + orow * DV;
+        float md = -INFINITY, dd = 0.f;
+#pragma unroll 4
+        for (int i = 2 * threadIdx.x; i < DV; i += 1024) {
+            const __nv_bfloat16 a = row[__ldg(d2t_idx + i)];
+            const float fa = __bfloat162float(a);
+            if (i + 1 < DV) {
+                const __nv_bfloat16 bq = row[__ldg(d2t_idx + i + 1)];
+                const float fb = __bfloat162float(bq);
+                __nv_bfloat162 pr; pr.x = a; pr.y = bq;
+                if ((DV & 1) == 0) *reinterpret_cast<__nv_bfloat162*>(xo + i) = pr;
+                else { xo[i] = a; xo[i + 1] = bq; }
+                const float cm = fmaxf(fa, fb);
+                if (cm > md) { dd *= __expf(md - cm); md = cm; }
+                dd += __expf(fa - md) + __expf(fb - md);
+            } else {
+                xo[i] = a;
+                if (fa > md) { dd *= __expf(md - fa); md = fa; }
+                dd += __expf(fa - md);
+            }
+        }
+        const float my_md = md;
+        md = block_max_f(md, redv);
+        dd = block_sum_f(my_md == -INFINITY ? 0.f : dd * __expf(my_md - md), redv);
+        if (threadIdx.x == 0) {
+            tstats[orow] = make_float4(md, 1.f / dd, dd * __expf(md - lse), 0.f);
+            ids[orow] = mi.i;
+            position_mask[r] = (t2d[mi.i] ? 1 : 0) * loss_mask[r];
+        }
     }
 }
 
 // padded tail rows: target_p = 1/DV, p_on_draft = 0, ids = 0   (eagle3/model.py:459-477)
 __global__ void __launch_bounds__(256)
-teacher_pad_kernel(float* __restrict__ target_p, float* __restrict__ pod, int64_t* __restrict__ ids, int B, int S, int T,
-                   int DV) {
+teacher_pad_kernel(__nv_bfloat16* __restrict__ xg, float4* __restrict__ tstats, int64_t* __restrict__ ids, int B, int S,
+                   int T, int DV) {
     const int64_t total = (int64_t)B * T * DV;
-    const float u = 1.0f / (float)DV;
+    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pr = i / DV;
         const int c = (int)(i % DV);
         const int b = (int)(pr / T), t = (int)(pr % T);
         const int64_t orow = (int64_t)b * (S + T) + S + t;
-        target_p[orow * DV + c] = u;
-        pod[orow * DV + c] = 0.f;
-        if (c == 0) ids[orow] = 0;
+        xg[orow * DV + c] = z;
+        if (c == 0) { ids[orow] = 0; tstats[orow] = make_float4(0.f, 1.0f / (float)DV, 0.f, 0.f); }
     }
 }
 
 // ------------------------------------------------------------------ fused loss / metrics / gradient
 // Reference: core/loss.py:15-21,49-170 (soft-label CE, mean over ALL rows, in-place backward),
 // core/lk_loss.py:43-80 (acceptance = sum_v min(p_on_draft, softmax)), eagle3/model.py:161-173 (top-1).
-// One block per row; the bf16 logits row is staged in smem once, the gradient overwrites it in HBM.
+// One block per row, two passes:
+//   A  logits row from HBM: online max / sum-exp / first-index argmax, ONE block reduction
+//   B  logits row again (L2-hot) + the gathered bf16 teacher logits: target_p re-evaluated (see teacher_kernel),
+//      soft-label CE sum, acceptance sum, and the gradient written over the logits row
+//          d loss / d x_v = coef * (softmax(x)_v * sum_v(target_p) - target_p_v),   sum_v(target_p) = 1
+// 192 KB of HBM traffic per 32000-wide row (64 read + 64 read + 64 written); no dynamic smem, <= 40 registers so three
+// blocks fit per SM and the row-serial latency is hidden.
 struct LossParams {
     __nv_bfloat16* logits; int64_t ld;
-    const float* target_p; const float* pod; const int64_t* tgt_ids;  // padded [B, S+T, ...]
-    const int* position_mask; const int* loss_mask;                  // [B, S] (step-0 masks)
+    const __nv_bfloat16* xg; const float4* tstats; const int64_t* tgt_ids;  // padded [B, S+T, ...]
+    const int* position_mask; const int* loss_mask;                         // [B, S] (step-0 masks)
     const int64_t* d2t;
     int S, T, DV, step;
+    int64_t M;
     float grad_coef;      // ploss_decay^step * upstream / M
     int write_grad;
-    int use_smem;
     float* row_loss; float* row_accept; float* row_correct;  // [M]
 };
 
-__global__ void __launch_bounds__(512) loss_kernel(LossParams p) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+__global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
     __shared__ float redv[32];
+    __shared__ float redd[32];
     __shared__ int redi[32];
+    const int nch = p.DV / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.S), s = (int)(r % p.S);
     const bool in_range = s + p.step < p.S;
     const int pm = in_range ? p.position_mask[(int64_t)b * p.S + s + p.step] : 0;
     const int lm = in_range ? p.loss_mask[(int64_t)b * p.S + s + p.step] : 0;
-    __nv_bfloat16* grow = p.logits + r * p.ld;
-    const int nch = p.DV / 8;
-    const uint4* xrow = p.use_smem ? reinterpret_cast<const uint4*>(smem_raw) : reinterpret_cast<const uint4*>(grow);
-
-    if (pm == 0 && lm == 0) {  // nothing to measure: zero gradient row and leave
+    uint4* grow = reinterpret_cast<uint4*>(p.logits + r * p.ld);
+    if (pm == 0 && lm == 0) {  // nothing to measure: zero gradient row
         if (p.write_grad)
-            for (int c = threadIdx.x; c < nch; c += blockDim.x) reinterpret_cast<uint4*>(grow)[c] = make_uint4(0, 0, 0, 0);
+            for (int c = threadIdx.x; c < nch; c += 512) grow[c] = make_uint4(0, 0, 0, 0);
         if (threadIdx.x == 0) { p.row_loss[r] = 0.f; p.row_accept[r] = 0.f; p.row_correct[r] = 0.f; }
         return;
     }
-    // pass 1: stage the row, max / argmax
+    // pass A: online max / sum-exp, first-index argmax
     MaxIdx mi{-INFINITY, 0x7fffffff};
-    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-        const uint4 u = reinterpret_cast<const uint4*>(grow)[c];
-        if (p.use_smem) reinterpret_cast<uint4*>(smem_raw)[c] = u;
-        float f[8];
-        unpack8(u, f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if (f[e] > mi.v) { mi.v = f[e]; mi.i = c * 8 + e; }
-    }
-    mi = block_argmax(mi, redv, redi);  // contains __syncthreads: smem row is visible afterwards
-    const float m = mi.v;
     float d = 0.f;
-    for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+#pragma unroll 4
+    for (int c = threadIdx.x; c < nch; c += 512) {
         float f[8];
-        unpack8(xrow[c], f);
+        unpack8(grow[c], f);
+        float cm = f[0]; int ci = 0;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d += __expf(f[e] - m);
+        for (int e = 1; e < 8; ++e)
+            if (f[e] > cm) { cm = f[e]; ci = e; }
+        if (cm > mi.v) { d *= __expf(mi.v - cm); mi.v = cm; mi.i = c * 8 + ci; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d += __expf(f[e] - mi.v);
     }
-    d = block_sum_f(d, redv);
+    {   // one combined block reduction of (max, argmax, sum-exp)
+        const float my_m = mi.v;
+        MaxIdx wm = warp_argmax(mi);
+        float wd = warp_sum(my_m == -INFINITY ? 0.f : d * __expf(my_m - wm.v));
+        if (lane == 0) { redv[warp] = wm.v; redi[warp] = wm.i; redd[warp] = wd; }
+        __syncthreads();
+        MaxIdx t{(lane < 16) ? redv[lane] : -INFINITY, (lane < 16) ? redi[lane] : 0x7fffffff};
+        const float td = (lane < 16) ? redd[lane] : 0.f;
+        mi = warp_argmax(t);
+        d = warp_sum(t.v == -INFINITY ? 0.f : td * __expf(t.v - mi.v));
+        __syncthreads();   // red* are reused below
+    }
+    const float m = mi.v;
     const float inv_d = 1.f / d;
     const int64_t trow = (int64_t)b * (p.S + p.T) + s + p.step;
-    float sum_p = 0.f, sum_px = 0.f, sum_min = 0.f;
+    float sum_px = 0.f, sum_min = 0.f;
     if (pm) {
-        const float4* tp = reinterpret_cast<const float4*>(p.target_p + trow * p.DV);
-        const float4* pp = reinterpret_cast<const float4*>(p.pod + trow * p.DV);
-        for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-            float f[8];
-            unpack8(xrow[c], f);
-            const float4 t0 = __ldg(tp + 2 * c), t1 = __ldg(tp + 2 * c + 1);
-            const float4 q0 = __ldg(pp + 2 * c), q1 = __ldg(pp + 2 * c + 1);
-            const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-            const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        // pass B: soft-label CE sums, acceptance, gradient
+        const uint4* tx = reinterpret_cast<const uint4*>(p.xg + trow * p.DV);
+        const float4 ts = __ldg(p.tstats + trow);
+        const float a = inv_d * p.grad_coef;
+        const float tcoef = ts.y * p.grad_coef;
+#pragma unroll 2
+        for (int c = threadIdx.x; c < nch; c += 512) {
+            float f[8], g[8], t[8];
+            unpack8(grow[c], f);
+            unpack8(__ldg(tx + c), g);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                sum_p += tv[e];
-                sum_px += tv[e] * f[e];
-                sum_min += fminf(qv[e], __expf(f[e] - m) * inv_d);
+                const float ex = __expf(f[e] - m);
+                const float et = __expf(g[e] - ts.x);
+                const float tv = et * ts.y;
+                sum_px += tv * f[e];
+                sum_min += fminf(tv * ts.z, ex * inv_d);
+                t[e] = ex * a - et * tcoef;
+            }
+            if (p.write_grad) {
+                uint4 o;
+                o.x = pack_bf16x2(t[0], t[1]); o.y = pack_bf16x2(t[2], t[3]);
+                o.z = pack_bf16x2(t[4], t[5]); o.w = pack_bf16x2(t[6], t[7]);
+                grow[c] = o;
             }
         }
-        sum_p = block_sum_f(sum_p, redv);
-        sum_px = block_sum_f(sum_px, redv);
-        sum_min = block_sum_f(sum_min, redv);
+        sum_px = warp_sum(sum_px);
+        sum_min = warp_sum(sum_min);
+        if (lane == 0) { redv[warp] = sum_px; redd[warp] = sum_min; }
+        __syncthreads();
+        if (warp == 0) {
+            sum_px = warp_sum(lane < 16 ? redv[lane] : 0.f);
+            sum_min = warp_sum(lane < 16 ? redd[lane] : 0.f);
+        }
+    } else if (p.write_grad) {
+        for (int c = threadIdx.x; c < nch; c += 512) grow[c] = make_uint4(0, 0, 0, 0);
     }
     if (threadIdx.x == 0) {
-        p.row_loss[r] = pm ? -(sum_px - (m + logf(d)) * sum_p) : 0.f;
+        p.row_loss[r] = pm ? -(sum_px - (m + logf(d))) : 0.f;
         p.row_accept[r] = pm ? sum_min : 0.f;
         const int64_t pred = mi.i;
         p.row_correct[r] = (lm && (pred + p.d2t[pred] == p.tgt_ids[trow])) ? (float)lm : 0.f;
-    }
-    if (p.write_grad) {
-        if (pm) {
-            const float4* tp = reinterpret_cast<const float4*>(p.target_p + trow * p.DV);
-            const float a = sum_p * inv_d * p.grad_coef;
-            for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-                float f[8];
-                unpack8(xrow[c], f);
-                const float4 t0 = __ldg(tp + 2 * c), t1 = __ldg(tp + 2 * c + 1);
-                const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                uint4 o;
-                o.x = pack_bf16x2(__expf(f[0] - m) * a - tv[0] * p.grad_coef, __expf(f[1] - m) * a - tv[1] * p.grad_coef);
-                o.y = pack_bf16x2(__expf(f[2] - m) * a - tv[2] * p.grad_coef, __expf(f[3] - m) * a - tv[3] * p.grad_coef);
-                o.z = pack_bf16x2(__expf(f[4] - m) * a - tv[4] * p.grad_coef, __expf(f[5] - m) * a - tv[5] * p.grad_coef);
-                o.w = pack_bf16x2(__expf(f[6] - m) * a - tv[6] * p.grad_coef, __expf(f[7] - m) * a - tv[7] * p.grad_coef);
-                reinterpret_cast<uint4*>(grow)[c] = o;
-            }
-        } else {
-            for (int c = threadIdx.x; c < nch; c += blockDim.x) reinterpret_cast<uint4*>(grow)[c] = make_uint4(0, 0, 0, 0);
-        }
     }
 }
 
@@ -371,27 +320,23 @@ metrics_reduce_kernel(const float* __restrict__ row_loss, const float* __restric
 // LK-loss gradient (second pass, only when lk_loss_type is set): d ploss / d logits written in place.
 //   a_r = sum_v min(pod_v, q_v),  d a_r / d x_v = q_v (1[q_v < pod_v] - s_r),  s_r = sum_u 1[q_u < pod_u] q_u
 //   lambda: g = w * dKL + -(1-w) * pm/den * d a_r        alpha: g = -pm / (den * a_r) * d a_r
-__global__ void __launch_bounds__(512) lk_grad_kernel(LossParams p, int lk_type, float step_weight, int64_t M,
+__global__ void __launch_bounds__(512) lk_grad_kernel(LossParams p, int lk_type, float step_weight,
                                                       const float* __restrict__ metrics) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ float redv[32];
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.S), s = (int)(r % p.S);
     const bool in_range = s + p.step < p.S;
     const int pm = in_range ? p.position_mask[(int64_t)b * p.S + s + p.step] : 0;
-    __nv_bfloat16* grow = p.logits + r * p.ld;
+    uint4* grow = reinterpret_cast<uint4*>(p.logits + r * p.ld);
     const int nch = p.DV / 8;
     if (pm == 0) {
-        for (int c = threadIdx.x; c < nch; c += blockDim.x) reinterpret_cast<uint4*>(grow)[c] = make_uint4(0, 0, 0, 0);
+        for (int c = threadIdx.x; c < nch; c += blockDim.x) grow[c] = make_uint4(0, 0, 0, 0);
         return;
     }
-    const uint4* xrow = p.use_smem ? reinterpret_cast<const uint4*>(smem_raw) : reinterpret_cast<const uint4*>(grow);
     float mx = -INFINITY;
     for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-        const uint4 u = reinterpret_cast<const uint4*>(grow)[c];
-        if (p.use_smem) reinterpret_cast<uint4*>(smem_raw)[c] = u;
         float f[8];
-        unpack8(u, f);
+        unpack8(grow[c], f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) mx = fmaxf(mx, f[e]);
     }
@@ -399,49 +344,47 @@ __global__ void __launch_bounds__(512) lk_grad_kernel(LossParams p, int lk_type,
     float d = 0.f;
     for (int c = threadIdx.x; c < nch; c += blockDim.x) {
         float f[8];
-        unpack8(xrow[c], f);
+        unpack8(grow[c], f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) d += __expf(f[e] - m);
     }
     d = block_sum_f(d, redv);
     const float inv_d = 1.f / d;
     const int64_t trow = (int64_t)b * (p.S + p.T) + s + p.step;
-    const float4* tp = reinterpret_cast<const float4*>(p.target_p + trow * p.DV);
-    const float4* pp = reinterpret_cast<const float4*>(p.pod + trow * p.DV);
-    float sum_p = 0.f, s_r = 0.f;
+    const uint4* tx = reinterpret_cast<const uint4*>(p.xg + trow * p.DV);
+    const float4 ts = __ldg(p.tstats + trow);
+    float s_r = 0.f;
     for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-        float f[8];
-        unpack8(xrow[c], f);
-        const float4 t0 = __ldg(tp + 2 * c), t1 = __ldg(tp + 2 * c + 1);
-        const float4 q0 = __ldg(pp + 2 * c), q1 = __ldg(pp + 2 * c + 1);
-        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        sum_p += t0.x + t0.y + t0.z + t0.w + t1.x + t1.y + t1.z + t1.w;
+        float f[8], g[8];
+        unpack8(grow[c], f);
+        unpack8(__ldg(tx + c), g);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { const float q = __expf(f[e] - m) * inv_d; if (q < qv[e]) s_r += q; }
+        for (int e = 0; e < 8; ++e) {
+            const float q = __expf(f[e] - m) * inv_d;
+            const float pod = __expf(g[e] - ts.x) * ts.y * ts.z;
+            if (q < pod) s_r += q;
+        }
     }
-    sum_p = block_sum_f(sum_p, redv);
     s_r = block_sum_f(s_r, redv);
     const float* mt = metrics + p.step * 8;
     const float den = mt[5], w = mt[7];
     const float a_r = p.row_accept[r];
     float ck, ca;
-    if (lk_type == 1) { ck = w * step_weight / (float)M; ca = -(1.f - w) * step_weight / den; }
+    if (lk_type == 1) { ck = w * step_weight / (float)p.M; ca = -(1.f - w) * step_weight / den; }
     else { ck = 0.f; ca = (a_r > 0.f) ? -step_weight / (den * a_r) : 0.f; }
     for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-        float f[8], o[8];
-        unpack8(xrow[c], f);
-        const float4 t0 = __ldg(tp + 2 * c), t1 = __ldg(tp + 2 * c + 1);
-        const float4 q0 = __ldg(pp + 2 * c), q1 = __ldg(pp + 2 * c + 1);
-        const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        float f[8], g[8], o[8];
+        unpack8(grow[c], f);
+        unpack8(__ldg(tx + c), g);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const float q = __expf(f[e] - m) * inv_d;
-            o[e] = ck * (q * sum_p - tv[e]) + ca * q * ((q < qv[e] ? 1.f : 0.f) - s_r);
+            const float tv = __expf(g[e] - ts.x) * ts.y;
+            o[e] = ck * (q - tv) + ca * q * ((q < tv * ts.z ? 1.f : 0.f) - s_r);
         }
         uint4 ou;
         ou.x = pack_bf16x2(o[0], o[1]); ou.y = pack_bf16x2(o[2], o[3]); ou.z = pack_bf16x2(o[4], o[5]); ou.w = pack_bf16x2(o[6], o[7]);
-        reinterpret_cast<uint4*>(grow)[c] = ou;
+        grow[c] = ou;
     }
 }
 
@@ -529,57 +472,52 @@ __global__ void __launch_bounds__(256) cvt_flat_f32_bf16_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------ host wrappers
-int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, const int* loss_mask, float* target_p,
-            float* pod, int64_t* ids, int* position_mask, int B, int S, int T, int V, int DV, cudaStream_t st) {
+static int sm_count() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148; }
+    return n;
+}
+
+// rows [row0, row0 + nrows) of the [B*S, V] teacher logits; `lean` = one block per SM (fits beside a GEMM CTA).
+int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, const int* loss_mask, void* xg, float* tstats,
+            int64_t* ids, int* position_mask, int B, int S, int T, int V, int DV, int64_t row0, int64_t nrows, int pad,
+            int lean, cudaStream_t st) {
     if (V % 8) return set_error(-22, "teacher: target vocab %d must be a multiple of 8", V);
-    const unsigned rows = (unsigned)((int64_t)B * S);
-#define SF_TEACHER_REG(K) teacher_reg_kernel<K><<<rows, 512, 0, st>>>((const __nv_bfloat16*)tl, ld, d2t_idx, t2d, loss_mask, \
-                                                                    target_p, pod, ids, position_mask, S, T, V, DV)
-    if (DV <= 512 * 8) SF_TEACHER_REG(8);
-    else if (DV <= 512 * 32) SF_TEACHER_REG(32);
-    else if (DV <= 512 * 64) SF_TEACHER_REG(64);
-    else {
-        const int smem = DV * 2;
-        if (smem > 200 * 1024) return set_error(-22, "teacher: draft vocab %d too large for the smem-staged path", DV);
-        static int smem_set = 0;
-        if (smem > smem_set) { cudaFuncSetAttribute(teacher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
-        teacher_kernel<<<rows, 512, smem, st>>>((const __nv_bfloat16*)tl, ld, d2t_idx, t2d, loss_mask, target_p, pod, ids,
-                                                position_mask, S, T, V, DV);
+    if (nrows > 0) {
+        int64_t grid = (int64_t)sm_count() * (lean ? 1 : 2);
+        if (grid > nrows) grid = nrows;
+        teacher_kernel<<<(unsigned)grid, 512, 0, st>>>((const __nv_bfloat16*)tl, ld, d2t_idx, t2d, loss_mask, (__nv_bfloat16*)xg,
+                                                     reinterpret_cast<float4*>(tstats), ids, position_mask, S, T, V, DV, row0, nrows);
+        SF_CUDA_CHECK_LAUNCH("teacher");
     }
-#undef SF_TEACHER_REG
-    SF_CUDA_CHECK_LAUNCH("teacher");
-    if (T > 0) {
-        teacher_pad_kernel<<<148 * 4, 256, 0, st>>>(target_p, pod, ids, B, S, T, DV);
+    if (pad && T > 0) {
+        teacher_pad_kernel<<<sm_count(), 256, 0, st>>>((__nv_bfloat16*)xg, reinterpret_cast<float4*>(tstats), ids, B, S, T, DV);
         SF_CUDA_CHECK_LAUNCH("teacher_pad");
     }
     return 0;
 }
 
-int loss_step(void* logits, int64_t ld, const float* target_p, const float* pod, const int64_t* tgt_ids,
+int loss_step(void* logits, int64_t ld, const void* xg, const float* tstats, const int64_t* tgt_ids,
               const int* position_mask, const int* loss_mask, const int64_t* d2t, int B, int S, int T, int DV, int step,
               float step_weight, int write_grad, int lk_type, float kl_scale, float kl_decay, float* row_ws, float* metrics,
-              int no_smem, cudaStream_t st) {
+              int lean, cudaStream_t st) {
     if (DV % 8 || ld % 8) return set_error(-22, "loss: draft vocab %d / ld must be multiples of 8", DV);
     LossParams p;
-    p.logits = (__nv_bfloat16*)logits; p.ld = ld; p.target_p = target_p; p.pod = pod; p.tgt_ids = tgt_ids;
+    p.logits = (__nv_bfloat16*)logits; p.ld = ld; p.xg = (const __nv_bfloat16*)xg; p.tstats = reinterpret_cast<const float4*>(tstats);
+    p.tgt_ids = tgt_ids;
     p.position_mask = position_mask; p.loss_mask = loss_mask; p.d2t = d2t; p.S = S; p.T = T; p.DV = DV; p.step = step;
     const int64_t M = (int64_t)B * S;
+    p.M = M;
     p.grad_coef = step_weight / (float)M; p.write_grad = (lk_type == 0) ? write_grad : 0;
     p.row_loss = row_ws; p.row_accept = row_ws + M; p.row_correct = row_ws + 2 * M;
-    int smem = DV * 2;
-    p.use_smem = !no_smem && smem <= 100 * 1024;
-    if (!p.use_smem) smem = 0;
-    static int smem_set = 0;
-    if (smem > smem_set) { cudaFuncSetAttribute(loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
-    loss_kernel<<<(unsigned)M, 512, smem, st>>>(p);
+    (void)lean;
+    loss_kernel<<<(unsigned)M, 512, 0, st>>>(p);
     SF_CUDA_CHECK_LAUNCH("loss");
     metrics_reduce_kernel<<<1, 1024, 0, st>>>(p.row_loss, p.row_accept, p.row_correct, position_mask, loss_mask, B, S, step,
                                              lk_type, kl_scale, kl_decay, metrics);
     SF_CUDA_CHECK_LAUNCH("metrics_reduce");
     if (lk_type != 0 && write_grad) {
-        static int smem_set2 = 0;
-        if (smem > smem_set2) { cudaFuncSetAttribute(lk_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set2 = smem; }
-        lk_grad_kernel<<<(unsigned)M, 512, smem, st>>>(p, lk_type, step_weight, M, metrics);
+        lk_grad_kernel<<<(unsigned)M, 512, 0, st>>>(p, lk_type, step_weight, metrics);
         SF_CUDA_CHECK_LAUNCH("lk_grad");
     }
     return 0;
