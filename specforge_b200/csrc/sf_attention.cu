@@ -81,29 +81,50 @@ struct AttnParams {
 };
 
 // ------------------------------------------------------------------ diagonal scores
-// sd[b,h,t,i-1] = (q[b,t,h,:] . K_i[b,t,h/g,:]) * scale * log2e          one warp per (row, head)
+// Row kernels of the TTT diagonal terms.  A head's D elements are spread over LPH = D/8 lanes, 16 bytes (8 bf16) each,
+// so one warp serves 32/LPH (row, head) items with fully vectorised loads and log2(LPH) shuffle steps per dot product.
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+        f[2 * i] = __bfloat162float(b.x);
+        f[2 * i + 1] = __bfloat162float(b.y);
+    }
+}
+template <int LPH>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LPH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float dot8(const float (&a)[8], const float (&b)[8]) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += a[e] * b[e];
+    return s;
+}
+
+// sd[b,h,t,i-1] = (q[b,t,h,:] . K_i[b,t,h/g,:]) * scale * log2e
 template <int D>
 __global__ void __launch_bounds__(256) diag_scores_kernel(AttnParams p) {
+    constexpr int LPH = D / 8, HPW = 32 / LPH;
     const int g = p.nh / p.nkv;
     const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane / LPH, l = lane % LPH;
     const int64_t total = (int64_t)p.B * p.S * p.nh;
-    if (warp_global >= total) return;
-    const int h = (int)(warp_global % p.nh);
-    const int64_t r = warp_global / p.nh;  // b*S + t
+    const int64_t item = warp_global * HPW + sub;
+    const bool ok = item < total;
+    const int h = ok ? (int)(item % p.nh) : 0;
+    const int64_t r = ok ? item / p.nh : 0;  // b*S + t
     const int b = (int)(r / p.S), t = (int)(r % p.S);
-    constexpr int E = D / 32;  // elements per lane
-    float qf[E];
-    const __nv_bfloat16* qp = p.q + r * p.ldq + h * D + lane * E;
-#pragma unroll
-    for (int e = 0; e < E; ++e) qf[e] = __bfloat162float(qp[e]);
+    float qf[8];
+    unpack8f(*reinterpret_cast<const uint4*>(p.q + r * p.ldq + h * D + l * 8), qf);
     for (int i = 0; i < p.J; ++i) {
-        const __nv_bfloat16* kp = p.kdiag[i] + r * p.ldkv + (h / g) * D + lane * E;
-        float acc = 0.f;
-#pragma unroll
-        for (int e = 0; e < E; ++e) acc += qf[e] * __bfloat162float(kp[e]);
-        acc = warp_sum(acc);
-        if (lane == 0) p.sd[(((int64_t)b * p.nh + h) * p.S + t) * p.J + i] = acc * p.scale_log2;
+        float kf[8];
+        unpack8f(*reinterpret_cast<const uint4*>(p.kdiag[i] + r * p.ldkv + (h / g) * D + l * 8), kf);
+        const float acc = group_sum<LPH>(dot8(qf, kf));
+        if (ok && l == 0) p.sd[(((int64_t)b * p.nh + h) * p.S + t) * p.J + i] = acc * p.scale_log2;
     }
 }
 
@@ -293,96 +314,101 @@ __global__ void __launch_bounds__(256, 1) attn_fwd_kernel(AttnParams p) {
 // ------------------------------------------------------------------ backward prep: delta = rowsum(dO * O)
 template <int D>
 __global__ void __launch_bounds__(256) attn_delta_kernel(AttnParams p) {
+    constexpr int LPH = D / 8, HPW = 32 / LPH;
     const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane / LPH, l = lane % LPH;
     const int64_t total = (int64_t)p.B * p.S * p.nh;
-    if (warp_global >= total) return;
-    const int h = (int)(warp_global % p.nh);
-    const int64_t r = warp_global / p.nh;
-    constexpr int E = D / 32;
-    const __nv_bfloat16* op = p.out + r * p.ldo + h * D + lane * E;
-    const __nv_bfloat16* dp = p.dout + r * p.lddo + h * D + lane * E;
-    float acc = 0.f;
-#pragma unroll
-    for (int e = 0; e < E; ++e) acc += __bfloat162float(op[e]) * __bfloat162float(dp[e]);
-    acc = warp_sum(acc);
-    if (lane == 0) p.delta[((r / p.S) * p.nh + h) * p.S + (r % p.S)] = acc;
+    const int64_t item = warp_global * HPW + sub;
+    const bool ok = item < total;
+    const int h = ok ? (int)(item % p.nh) : 0;
+    const int64_t r = ok ? item / p.nh : 0;
+    float of[8], df[8];
+    unpack8f(*reinterpret_cast<const uint4*>(p.out + r * p.ldo + h * D + l * 8), of);
+    unpack8f(*reinterpret_cast<const uint4*>(p.dout + r * p.lddo + h * D + l * 8), df);
+    const float acc = group_sum<LPH>(dot8(of, df));
+    if (ok && l == 0) p.delta[((r / p.S) * p.nh + h) * p.S + (r % p.S)] = acc;
 }
 
 // ------------------------------------------------------------------ backward, diagonal terms (row kernel)
-// One warp per (row, kv head): loops the g query heads of the group so dK_i/dV_i need no atomics.
+// One warp per (row, kv head).  The g query heads of the group are processed 2*HPW at a time (HPW of them side by side in
+// the warp's lane groups), the diagonal blocks in the outer loop, so dK_i/dV_i of a row are read-modify-written once per
+// head chunk and need no atomics.
 template <int D>
 __global__ void __launch_bounds__(256) attn_bwd_diag_kernel(AttnParams p) {
+    constexpr int LPH = D / 8, HPW = 32 / LPH, CH = 2 * HPW;
     const int g = p.nh / p.nkv;
     const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane / LPH, l = lane % LPH;
     const int64_t total = (int64_t)p.B * p.S * p.nkv;
     if (warp_global >= total) return;
     const int kvh = (int)(warp_global % p.nkv);
     const int64_t r = warp_global / p.nkv;
     const int b = (int)(r / p.S), t = (int)(r % p.S);
-    constexpr int E = D / 32;
     const float scale = p.scale_log2 * 0.6931471805599453f;  // back to 1/sqrt(D)
-    float dq[4][E];  // up to g <= 8 handled in chunks of 4 heads
-    for (int h0 = 0; h0 < g; h0 += 4) {
-        float qf[4][E], dof[4][E], lse[4], dl[4];
+    for (int h0 = 0; h0 < g; h0 += CH) {
+        float qf[2][8], dof[2][8], dq[2][8], lse[2], dl[2];
+        bool okh[2];
 #pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
-            const int h = kvh * g + h0 + hh;
-            const bool ok = h0 + hh < g;
+        for (int hh = 0; hh < 2; ++hh) {
+            const int hg = h0 + hh * HPW + sub;
+            okh[hh] = hg < g;
+            const int h = kvh * g + (okh[hh] ? hg : 0);
+            unpack8f(*reinterpret_cast<const uint4*>(p.q + r * p.ldq + h * D + l * 8), qf[hh]);
+            unpack8f(*reinterpret_cast<const uint4*>(p.dout + r * p.lddo + h * D + l * 8), dof[hh]);
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                qf[hh][e] = ok ? __bfloat162float(p.q[r * p.ldq + h * D + lane * E + e]) : 0.f;
-                dof[hh][e] = ok ? __bfloat162float(p.dout[r * p.lddo + h * D + lane * E + e]) : 0.f;
-                dq[hh][e] = 0.f;
-            }
-            lse[hh] = ok ? p.lse[((int64_t)b * p.nh + h) * p.S + t] : 0.f;
-            dl[hh] = ok ? p.delta[((int64_t)b * p.nh + h) * p.S + t] : 0.f;
+            for (int e = 0; e < 8; ++e) dq[hh][e] = 0.f;
+            lse[hh] = p.lse[((int64_t)b * p.nh + h) * p.S + t];
+            dl[hh] = p.delta[((int64_t)b * p.nh + h) * p.S + t];
         }
         for (int i = 0; i < p.J; ++i) {
-            float kf[E], vf[E], dk[E], dv[E];
+            float kf[8], vf[8], dk[8], dv[8];
+            unpack8f(*reinterpret_cast<const uint4*>(p.kdiag[i] + r * p.ldkv + kvh * D + l * 8), kf);
+            unpack8f(*reinterpret_cast<const uint4*>(p.vdiag[i] + r * p.ldkv + kvh * D + l * 8), vf);
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                kf[e] = __bfloat162float(p.kdiag[i][r * p.ldkv + kvh * D + lane * E + e]);
-                vf[e] = __bfloat162float(p.vdiag[i][r * p.ldkv + kvh * D + lane * E + e]);
-                dk[e] = 0.f; dv[e] = 0.f;
-            }
+            for (int e = 0; e < 8; ++e) { dk[e] = 0.f; dv[e] = 0.f; }
 #pragma unroll
-            for (int hh = 0; hh < 4; ++hh) {
-                if (h0 + hh >= g) continue;
-                float sdot = 0.f, pdot = 0.f;
-#pragma unroll
-                for (int e = 0; e < E; ++e) { sdot += qf[hh][e] * kf[e]; pdot += dof[hh][e] * vf[e]; }
-                sdot = warp_sum(sdot);
-                pdot = warp_sum(pdot);
-                const float pr = exp2f(sdot * p.scale_log2 - lse[hh]);
+            for (int hh = 0; hh < 2; ++hh) {
+                const float sdot = group_sum<LPH>(dot8(qf[hh], kf));
+                const float pdot = group_sum<LPH>(dot8(dof[hh], vf));
+                const float pr = okh[hh] ? exp2f(sdot * p.scale_log2 - lse[hh]) : 0.f;
                 const float ds = pr * (pdot - dl[hh]) * scale;
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
+                for (int e = 0; e < 8; ++e) {
                     dq[hh][e] += ds * kf[e];
                     dk[e] += ds * qf[hh][e];
                     dv[e] += pr * dof[hh][e];
                 }
             }
-            float* dkp = p.dkdiag[i] + r * p.ldacc + kvh * D + lane * E;
-            float* dvp = p.dvdiag[i] + r * p.ldacc + kvh * D + lane * E;
+            // sum the lane groups (different heads, same elements); group 0 updates dK, group 1 dV
 #pragma unroll
-            for (int e = 0; e < E; ++e) { dkp[e] += dk[e]; dvp[e] += dv[e]; }
+            for (int o = LPH; o < 32; o <<= 1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    dk[e] += __shfl_xor_sync(0xffffffffu, dk[e], o);
+                    dv[e] += __shfl_xor_sync(0xffffffffu, dv[e], o);
+                }
+            }
+            if (sub < 2) {
+                float* dst = (sub == 0 ? p.dkdiag[i] : p.dvdiag[i]) + r * p.ldacc + kvh * D + l * 8;
+                float4 a0 = reinterpret_cast<float4*>(dst)[0], a1 = reinterpret_cast<float4*>(dst)[1];
+                const float* src = sub == 0 ? dk : dv;
+                a0.x += src[0]; a0.y += src[1]; a0.z += src[2]; a0.w += src[3];
+                a1.x += src[4]; a1.y += src[5]; a1.z += src[6]; a1.w += src[7];
+                reinterpret_cast<float4*>(dst)[0] = a0;
+                reinterpret_cast<float4*>(dst)[1] = a1;
+            }
         }
 #pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
-            if (h0 + hh >= g) continue;
-            const int h = kvh * g + h0 + hh;
-#pragma unroll
-            for (int e = 0; e < E; ++e) p.dq_diag[r * (int64_t)(p.nh * D) + h * D + lane * E + e] = dq[hh][e];
+        for (int hh = 0; hh < 2; ++hh) {
+            if (!okh[hh]) continue;
+            const int h = kvh * g + h0 + hh * HPW + sub;
+            float4* dst = reinterpret_cast<float4*>(p.dq_diag + r * (int64_t)(p.nh * D) + h * D + l * 8);
+            dst[0] = make_float4(dq[hh][0], dq[hh][1], dq[hh][2], dq[hh][3]);
+            dst[1] = make_float4(dq[hh][4], dq[hh][5], dq[hh][6], dq[hh][7]);
         }
     }
 }
 
-// ------------------------------------------------------------------ backward, block 0: dK / dV (KV tile stationary)
-// CTA = (kv block of 128 keys, kv head, batch); loops the g query heads of the group and the query tiles
-// (32 rows) at or below the diagonal.  Scores are computed transposed (S^T = K Q^T) so that P^T / dS^T come
-// out of the accumulators already in A-operand layout for dV += P^T dO and dK += dS^T Q.
 template <int D>
 __global__ void __launch_bounds__(256, 1) attn_bwd_dkv_kernel(AttnParams p) {
     constexpr int BC = 128, BR = 32, CH = D / 8;
@@ -665,7 +691,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_dq_kernel(AttnParams p) {
 template <int D>
 static int attn_fwd_t(AttnParams& p, cudaStream_t st) {
     if (p.J > 0) {
-        const int64_t warps = (int64_t)p.B * p.S * p.nh;
+        const int64_t warps = ((int64_t)p.B * p.S * p.nh + (256 / D) - 1) / (256 / D);   // 256/D (row, head) items per warp
         diag_scores_kernel<D><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
         SF_CUDA_CHECK_LAUNCH("diag_scores");
     }
@@ -680,7 +706,7 @@ static int attn_fwd_t(AttnParams& p, cudaStream_t st) {
 template <int D>
 static int attn_bwd_t(AttnParams& p, cudaStream_t st) {
     {
-        const int64_t warps = (int64_t)p.B * p.S * p.nh;
+        const int64_t warps = ((int64_t)p.B * p.S * p.nh + (256 / D) - 1) / (256 / D);
         attn_delta_kernel<D><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
         SF_CUDA_CHECK_LAUNCH("attn_delta");
     }
@@ -755,11 +781,7 @@ int mask_prefix(const uint8_t* key_mask, int B, int S, int* kvlen, int* nonprefi
     return 0;
 }
 
-static bool use_legacy_attention() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SF_ATTN_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
+static bool use_legacy_attention() { return opt(OPT_ATTN_LEGACY) == 1; }
 
 int attn_fwd(const AttnDesc& a, cudaStream_t st) {
     if (int rc = attn_validate(a)) return rc;
@@ -768,7 +790,8 @@ int attn_fwd(const AttnDesc& a, cudaStream_t st) {
     if (!use_legacy_attention()) {
         // diagonal scores by the row kernel, block 0 on tcgen05
         if (p.J > 0) {
-            const int64_t warps = (int64_t)p.B * p.S * p.nh;
+            const int ipw = 256 / a.head_dim;   // (row, head) items per warp
+            const int64_t warps = ((int64_t)p.B * p.S * p.nh + ipw - 1) / ipw;
             if (a.head_dim == 128) diag_scores_kernel<128><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
             else diag_scores_kernel<64><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
             SF_CUDA_CHECK_LAUNCH("diag_scores");
@@ -780,7 +803,7 @@ int attn_fwd(const AttnDesc& a, cudaStream_t st) {
 template <int D>
 static int attn_bwd_prep_t(AttnParams& p, cudaStream_t st) {
     {
-        const int64_t warps = (int64_t)p.B * p.S * p.nh;
+        const int64_t warps = ((int64_t)p.B * p.S * p.nh + (256 / D) - 1) / (256 / D);
         attn_delta_kernel<D><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
         SF_CUDA_CHECK_LAUNCH("attn_delta");
     }

@@ -82,9 +82,8 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     // Raster: tiles walk N inside groups of `group_m` M-blocks, so a group's A rows stay L2-resident while B streams.
     // Forward / dgrad GEMMs (K <= 16K) measured fastest with 16 (half the B re-reads of 8: -4 % step time); the
     // weight-gradient GEMMs (K = T*M) cannot keep an A panel in L2 at all and want the squarest wave (8 x 9 tiles).
-    static const int group_m_env = [] { const char* e = getenv("SF_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
-    static const int group_m_wgrad_env = [] { const char* e = getenv("SF_GEMM_GROUP_M_WGRAD"); return e ? atoi(e) : 0; }();
-    p.group_m = g.K > 32768 ? (group_m_wgrad_env > 0 ? group_m_wgrad_env : 8) : (group_m_env > 0 ? group_m_env : 16);
+    const int gm = opt(OPT_GEMM_GROUP_M), gmk = opt(OPT_GEMM_GROUP_M_MIDK), gmw = opt(OPT_GEMM_GROUP_M_WGRAD);
+    p.group_m = g.K > 32768 ? (gmw > 0 ? gmw : 8) : g.K > 4608 ? (gmk > 0 ? gmk : 16) : (gm > 0 ? gm : 16);
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int clusters = num_sms() / G;
     if (tiles < clusters) clusters = tiles;
@@ -101,10 +100,15 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     cfg.blockDim = dim3(Cfg::kThreads);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (g.overlap_prev && !opt(OPT_NO_PDL) && !g_prof.on) {   // per-launch profiling events would sit between the two kernels
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_prof.on) {
         std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -87,6 +87,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+    // Let a programmatically-dependent successor (GemmDesc::overlap_prev) be scheduled as soon as this grid's CTAs exit.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;

@@ -10,6 +10,11 @@ int set_error(int code, const char* fmt, ...);
 // Every kernel launch made by this library goes through here; bench.py reports the count.
 void count_launch(int n = 1);
 
+// Tuning / A-B switches.  Each starts from its environment variable (SF_<NAME>, upper case) and can be changed at run time
+// through sf_debug_option() so that two settings can be alternated inside ONE process (boxes of the pool differ by +-8 %).
+enum Opt { OPT_NO_PDL, OPT_LOSS_SIDE, OPT_NO_OVERLAP, OPT_NO_SWIGLU_FUSION, OPT_GEMM_GROUP_M, OPT_GEMM_GROUP_M_MIDK, OPT_GEMM_GROUP_M_WGRAD, OPT_ATTN_LEGACY, OPT_COUNT };
+int opt(Opt o);
+
 struct GemmDesc {
     const void* A; int64_t lda; int a_major;   // a_major/b_major: 0 = K-major, 1 = MN-major
     const void* B; int64_t ldb; int b_major;
@@ -20,6 +25,8 @@ struct GemmDesc {
     int cta_group;                             // 0 = auto, 1, 2
     void* D2 = nullptr; int64_t ldd2 = 0;      // EPI_SWIGLU: act output [M, I]
     int n_half = 0;                            // EPI_SWIGLU(_BWD): I
+    int overlap_prev = 0;                      // 1: independent of the previous kernel in the stream — programmatic
+                                               // dependent launch lets its CTAs start on the SMs the previous GEMM's tail frees
 };
 int gemm(const GemmDesc& g, cudaStream_t stream);
 
