@@ -156,6 +156,29 @@ int sf_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t M, int I,
 int sf_rope(void* x, int64_t ld, int n_heads, int head_dim, const void* cos_t, const void* sin_t, int S, int pos_offset,
             int64_t M, int inverse, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Packed shards of offline feature records (host side of the input feed).
+ * Replaces, for reading, the reference's one-`torch.save`-file-per-sample layout (scripts/prepare_hidden_states.py:446-480,
+ * :578-595; reader runtime/data_plane/feature_store.py:235-240) followed by per-sample truncation
+ * (algorithms/eagle3/data.py:10-27) and host-side pad + concatenate (data/utils.py:106-200).  File layout: see
+ * specforge_b200/csrc/sf_shard.cpp.  No CUDA involved; destination buffers are plain host pointers (pin them).
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum { SF_DT_U8 = 0, SF_DT_I32 = 1, SF_DT_I64 = 2, SF_DT_BF16 = 3, SF_DT_F16 = 4, SF_DT_F32 = 5, SF_DT_BOOL = 6 };
+int sf_shard_open(const char* path, void** handle);
+void sf_shard_close(void* handle);
+int64_t sf_shard_num_records(void* handle);
+int sf_shard_num_features(void* handle);
+/* name40: caller buffer of 40 bytes (NUL-padded raw key, e.g. "aux_hidden_state"); width = elements per token */
+int sf_shard_feature_info(void* handle, int feature, char* name40, int* dtype, int* elem_bytes, int64_t* width);
+int64_t sf_shard_record_tokens(void* handle, int64_t record);
+/* recompute the payload CRC-32 from disk: 0 = matches the index, 1 = mismatch, <0 = error */
+int sf_shard_verify_record(void* handle, int64_t record);
+/* Gather n_rec records into batch-major buffers: dst[f] is [n_rec, pad_tokens, width_f] (row-major) for feature f, or NULL
+ * to skip it.  Each record contributes its first min(num_tokens, max_tokens) tokens; the rest of its pad_tokens rows are
+ * zero-filled.  Fails if a truncated record is longer than pad_tokens.  n_threads pread() workers (<= 0: 4). */
+int sf_shard_read_batch(void* handle, const int64_t* records, int n_rec, int64_t max_tokens, int64_t pad_tokens,
+                        void* const* dst, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

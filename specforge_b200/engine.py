@@ -232,6 +232,7 @@ class Eagle3Engine:
         self.frozen_tensors: Dict[str, torch.Tensor] = {}
         self._frozen = None
         self._batch = None
+        self._call_cfg = self.cfg
         self._batch_keep = None
         self._grads_dirty = False
 
@@ -301,10 +302,28 @@ class Eagle3Engine:
         }
         am = batch.get("attention_mask")
         t["attention_mask"] = None if am is None else am.to(dev, torch.int64, non_blocking=True).contiguous()
-        if t["input_ids"].shape != (B, S):
-            raise ValueError(f"input_ids must be [{B}, {S}], got {tuple(t['input_ids'].shape)}")
+        if t["input_ids"].dim() != 2:
+            raise ValueError(f"input_ids must be [batch, seq], got {tuple(t['input_ids'].shape)}")
+        # The engine is bound to a MAXIMUM (batch, seq_len): the reference collator pads each batch to its own longest
+        # sample (data/utils.py:122) and the loss is a mean over all B*S rows (core/loss.py), so the batch's own shape
+        # has to reach the kernels.  The C ABI takes the shape per call; only the workspace bound is fixed.
+        Bb, Sb = (int(v) for v in t["input_ids"].shape)
+        if (Bb, Sb) == (B, S):
+            self._call_cfg = self.cfg
+        else:
+            cfg = SfConfig.from_buffer_copy(self.cfg)
+            cfg.batch, cfg.seq_len = Bb, Sb
+            need = lib().sf_eagle3_workspace_bytes(cfg)
+            if need == 0:
+                check(-22, "sf_eagle3_workspace_bytes")
+            if need > self.workspace_bytes or Sb + self.T > self.cfg.rope_rows:
+                raise ValueError(f"batch [{Bb}, {Sb}] exceeds the shape the engine was bound with ([{B}, {S}])")
+            self._call_cfg = cfg
+        B, S = Bb, Sb
         if t["loss_mask"].numel() != B * S:
             raise ValueError(f"loss_mask must have {B * S} elements, got {tuple(t['loss_mask'].shape)}")
+        if t["attention_mask"] is not None and t["attention_mask"].numel() != B * S:
+            raise ValueError(f"attention_mask must have {B * S} elements, got {tuple(t['attention_mask'].shape)}")
         if t["hidden_state"].shape != (B, S, 3 * d.target_hidden_size):
             raise ValueError(f"hidden_state must be [{B}, {S}, {3 * d.target_hidden_size}], got {tuple(t['hidden_state'].shape)}")
         if t["target"].shape != (B, S, d.target_hidden_size):
@@ -318,7 +337,7 @@ class Eagle3Engine:
         if self._frozen is None:
             raise RuntimeError("set_frozen() must be called before forward()")
         self._bind_batch(batch)
-        check(lib().sf_eagle3_forward(self.cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
+        check(lib().sf_eagle3_forward(self._call_cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
                                       self.workspace_bytes, self.metrics.data_ptr(), self.loss.data_ptr(), int(need_grad),
                                       self._stream()), "sf_eagle3_forward")
         return self.loss, self.metrics
@@ -329,7 +348,7 @@ class Eagle3Engine:
         if self._batch is None:
             raise RuntimeError("backward() without a preceding forward(need_grad=True)")
         if on_ready is None:
-            check(lib().sf_eagle3_backward(self.cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
+            check(lib().sf_eagle3_backward(self._call_cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
                                            self.workspace_bytes, loss_scale, self.grads_f32.data_ptr(), int(accumulate),
                                            self._stream()), "sf_eagle3_backward")
         else:
@@ -345,7 +364,7 @@ class Eagle3Engine:
                     errors.append(exc)
 
             cb = GRAD_READY_FN(_cb)
-            check(lib().sf_eagle3_backward_ex(self.cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
+            check(lib().sf_eagle3_backward_ex(self._call_cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr,
                                               self.workspace_bytes, loss_scale, self.grads_f32.data_ptr(), int(accumulate),
                                               cb, None, self._stream()), "sf_eagle3_backward_ex")
             if errors:

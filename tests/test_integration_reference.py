@@ -40,3 +40,34 @@ def test_registry_binding_and_state_dict_contract(ref, cfg_name, monkeypatch):
     assert isinstance(ours, B200Eagle3DraftModel)
     assert ours.state_dict_spec() == ref_sd
     assert ours.dims.fc_norm == bool(getattr(config, "fc_norm", False))
+
+
+def test_shard_batches_equal_the_reference_input_pipe(ref, tmp_path):
+    """Input-feed row: SFPK shard batches == the reference's OfflineManifestReader listing + load_feature_file +
+    normalize_offline_sample + DataCollatorWithPadding on the same files; also pins oracle/offline_feed_oracle.py."""
+    import torch
+    from specforge.algorithms.eagle3.data import normalize_offline_sample
+    from specforge.data.utils import DataCollatorWithPadding
+    from specforge.runtime.data_plane.feature_store import load_feature_file
+    from specforge.runtime.data_plane.offline_reader import OfflineManifestReader
+    from oracle import offline_feed_oracle as FO
+    from specforge_b200.shards import Eagle3ShardLoader, pack_offline_dir
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_shards import _write_reference_files
+    _write_reference_files(str(tmp_path / "feat"), [37, 5, 64, 1, 90, 12, 33, 48], seed=9)
+    reader = OfflineManifestReader(str(tmp_path / "feat"), run_id="offline", max_len=48)
+    refs = reader.read()
+    assert len(refs) == 8
+    (shard,) = pack_offline_dir(str(tmp_path / "feat"), str(tmp_path / "a.sfpk"))
+    collate = DataCollatorWithPadding()
+    for bi, batch in enumerate(Eagle3ShardLoader([shard], batch_size=4, max_len=48)):
+        rs = refs[4 * bi:4 * bi + 4]
+        assert batch.sample_ids == [r.sample_id for r in rs]
+        raws = [load_feature_file(r.feature_store_uri[len("file://"):]) for r in rs]
+        want = collate([normalize_offline_sample(raw, 48) for raw in raws])
+        mine = FO.collate_with_padding([FO.normalize_offline_sample(raw, 48) for raw in raws])
+        for k in ("input_ids", "attention_mask", "loss_mask", "hidden_state", "target"):
+            w, g, o = want[k], batch.tensors[k], mine[k]
+            assert g.dtype == w.dtype and g.shape == w.shape and o.shape == w.shape, k
+            same = lambda a, b: torch.equal(a.view(torch.int16), b.view(torch.int16)) if a.dtype == torch.bfloat16 else torch.equal(a, b)
+            assert same(g, w) and same(o, w), k

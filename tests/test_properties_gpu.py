@@ -42,6 +42,20 @@ def test_deterministic_and_accumulation_and_scale():
     assert torch.equal(eng.loss, l1)
 
 
+def test_batch_shape_below_the_bound_shape_is_exact():
+    """The reference collator pads each batch to ITS longest sample (data/utils.py:122): an engine bound for [3, 200] must
+    run a [2, 131] batch exactly like an engine bound for [2, 131] (same loss mean over B*S rows, same gradients)."""
+    big, *_ = _make(SMALL, 3, 200, 3)
+    exact, _, _, batch, *_ = _make(SMALL, 2, 131, 3, pad_tail=9)
+    exact.forward(batch); exact.backward()
+    big.forward(batch); big.backward()
+    assert torch.equal(big.loss, exact.loss) and torch.equal(big.metrics, exact.metrics)
+    assert torch.equal(big.grads_f32, exact.grads_f32)
+    with pytest.raises(ValueError):
+        too_long = {k: torch.cat([v, v, v, v], dim=1) for k, v in batch.items()}     # [2, 524] > the [3, 200] bound
+        big.forward(too_long)
+
+
 @pytest.mark.parametrize("B,S,T,pad", [(1, 64, 1, 0), (1, 65, 2, 3), (3, 130, 9, 70), (2, 448, 4, 0)])
 def test_ragged_and_extreme_shapes_match_oracle(B, S, T, pad):
     from oracle import eagle3_oracle as O
