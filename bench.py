@@ -322,6 +322,51 @@ def run_ours(args):
     ms_e2e, last_loss = timed_e2e(args.steps)
     e2e = world * B / (ms_e2e / args.steps / 1e3)
 
+    e2e_shards = None
+    if args.feed_shards:
+        # optional: the same end-to-end loop fed from an SFPK shard on local disk (specforge_b200/shards.py): every step's
+        # records are gathered from the file into pinned batch tensors by the C++ reader, then H2D, then the step
+        import tempfile
+        from specforge_b200.shards import Eagle3ShardLoader, ShardWriter
+        tmpd = tempfile.mkdtemp(prefix="sfpk_bench_")
+        shard = os.path.join(tmpd, f"rank{rank}.sfpk")
+        feats = [("input_ids", torch.int64, 1), ("loss_mask", torch.int64, 1), ("hidden_state", torch.bfloat16, H),
+                 ("aux_hidden_state", torch.bfloat16, 3 * H)]
+        with ShardWriter(shard, feats) as w:
+            for rep in range(2):
+                for i in range(B):
+                    w.add({"input_ids": host_t["input_ids"][i], "loss_mask": host_t["loss_mask"][i],
+                           "hidden_state": host_t["target"][i], "aux_hidden_state": host_t["hidden_state"][i]})
+        loader = Eagle3ShardLoader([shard], batch_size=B, max_len=S, pad_to=S, threads=8, buffers=4)
+
+        def shard_batches(n):
+            done = 0
+            while done < n:
+                for b in loader:
+                    yield b
+                    done += 1
+                    if done == n:
+                        return
+
+        for batch in DevicePrefetcher(shard_batches(3), device=dev):
+            step(batch, True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for batch in DevicePrefetcher(shard_batches(args.steps), device=dev):
+            last_s = step(batch, True)
+        e1.record()
+        barrier()
+        ms_sh = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_sh], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_sh = float(t.item())
+        e2e_shards = {"value": world * B / (ms_sh / args.steps / 1e3), "unit": "samples/s", "ms_per_step": ms_sh / args.steps,
+                      "disk_read_bytes_per_step": h2d, "last_loss": last_s, "source": "SFPK shard on local disk, page cache warm"}
+        import shutil
+        shutil.rmtree(tmpd, ignore_errors=True)
+
     for ab in (args.ab or []) if rank == 0 else []:
         # in-process A/B of a library switch: the settings alternate step by step, so box-to-box clock differences cancel
         import statistics
@@ -355,6 +400,7 @@ def run_ours(args):
                    "weights": "random-init, reference shapes; draft-vocab rows of the frozen head x2 so ~95 % of positions are live"},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
+        "e2e_shards": e2e_shards,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "sf::gemm_kernel (tcgen05, all %d launches/step)" % (n_gemm // max(1, args.steps)),
@@ -389,6 +435,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--ab", action="append", default=None, help="diagnostic: NAME=V0,V1[,..] alternates sf_debug_option(NAME) step by step, prints ms/step per value to stderr")
     ap.add_argument("--ab-rounds", type=int, default=10)
+    ap.add_argument("--feed-shards", action="store_true", help="also measure e2e fed from an SFPK shard on local disk")
     ap.add_argument("--timeline", default=None, help="also write a CUPTI kernel-timeline summary of 2 steps to this path")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)

@@ -86,18 +86,23 @@ class ShardWriter:
                 tokens = rows.shape[0]
             elif rows.shape[0] != tokens:
                 raise ValueError(f"feature {name!r} has {rows.shape[0]} tokens, others {tokens}")
-            blocks.append(rows.cpu().view(torch.uint8).numpy().tobytes() if rows.numel() else b"")
-        payload = bytearray()
-        for b in blocks:       # every block ends on a 64-byte boundary, so block_offset() in the reader is closed-form
-            payload += b
-            payload += b"\0" * (_align(len(payload), 64) - len(payload))
-        off = self._pos
-        self._f.write(payload)
-        self._pos += len(payload)
+            blocks.append(rows.cpu())
+        off, crc, n = self._pos, 0, 0
+        for rows in blocks:    # every block ends on a 64-byte boundary, so block_offset() in the reader is closed-form
+            if rows.numel():
+                mv = memoryview(rows.view(torch.uint8).numpy()).cast("B")
+                self._f.write(mv)
+                crc = zlib.crc32(mv, crc)
+                n += len(mv)
+            tail = b"\0" * (_align(n, 64) - n)
+            self._f.write(tail)
+            crc = zlib.crc32(tail, crc)
+            n += len(tail)
+        self._pos += n
         pad = _align(self._pos, 4096) - self._pos
         self._f.write(b"\0" * pad)
         self._pos += pad
-        self._index.append((off, int(tokens), zlib.crc32(bytes(payload)) & 0xFFFFFFFF))
+        self._index.append((off, int(tokens), crc & 0xFFFFFFFF))
         return len(self._index) - 1
 
     def close(self) -> None:
@@ -254,11 +259,15 @@ class Eagle3ShardLoader:
 
     def __init__(self, shards: Sequence[str], batch_size: int, max_len: int, *, run_id: str = "offline", shuffle: bool = False,
                  seed: int = 0, drop_last: bool = True, pad_to: Optional[int] = None, rank: int = 0, world: int = 1,
-                 threads: int = 8, pin: bool = True):
+                 threads: int = 8, pin: bool = True, buffers: int = 4):
         self.readers = [ShardReader(p) for p in ([shards] if isinstance(shards, str) else shards)]
         self.batch_size, self.max_len, self.run_id = batch_size, max_len, run_id
         self.shuffle, self.seed, self.drop_last, self.pad_to = shuffle, seed, drop_last, pad_to
         self.rank, self.world, self.threads, self.pin = rank, world, threads, pin
+        # Ring of reusable (pinned) destination buffer sets: no page faults / cudaHostAlloc per batch.  A yielded batch's host
+        # tensors stay valid until `buffers - 1` further batches have been produced (DevicePrefetcher depth 2 needs >= 3).
+        self._ring: List[Dict[str, torch.Tensor]] = [dict() for _ in range(max(1, buffers))]
+        self._ring_pos = 0
         self.epoch = 0
         self._where: List[Tuple[int, int]] = [(i, r) for i, rd in enumerate(self.readers) for r in range(len(rd))]
         for rd in self.readers:
@@ -289,8 +298,11 @@ class Eagle3ShardLoader:
         B = len(sample_indices)
         if len(by_reader) == 1:
             (ri, _), = by_reader.items()
+            slot = self._ring[self._ring_pos]
+            self._ring_pos = (self._ring_pos + 1) % len(self._ring)
             raw = self.readers[ri].read_batch([self._where[gi][1] for gi in sample_indices], self.max_len, S, EAGLE3_KEYS,
-                                              self.pin, self.threads)
+                                              self.pin, self.threads, out=slot)
+            slot.update(raw)
         else:                                        # a batch straddling shards: gather per shard, then place the rows
             raw = {}
             for ri, poss in by_reader.items():
