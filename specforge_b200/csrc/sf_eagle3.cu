@@ -324,9 +324,17 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
     cudaStream_t st = c.st;
     int64_t off[SF_P_COUNT], sz[SF_P_COUNT], total;
     layout(cfg, off, sz, &total);
-    // When not accumulating we still need zeroed norm-weight slots (they are filled by atomics) and, because the
-    // weight-gradient GEMMs run in accumulate mode only when asked, a clean start is cheapest as one memset.
-    if (!accumulate) { if (cudaMemsetAsync(G, 0, (size_t)total * 4, st) != cudaSuccess) return set_error(-5, "memset grads failed"); }
+    // A fresh step zeroes only the norm-weight slots (their gradients are summed over the TTT steps by the row kernels);
+    // every matrix gradient is produced by exactly one GEMM, which then simply overwrites its slice (EPI_F32) instead of
+    // read-modify-writing 1.6 GB of zeros.  With `accumulate` the GEMMs add into what is there (EPI_F32_ACCUM).
+    if (!accumulate) {
+        const size_t n0 = (size_t)(off[SF_P_LM_HEAD] - off[SF_P_HIDDEN_NORM]) * 4;   // hidden_norm, input_norm, post_norm, norm
+        if (cudaMemsetAsync(G + off[SF_P_HIDDEN_NORM], 0, n0, st) != cudaSuccess) return set_error(-5, "memset grads failed");
+        if (total > off[SF_P_FC_NORM0] &&
+            cudaMemsetAsync(G + off[SF_P_FC_NORM0], 0, (size_t)(total - off[SF_P_FC_NORM0]) * 4, st) != cudaSuccess)
+            return set_error(-5, "memset grads failed");
+    }
+    const int wepi = accumulate ? EPI_F32_ACCUM : EPI_F32;
     // loss_scale is applied by scaling d(logits)-derived quantities linearly: we fold it into the final gradients
     // only when != 1 (the common 1/accumulation_steps case is passed to forward via grad_coef by the caller).
     if (cudaMemsetAsync(c.ws + p.dk_acc, 0, (size_t)T * M * x.KV * 4, st) != cudaSuccess ||
@@ -402,23 +410,23 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
     auto ready = [&](int first, int n) { if (on_ready) on_ready(first, n, user); };
     const int64_t TM = (int64_t)T * M;
     ready(SF_P_HIDDEN_NORM, 4);     // the four norm-weight gradients were finished inside the TTT loop
-    SF_TRY(mm(c, c.bf(p.logits), x.DV, MAJOR_MN, c.bf(p.hf), x.H, MAJOR_MN, Gn + off[SF_P_LM_HEAD], x.H, nullptr, 0, x.DV, x.H, TM, EPI_F32_ACCUM));
+    SF_TRY(mm(c, c.bf(p.logits), x.DV, MAJOR_MN, c.bf(p.hf), x.H, MAJOR_MN, Gn + off[SF_P_LM_HEAD], x.H, nullptr, 0, x.DV, x.H, TM, wepi));
     ready(SF_P_LM_HEAD, 1);
     // The weight-gradient GEMMs are mutually independent (disjoint outputs, inputs final): without a caller hook between
     // them each one is launched as a programmatic dependent of the previous, so its CTAs fill the SMs the previous
     // GEMM's last partial wave leaves idle (2000/768/1536/256/768 tiles over 74 clusters: 4 % of the wgrad time).
     const int chain = on_ready ? 0 : 1;
     g_overlap_prev = chain;
-    SF_TRY(mm(c, c.bf(p.dh_tot), x.H, MAJOR_MN, c.bf(p.act), x.I, MAJOR_MN, Gn + off[SF_P_DOWN], x.I, nullptr, 0, x.H, x.I, TM, EPI_F32_ACCUM));
+    SF_TRY(mm(c, c.bf(p.dh_tot), x.H, MAJOR_MN, c.bf(p.act), x.I, MAJOR_MN, Gn + off[SF_P_DOWN], x.I, nullptr, 0, x.H, x.I, TM, wepi));
     ready(SF_P_DOWN, 1);
     g_overlap_prev = chain;
-    SF_TRY(mm(c, c.bf(p.dgu), 2 * x.I, MAJOR_MN, c.bf(p.hn2), x.H, MAJOR_MN, Gn + off[SF_P_GATE], x.H, nullptr, 0, 2 * x.I, x.H, TM, EPI_F32_ACCUM));
+    SF_TRY(mm(c, c.bf(p.dgu), 2 * x.I, MAJOR_MN, c.bf(p.hn2), x.H, MAJOR_MN, Gn + off[SF_P_GATE], x.H, nullptr, 0, 2 * x.I, x.H, TM, wepi));
     ready(SF_P_GATE, 2);
     g_overlap_prev = chain;
-    SF_TRY(mm(c, c.bf(p.dhmid), x.H, MAJOR_MN, c.bf(p.attn), x.A, MAJOR_MN, Gn + off[SF_P_O], x.A, nullptr, 0, x.H, x.A, TM, EPI_F32_ACCUM));
+    SF_TRY(mm(c, c.bf(p.dhmid), x.H, MAJOR_MN, c.bf(p.attn), x.A, MAJOR_MN, Gn + off[SF_P_O], x.A, nullptr, 0, x.H, x.A, TM, wepi));
     ready(SF_P_O, 1);
     g_overlap_prev = chain;
-    SF_TRY(mm(c, c.bf(p.dqkv), x.QKV, MAJOR_MN, c.bf(p.xcat), 2 * x.H, MAJOR_MN, Gn + off[SF_P_Q], 2 * x.H, nullptr, 0, x.QKV, 2 * x.H, TM, EPI_F32_ACCUM));
+    SF_TRY(mm(c, c.bf(p.dqkv), x.QKV, MAJOR_MN, c.bf(p.xcat), 2 * x.H, MAJOR_MN, Gn + off[SF_P_Q], 2 * x.H, nullptr, 0, x.QKV, 2 * x.H, TM, wepi));
     ready(SF_P_Q, 3);
     // fc: dW_fc = d(h_0)^T fc_in ; with fc_norm also the three norm-weight gradients through d(fc_in) = d(h_0) W_fc
     const void* fc_in = bt.hidden_state;
@@ -431,7 +439,7 @@ static int backward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& b
         ready(SF_P_FC_NORM0, 3);
     }
     if (!cfg.fc_norm) g_overlap_prev = chain;
-    SF_TRY(mm(c, c.bf(p.dh_carry), x.H, MAJOR_MN, fc_in, 3 * x.Ht, MAJOR_MN, Gn + off[SF_P_FC], 3 * x.Ht, nullptr, 0, x.H, 3 * x.Ht, M, EPI_F32_ACCUM));
+    SF_TRY(mm(c, c.bf(p.dh_carry), x.H, MAJOR_MN, fc_in, 3 * x.Ht, MAJOR_MN, Gn + off[SF_P_FC], 3 * x.Ht, nullptr, 0, x.H, 3 * x.Ht, M, wepi));
     ready(SF_P_FC, 1);
     return 0;
 }

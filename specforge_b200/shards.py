@@ -259,11 +259,13 @@ class Eagle3ShardLoader:
 
     def __init__(self, shards: Sequence[str], batch_size: int, max_len: int, *, run_id: str = "offline", shuffle: bool = False,
                  seed: int = 0, drop_last: bool = True, pad_to: Optional[int] = None, rank: int = 0, world: int = 1,
-                 threads: int = 8, pin: bool = True, buffers: int = 4):
+                 threads: int = 8, pin: bool = True, buffers: int = 6, prefetch: int = 2):
         self.readers = [ShardReader(p) for p in ([shards] if isinstance(shards, str) else shards)]
         self.batch_size, self.max_len, self.run_id = batch_size, max_len, run_id
         self.shuffle, self.seed, self.drop_last, self.pad_to = shuffle, seed, drop_last, pad_to
         self.rank, self.world, self.threads, self.pin = rank, world, threads, pin
+        self.prefetch = max(0, prefetch)
+        buffers = max(buffers, self.prefetch + 4)     # queue + one in production + DevicePrefetcher depth 2 + the batch in use
         # Ring of reusable (pinned) destination buffer sets: no page faults / cudaHostAlloc per batch.  A yielded batch's host
         # tensors stay valid until `buffers - 1` further batches have been produced (DevicePrefetcher depth 2 needs >= 3).
         self._ring: List[Dict[str, torch.Tensor]] = [dict() for _ in range(max(1, buffers))]
@@ -324,10 +326,50 @@ class Eagle3ShardLoader:
         ids = [f"{self.run_id}:{gi:08d}" for gi in sample_indices]
         return TrainBatch(sample_ids=ids, strategy="eagle3", tensors=tensors, metadata={"target_repr": "hidden_state"})
 
-    def __iter__(self) -> Iterator[TrainBatch]:
+    def _batches(self) -> Iterator[TrainBatch]:
         order = self._order()
         for i in range(0, len(order), self.batch_size):
             chunk = order[i:i + self.batch_size]
             if len(chunk) < self.batch_size and self.drop_last:
                 return
             yield self.batch(chunk)
+
+    def __iter__(self) -> Iterator[TrainBatch]:
+        """With prefetch > 0 a background thread gathers the next batches (the C call releases the GIL) while the caller
+        launches / waits on the current step, so disk + memcpy time hides behind the GPU."""
+        if self.prefetch == 0:
+            yield from self._batches()
+            return
+        import queue
+        import threading
+        q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
+        stop = threading.Event()
+
+        def produce():
+            try:
+                for b in self._batches():
+                    while not stop.is_set():
+                        try:
+                            q.put(b, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                    if stop.is_set():
+                        return
+                q.put(None)
+            except BaseException as exc:           # surface reader errors in the consumer
+                q.put(exc)
+
+        t = threading.Thread(target=produce, name="sfpk-prefetch", daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+            t.join(timeout=5)
