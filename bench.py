@@ -348,6 +348,8 @@ def run_ours(args):
                     if done == n:
                         return
 
+        for _ in shard_batches(8):          # allocate (pin) every buffer set of the loader's ring before timing
+            pass
         for batch in DevicePrefetcher(shard_batches(3), device=dev):
             step(batch, True)
         barrier()
