@@ -1,0 +1,68 @@
+"""DFlash — oracle pinned against outputs of the unmodified reference (tests/golden/dflash_*.pt, made by
+oracle/make_dflash_golden.py).  CPU only.  The CUDA path of this row is next round's work; these goldens are its checker."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import dflash_oracle as D
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "dflash_*.pt")))
+
+
+def test_goldens_present():
+    assert len(GOLDEN) >= 6
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-3])
+def test_oracle_matches_reference(path):
+    g = torch.load(path, weights_only=False)
+    c = D.DFlashConfig(**g["config"])
+    f32 = g["dtype"] == "torch.float32"
+    loss, acc, terms, grads = D.train_step(g["params"], c, g["batch"], g["anchors"], g["keep"], g["embed_w"], g["lm_head_w"])
+    rt = 1e-5 if f32 else 2e-2
+    torch.testing.assert_close(loss.float(), g["loss"].float(), rtol=rt, atol=1e-6)
+    torch.testing.assert_close(terms["loss_num"].float(), g["loss_num"].float(), rtol=rt, atol=1e-5)
+    torch.testing.assert_close(terms["loss_den"].float(), g["loss_den"].float(), rtol=1e-6, atol=0)
+    assert float(terms["acc_den"]) == float(g["acc_den"])
+    if f32:
+        assert float(terms["correct"]) == float(g["correct"])
+        torch.testing.assert_close(acc, g["accuracy"])
+    else:
+        assert abs(float(terms["correct"]) - float(g["correct"])) <= 1      # a bf16 near-tie may flip one argmax
+    assert set(grads) == set(g["grads"])
+    for n, ref in g["grads"].items():
+        got = grads[n]
+        assert got is not None, n
+        if f32:
+            torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-6, msg=lambda m: f"{n}: {m}")
+        else:
+            cos = torch.nn.functional.cosine_similarity(got.float().flatten(), ref.float().flatten(), dim=0).item()
+            assert cos >= 0.99, (n, cos)
+
+
+def test_anchor_sampling_properties():
+    torch.manual_seed(0)
+    lm = (torch.rand(4, 64) > 0.4).float()
+    lm[3] = 0
+    lm[3, 10:13] = 1
+    a, keep = D.sample_anchor_positions(lm, 16)
+    assert a.shape == keep.shape and a.shape[1] <= 16
+    for b in range(4):
+        kept = a[b][keep[b]]
+        assert torch.equal(kept, kept.sort().values) and kept.unique().numel() == kept.numel()      # sorted, no repeats
+        assert all(lm[b, i] > 0.5 and lm[b, i + 1] > 0.5 for i in kept.tolist())                   # both tokens supervised
+    assert int(keep[3].sum()) == 2 and not bool((a[3][~keep[3]] != 0).any())                        # 2 candidates, rest dropped
+    with pytest.raises(ValueError):
+        D.sample_anchor_positions(torch.zeros(2, 8), 4)
+
+
+def test_mask_semantics():
+    anchors = torch.tensor([[2, 5]])
+    keep = torch.tensor([[True, False]])
+    m = D.dflash_mask(anchors, keep, S=8, bs=2)
+    assert m.shape == (1, 4, 12)
+    assert m[0, 0].tolist() == [True, True] + [False] * 6 + [True, True, False, False]      # context < anchor, own block
+    assert m[0, 1].tolist() == m[0, 0].tolist()                                              # bidirectional inside a block
+    assert not m[0, 2:].any()                                                                # dropped block sees nothing
