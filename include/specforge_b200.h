@@ -179,6 +179,51 @@ int sf_shard_verify_record(void* handle, int64_t record);
 int sf_shard_read_batch(void* handle, const int64_t* records, int n_rec, int64_t max_tokens, int64_t pad_tokens,
                         void* const* dst, int n_threads);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * DFlash block-parallel draft training step (first correct CUDA version).
+ * Replaces OnlineDFlashModel.forward + autograd (algorithms/common/dflash_family_model.py:385-461) around
+ * DFlashDraftModel.forward (modeling/draft/dflash.py:431-460).  Anchors are sampled by the caller (the reference draws them
+ * with torch's RNG, dflash_family_model.py:179-210).  Same conventions as the EAGLE3 entry points: device pointers, one flat
+ * bf16 parameter buffer, one flat fp32 gradient buffer, caller-owned workspace, sf_optimizer_step for the update.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct sf_dflash_config {
+    int32_t batch, seq_len;           /* context: B x S target tokens                                                     */
+    int32_t num_blocks, block_size;   /* N anchor blocks per sequence x bs draft slots  (config.block_size, num_anchors)  */
+    int32_t hidden_size;              /* H (the target's hidden size: the context feature is num_target_feats * H wide)   */
+    int32_t num_target_feats;         /* len(dflash_config.target_layer_ids)                                              */
+    int32_t intermediate, num_heads, num_kv_heads, head_dim, num_layers, vocab;
+    int32_t mask_token_id, rope_rows;
+    float rms_eps;
+    float loss_decay_gamma;           /* <= 0: no decay  (dflash_family_model.py:349-358)                                 */
+} sf_dflash_config;
+/* parameter order inside the flat buffer: for each layer the SF_DF_* slices below (q, k, v contiguous = one fused GEMM
+ * operand, likewise gate, up), then fc [H, F*H], hidden_norm [H], norm [H].  Names/shapes: dflash.py:336-375. */
+enum { SF_DF_Q = 0, SF_DF_K, SF_DF_V, SF_DF_O, SF_DF_GATE, SF_DF_UP, SF_DF_DOWN, SF_DF_Q_NORM, SF_DF_K_NORM, SF_DF_INPUT_LN,
+       SF_DF_POST_LN, SF_DF_PER_LAYER };
+typedef struct sf_dflash_frozen {
+    const void* embed_tokens;         /* [V, H] bf16  target embedding (noise tokens)        */
+    const void* lm_head;              /* [V, H] bf16  target lm_head                         */
+    const void* rope_cos;             /* [rope_rows, head_dim] bf16 (cos of cat(freqs, freqs)) */
+    const void* rope_sin;
+} sf_dflash_frozen;
+typedef struct sf_dflash_batch {
+    const int64_t* input_ids;         /* [B, S]                                              */
+    const void* hidden_states;        /* [B, S, F*H] bf16 concatenated target layers         */
+    const int64_t* loss_mask;         /* [B, S] 0/1                                          */
+    const int32_t* anchors;           /* [B, N] sorted anchor positions (0 for dropped)      */
+    const uint8_t* keep;              /* [B, N] block_keep_mask                              */
+} sf_dflash_batch;
+int sf_dflash_num_params(const sf_dflash_config* cfg);      /* 11 * num_layers + 3 */
+int sf_dflash_param_layout(const sf_dflash_config* cfg, int64_t* offsets, int64_t* sizes, int64_t* total);
+size_t sf_dflash_workspace_bytes(const sf_dflash_config* cfg);
+/* metrics[4] = {loss_num, loss_den, correct, accuracy_den} (device, dflash_family_model.py:441-459); loss = num / den */
+int sf_dflash_forward(const sf_dflash_config* cfg, const void* params_flat, const sf_dflash_frozen* frozen,
+                      const sf_dflash_batch* batch, void* workspace, size_t workspace_bytes, float* metrics, float* loss,
+                      int need_grad, void* stream);
+int sf_dflash_backward(const sf_dflash_config* cfg, const void* params_flat, const sf_dflash_frozen* frozen,
+                       const sf_dflash_batch* batch, void* workspace, size_t workspace_bytes, float* grads_flat_f32,
+                       int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

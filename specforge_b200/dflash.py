@@ -1,0 +1,212 @@
+"""Host side of the DFlash block-parallel draft step (first correct CUDA version behind
+`sf_dflash_*`).  Mirrors what `OnlineDFlashModel` owns on the host in the reference: anchor sampling
+(`algorithms/common/dflash_family_model.py:179-210`, torch RNG), the `DFlashDraftModel` state-dict names and shapes
+(`modeling/draft/dflash.py:336-375`), rotary tables (transformers `Qwen3RotaryEmbedding`, default rope).  Everything after the
+anchors are drawn runs in the CUDA library; there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+from ctypes import POINTER, Structure, c_float, c_int32, c_int64, c_size_t, c_void_p
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from ._lib import check, lib
+
+PER_LAYER = ("self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.o_proj.weight",
+             "mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight", "self_attn.q_norm.weight",
+             "self_attn.k_norm.weight", "input_layernorm.weight", "post_attention_layernorm.weight")
+GLOBALS = ("fc.weight", "hidden_norm.weight", "norm.weight")
+
+
+class SfDflashConfig(Structure):
+    _fields_ = [(n, c_int32) for n in ("batch", "seq_len", "num_blocks", "block_size", "hidden_size", "num_target_feats",
+                                       "intermediate", "num_heads", "num_kv_heads", "head_dim", "num_layers", "vocab",
+                                       "mask_token_id", "rope_rows")] + [("rms_eps", c_float), ("loss_decay_gamma", c_float)]
+
+
+class SfDflashFrozen(Structure):
+    _fields_ = [("embed_tokens", c_void_p), ("lm_head", c_void_p), ("rope_cos", c_void_p), ("rope_sin", c_void_p)]
+
+
+class SfDflashBatch(Structure):
+    _fields_ = [("input_ids", c_void_p), ("hidden_states", c_void_p), ("loss_mask", c_void_p), ("anchors", c_void_p),
+                ("keep", c_void_p)]
+
+
+@dataclasses.dataclass
+class DFlashDims:
+    hidden_size: int
+    intermediate_size: int
+    num_heads: int
+    num_kv_heads: int
+    head_dim: int
+    num_layers: int
+    num_target_feats: int
+    vocab_size: int
+    block_size: int = 16
+    mask_token_id: int = 0
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1000000.0
+    max_position_embeddings: int = 40960
+    loss_decay_gamma: Optional[float] = None
+
+
+def sample_anchor_positions(loss_mask: torch.Tensor, num_anchors: int, generator: Optional[torch.Generator] = None):
+    """Anchors whose clean token and first target are supervised (dflash_family_model.py:179-210); returns
+    (anchors [B, W] sorted, 0 where dropped; keep [B, W] bool).  Same tensor ops and RNG call as the reference, so with the
+    same generator state it draws the same anchors."""
+    B, S = loss_mask.shape
+    dev = loss_mask.device
+    n_cand = max(S - 1, 0)
+    valid = (loss_mask[:, :n_cand] > 0.5) & (loss_mask[:, 1:n_cand + 1] > 0.5)
+    counts = valid.sum(dim=1)
+    width = min(num_anchors, int(counts.max().item()))
+    if width == 0:
+        raise ValueError("DFlash-family training requires two consecutive supervised tokens")
+    r = torch.rand(valid.shape, device=dev, generator=generator)
+    r.masked_fill_(~valid, 2.0)
+    cand = r.argsort(dim=1)[:, :width]
+    keep = torch.arange(width, device=dev).unsqueeze(0) < counts.clamp(max=width).unsqueeze(1)
+    sentinel = valid.shape[1]
+    anchors = torch.where(keep, cand, torch.full_like(cand, sentinel)).sort(dim=1).values
+    keep = anchors < sentinel
+    return torch.where(keep, anchors, 0), keep
+
+
+def rope_tables(dims: DFlashDims, rows: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cos/sin of cat(freqs, freqs) in fp32, cast to bf16 (what Qwen3RotaryEmbedding hands a bf16 model)."""
+    d = dims.head_dim
+    inv = 1.0 / (dims.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    f = torch.arange(rows, dtype=torch.float32).unsqueeze(1) * inv.unsqueeze(0)
+    emb = torch.cat((f, f), dim=-1)
+    return emb.cos().to(device, torch.bfloat16).contiguous(), emb.sin().to(device, torch.bfloat16).contiguous()
+
+
+def _declare(l) -> None:
+    if getattr(l, "_sf_dflash_declared", False):
+        return
+    l.sf_dflash_num_params.argtypes = [POINTER(SfDflashConfig)]
+    l.sf_dflash_param_layout.argtypes = [POINTER(SfDflashConfig), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
+    l.sf_dflash_workspace_bytes.restype = c_size_t
+    l.sf_dflash_workspace_bytes.argtypes = [POINTER(SfDflashConfig)]
+    l.sf_dflash_forward.argtypes = [POINTER(SfDflashConfig), c_void_p, POINTER(SfDflashFrozen), POINTER(SfDflashBatch), c_void_p, c_size_t,
+                                    c_void_p, c_void_p, ctypes.c_int, c_void_p]
+    l.sf_dflash_backward.argtypes = [POINTER(SfDflashConfig), c_void_p, POINTER(SfDflashFrozen), POINTER(SfDflashBatch), c_void_p, c_size_t,
+                                     c_void_p, ctypes.c_int, c_void_p]
+    l._sf_dflash_declared = True
+
+
+class DFlashEngine:
+    """Flat bf16 parameters + fp32 gradient accumulators + workspace for `sf_dflash_forward/backward`, bound to a maximum
+    (batch, seq_len, num_blocks); the number of blocks of a call may be smaller (the reference's anchor width varies)."""
+
+    def __init__(self, dims: DFlashDims, batch: int, seq_len: int, num_blocks: int, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DFlashEngine needs a CUDA device (no CPU / PyTorch fallback)")
+        self.dims, self.B, self.S, self.N = dims, batch, seq_len, num_blocks
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        L = lib()
+        _declare(L)
+        rope_rows = max(dims.max_position_embeddings, seq_len + dims.block_size) + dims.block_size
+        self.cfg = self._cfg(batch, seq_len, num_blocks, rope_rows)
+        n = L.sf_dflash_num_params(self.cfg)
+        if n < 0:
+            check(n, "sf_dflash_num_params")
+        offs, sizes, total = (c_int64 * n)(), (c_int64 * n)(), c_int64()
+        check(L.sf_dflash_param_layout(self.cfg, offs, sizes, ctypes.byref(total)), "sf_dflash_param_layout")
+        self.names: List[str] = [f"layers.{l}.{p}" for l in range(dims.num_layers) for p in PER_LAYER] + list(GLOBALS)
+        self.offsets = {nm: int(offs[i]) for i, nm in enumerate(self.names)}
+        self.sizes = {nm: int(sizes[i]) for i, nm in enumerate(self.names)}
+        self.n_params = int(total.value)
+        self.params = torch.zeros(self.n_params, dtype=torch.bfloat16, device=self.device)
+        self.grads_f32 = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
+        self.rope_cos, self.rope_sin = rope_tables(dims, rope_rows, self.device)
+        ws = L.sf_dflash_workspace_bytes(self.cfg)
+        if ws == 0:
+            check(-22, "sf_dflash_workspace_bytes")
+        self.workspace_bytes = int(ws)
+        self.workspace = torch.empty(self.workspace_bytes + 1024, dtype=torch.uint8, device=self.device)
+        self._ws_ptr = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+        self.metrics = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._frozen = None
+        self._batch = None
+
+    def _cfg(self, B, S, N, rope_rows) -> SfDflashConfig:
+        d = self.dims
+        return SfDflashConfig(B, S, N, d.block_size, d.hidden_size, d.num_target_feats, d.intermediate_size, d.num_heads,
+                              d.num_kv_heads, d.head_dim, d.num_layers, d.vocab_size, d.mask_token_id, rope_rows, d.rms_norm_eps,
+                              float(d.loss_decay_gamma) if d.loss_decay_gamma else 0.0)
+
+    def shape_of(self, name: str) -> Tuple[int, ...]:
+        d = self.dims
+        A, KV = d.num_heads * d.head_dim, d.num_kv_heads * d.head_dim
+        tail = name.split(".", 2)[2] if name.startswith("layers.") else name
+        return {"self_attn.q_proj.weight": (A, d.hidden_size), "self_attn.k_proj.weight": (KV, d.hidden_size),
+                "self_attn.v_proj.weight": (KV, d.hidden_size), "self_attn.o_proj.weight": (d.hidden_size, A),
+                "mlp.gate_proj.weight": (d.intermediate_size, d.hidden_size), "mlp.up_proj.weight": (d.intermediate_size, d.hidden_size),
+                "mlp.down_proj.weight": (d.hidden_size, d.intermediate_size), "self_attn.q_norm.weight": (d.head_dim,),
+                "self_attn.k_norm.weight": (d.head_dim,), "input_layernorm.weight": (d.hidden_size,),
+                "post_attention_layernorm.weight": (d.hidden_size,), "fc.weight": (d.hidden_size, d.num_target_feats * d.hidden_size),
+                "hidden_norm.weight": (d.hidden_size,), "norm.weight": (d.hidden_size,)}[tail]
+
+    def param_view(self, name: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        buf = self.params if buf is None else buf
+        o, n = self.offsets[name], self.sizes[name]
+        return buf[o:o + n].view(self.shape_of(name))
+
+    def load_params(self, state: Dict[str, torch.Tensor]) -> None:
+        for name in self.names:
+            self.param_view(name).copy_(state[name].to(self.device, torch.bfloat16))
+
+    def set_frozen(self, *, embed_tokens: torch.Tensor, lm_head: torch.Tensor) -> None:
+        d = self.dims
+        e = embed_tokens.to(self.device, torch.bfloat16).contiguous()
+        h = lm_head.to(self.device, torch.bfloat16).contiguous()
+        assert e.shape == (d.vocab_size, d.hidden_size) and h.shape == (d.vocab_size, d.hidden_size), (e.shape, h.shape)
+        self._frozen_keep = (e, h)
+        self._frozen = SfDflashFrozen(e.data_ptr(), h.data_ptr(), self.rope_cos.data_ptr(), self.rope_sin.data_ptr())
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _bind(self, batch: Dict[str, torch.Tensor], anchors: torch.Tensor, keep: torch.Tensor) -> None:
+        dev, d = self.device, self.dims
+        t = {"input_ids": batch["input_ids"].to(dev, torch.int64).contiguous(),
+             "hidden_states": batch["hidden_states"].to(dev, torch.bfloat16).contiguous(),
+             "loss_mask": (batch["loss_mask"].to(dev) > 0.5).to(torch.int64).contiguous(),
+             "anchors": anchors.to(dev, torch.int32).contiguous(), "keep": keep.to(dev).to(torch.uint8).contiguous()}
+        B, S = (int(v) for v in t["input_ids"].shape)
+        N = int(t["anchors"].shape[1])
+        if t["hidden_states"].shape != (B, S, d.num_target_feats * d.hidden_size):
+            raise ValueError(f"hidden_states must be [{B}, {S}, {d.num_target_feats * d.hidden_size}], got {tuple(t['hidden_states'].shape)}")
+        if t["loss_mask"].shape != (B, S) or t["anchors"].shape != (B, N) or t["keep"].shape != (B, N):
+            raise ValueError("loss_mask / anchors / keep shapes do not match the batch")
+        cfg = self._cfg(B, S, N, self.cfg.rope_rows)
+        need = lib().sf_dflash_workspace_bytes(cfg)
+        if need == 0:
+            check(-22, "sf_dflash_workspace_bytes")
+        if need > self.workspace_bytes:
+            raise ValueError(f"batch [{B}, {S}] x {N} blocks exceeds the shape the engine was bound with")
+        self._call_cfg = cfg
+        self._keep = t
+        self._batch = SfDflashBatch(t["input_ids"].data_ptr(), t["hidden_states"].data_ptr(), t["loss_mask"].data_ptr(),
+                                    t["anchors"].data_ptr(), t["keep"].data_ptr())
+
+    def forward(self, batch: Dict[str, torch.Tensor], anchors: torch.Tensor, keep: torch.Tensor, need_grad: bool = True):
+        """Returns (loss[1], metrics[4] = loss_num, loss_den, correct, accuracy_den) as device tensors (no host sync)."""
+        if self._frozen is None:
+            raise RuntimeError("set_frozen() must be called before forward()")
+        self._bind(batch, anchors, keep)
+        check(lib().sf_dflash_forward(self._call_cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr, self.workspace_bytes,
+                                      self.metrics.data_ptr(), self.loss.data_ptr(), int(need_grad), self._stream()), "sf_dflash_forward")
+        return self.loss, self.metrics
+
+    def backward(self, accumulate: bool = False) -> None:
+        if self._batch is None:
+            raise RuntimeError("backward() without a preceding forward(need_grad=True)")
+        check(lib().sf_dflash_backward(self._call_cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr, self.workspace_bytes,
+                                       self.grads_f32.data_ptr(), int(accumulate), self._stream()), "sf_dflash_backward")

@@ -66,3 +66,14 @@ def test_mask_semantics():
     assert m[0, 0].tolist() == [True, True] + [False] * 6 + [True, True, False, False]      # context < anchor, own block
     assert m[0, 1].tolist() == m[0, 0].tolist()                                              # bidirectional inside a block
     assert not m[0, 2:].any()                                                                # dropped block sees nothing
+
+
+def test_product_anchor_sampler_equals_oracle_under_same_rng():
+    """specforge_b200.dflash.sample_anchor_positions is the host code that ships; same draws as the pinned oracle."""
+    from specforge_b200.dflash import sample_anchor_positions
+    lm = (torch.rand(5, 70, generator=torch.Generator().manual_seed(3)) > 0.35).float()
+    torch.manual_seed(11)
+    a1, k1 = sample_anchor_positions(lm, 9)
+    torch.manual_seed(11)
+    a2, k2 = D.sample_anchor_positions(lm, 9)
+    assert torch.equal(a1, a2) and torch.equal(k1, k2)
