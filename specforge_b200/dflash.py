@@ -210,3 +210,100 @@ class DFlashEngine:
             raise RuntimeError("backward() without a preceding forward(need_grad=True)")
         check(lib().sf_dflash_backward(self._call_cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr, self.workspace_bytes,
                                        self.grads_f32.data_ptr(), int(accumulate), self._stream()), "sf_dflash_backward")
+
+
+# ------------------------------------------------------------------------------------------------ draft-registry seam
+def dims_from_config(config) -> DFlashDims:
+    """DFlashDims from a Qwen3Config-like object or the dict of a draft JSON (configs/qwen3-8b-dflash.json)."""
+    get = (lambda k, d=None: config.get(k, d)) if isinstance(config, dict) else (lambda k, d=None: getattr(config, k, d))
+    H, nh, L = get("hidden_size"), get("num_attention_heads"), get("num_hidden_layers")
+    dcfg = get("dflash_config") or {}
+    layer_ids = dcfg.get("target_layer_ids")
+    if layer_ids is None:          # build_target_layer_ids (modeling/draft/dflash.py:271-281)
+        nt = get("num_target_layers")
+        layer_ids = [nt // 2] if L == 1 else [int(round(1 + i * (nt - 4) / (L - 1))) for i in range(L)]
+    types = get("layer_types")
+    if types and any(t != "full_attention" for t in types):
+        raise NotImplementedError("sliding_attention DFlash layers are not implemented on the CUDA path")
+    rope_params = get("rope_parameters")
+    theta = rope_params["rope_theta"] if rope_params else get("rope_theta", 1000000.0)
+    for rp in (get("rope_scaling"), rope_params):       # transformers 5 mirrors rope_parameters into rope_scaling
+        if rp and rp.get("rope_type", rp.get("type", "default")) not in (None, "default"):
+            raise NotImplementedError("rope scaling is not implemented for the DFlash CUDA path")
+    return DFlashDims(hidden_size=H, intermediate_size=get("intermediate_size"), num_heads=nh, num_kv_heads=get("num_key_value_heads", nh),
+                      head_dim=get("head_dim") or H // nh, num_layers=L, num_target_feats=len(layer_ids), vocab_size=get("vocab_size"),
+                      block_size=get("block_size", 16), mask_token_id=int(dcfg.get("mask_token_id") or 0),
+                      rms_norm_eps=get("rms_norm_eps", 1e-6), rope_theta=float(theta),
+                      max_position_embeddings=get("max_position_embeddings", 40960))
+
+
+try:  # the reference's registry needs `config_class` (registry.py:38-41); its DFlash draft uses Qwen3Config
+    from transformers.models.qwen3.modeling_qwen3 import Qwen3Config as _Qwen3Config
+except Exception:  # pragma: no cover
+    _Qwen3Config = None
+
+
+class B200DFlashDraftModel(torch.nn.Module):
+    """State-dict twin of `DFlashDraftModel` (modeling/draft/dflash.py:336-375) for the `@register_draft` seam: same
+    parameter names and shapes, `target_layer_ids`, `block_size`, `mask_token_id`; the parameters are views into the
+    DFlashEngine's flat bf16 buffer once `bind_engine()` ran.  No eager forward: compute goes through `sf_dflash_*`."""
+    architectures = ["DFlashDraftModel"]
+    config_class = _Qwen3Config
+
+    def __init__(self, config, dflash_kernels=None):
+        super().__init__()
+        self.config = config
+        self.dims = dims_from_config(config)
+        get = (lambda k, d=None: config.get(k, d)) if isinstance(config, dict) else (lambda k, d=None: getattr(config, k, d))
+        dcfg = get("dflash_config") or {}
+        self.block_size = self.dims.block_size
+        self.mask_token_id = dcfg.get("mask_token_id", None)
+        self.target_layer_ids = dcfg.get("target_layer_ids")
+        self.sliding_window = None
+        self.engine: Optional[DFlashEngine] = None
+        self._names = [f"layers.{l}.{p}" for l in range(self.dims.num_layers) for p in PER_LAYER] + list(GLOBALS)
+        self._flat: Dict[str, torch.nn.Parameter] = {}
+
+    def state_dict_spec(self) -> Dict[str, tuple]:
+        d = self.dims
+        A, KV, H, I = d.num_heads * d.head_dim, d.num_kv_heads * d.head_dim, d.hidden_size, d.intermediate_size
+        per = {"self_attn.q_proj.weight": (A, H), "self_attn.k_proj.weight": (KV, H), "self_attn.v_proj.weight": (KV, H),
+               "self_attn.o_proj.weight": (H, A), "mlp.gate_proj.weight": (I, H), "mlp.up_proj.weight": (I, H),
+               "mlp.down_proj.weight": (H, I), "self_attn.q_norm.weight": (d.head_dim,), "self_attn.k_norm.weight": (d.head_dim,),
+               "input_layernorm.weight": (H,), "post_attention_layernorm.weight": (H,)}
+        spec = {f"layers.{l}.{k}": v for l in range(d.num_layers) for k, v in per.items()}
+        spec.update({"fc.weight": (H, d.num_target_feats * H), "hidden_norm.weight": (H,), "norm.weight": (H,)})
+        return spec
+
+    def bind_engine(self, batch: int, seq_len: int, num_anchors: int = 512, device=None, init_std: float = 0.02, seed: int = 0) -> DFlashEngine:
+        eng = DFlashEngine(self.dims, batch=batch, seq_len=seq_len, num_blocks=num_anchors, device=device)
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for name in self._names:
+            view = eng.param_view(name)
+            if view.dim() == 1:
+                view.fill_(1.0)
+            else:
+                view.copy_((torch.randn(view.shape, generator=g) * init_std).to(torch.bfloat16))
+            p = torch.nn.Parameter(view, requires_grad=True)
+            self._flat[name] = p
+            self.register_parameter(name.replace(".", "__"), p)
+        self.engine = eng
+        return eng
+
+    def state_dict(self, *args, destination=None, prefix: str = "", keep_vars: bool = False):
+        out = destination if destination is not None else {}
+        for name in self._names:
+            if name in self._flat:
+                p = self._flat[name]
+                out[prefix + name] = p if keep_vars else p.detach()
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        if self.engine is None:
+            raise RuntimeError("bind_engine() must be called before load_state_dict()")
+        missing = [n for n in self._names if n not in state_dict]
+        unexpected = [k for k in state_dict if k not in self._names and "rotary_emb" not in k]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"state_dict mismatch: missing={missing} unexpected={unexpected}")
+        self.engine.load_params({n: state_dict[n] for n in self._names if n in state_dict} | {n: self._flat[n] for n in missing})
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)

@@ -51,3 +51,33 @@ def test_gemm_rejects_bad_arguments_without_a_gpu(L):
     assert rc != 0 and b"empty" in L.sf_last_error()
     with pytest.raises(_lib.SfError):
         _lib.check(rc, "sf_gemm_bf16")
+
+
+def test_dflash_param_layout_and_workspace(L):
+    """sf_dflash_param_layout on the BASELINE config-4 draft (configs/qwen3-8b-dflash.json): names/sizes of DFlashDraftModel,
+    q|k|v and gate|up adjacent (fused GEMM operands), workspace within the 180 GB part."""
+    import ctypes
+    from ctypes import c_int64
+    from specforge_b200.dflash import GLOBALS, PER_LAYER, SfDflashConfig, _declare
+    from oracle import dflash_oracle as D
+    _declare(L)
+    cfg = SfDflashConfig(4, 2048, 512, 16, 4096, 5, 12288, 32, 8, 128, 5, 151936, 151669, 41000, 1e-6, 0.0)
+    n = L.sf_dflash_num_params(cfg)
+    assert n == 11 * 5 + 3
+    offs, sizes, total = (c_int64 * n)(), (c_int64 * n)(), c_int64()
+    assert L.sf_dflash_param_layout(cfg, offs, sizes, ctypes.byref(total)) == 0
+    names = [f"layers.{l}.{p}" for l in range(5) for p in PER_LAYER] + list(GLOBALS)
+    shapes = D.param_shapes(D.DFlashConfig(hidden_size=4096, intermediate_size=12288, num_heads=32, num_kv_heads=8, head_dim=128,
+                                           num_layers=5, num_target_feats=5, vocab_size=151936, block_size=16))
+    assert set(names) == set(shapes)
+    for i, nm in enumerate(names):
+        numel = 1
+        for s in shapes[nm]:
+            numel *= s
+        assert sizes[i] == numel, nm
+        assert offs[i] == (0 if i == 0 else offs[i - 1] + sizes[i - 1])
+    assert total.value == sum(sizes) == 5 * (4096 * 4096 * 2 + 2 * 1024 * 4096 + 3 * 12288 * 4096 + 2 * 128 + 2 * 4096) + 4096 * 5 * 4096 + 2 * 4096
+    ws = L.sf_dflash_workspace_bytes(cfg)
+    assert 20e9 < ws < 80e9, ws
+    bad = SfDflashConfig(4, 2048, 512, 16, 4096, 5, 12288, 32, 8, 100, 5, 151936, 151669, 41000, 1e-6, 0.0)
+    assert L.sf_dflash_workspace_bytes(bad) == 0 and b"multiples of 8" in L.sf_last_error()

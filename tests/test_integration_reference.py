@@ -71,3 +71,22 @@ def test_shard_batches_equal_the_reference_input_pipe(ref, tmp_path):
             assert g.dtype == w.dtype and g.shape == w.shape and o.shape == w.shape, k
             same = lambda a, b: torch.equal(a.view(torch.int16), b.view(torch.int16)) if a.dtype == torch.bfloat16 else torch.equal(a, b)
             assert same(g, w) and same(o, w), k
+
+
+def test_dflash_registry_binding_and_state_dict_contract(ref, monkeypatch):
+    """Seam 1 for the DFlash draft: our class resolves from the reference's own draft JSON through its registry and promises
+    exactly the reference DFlashDraftModel's parameter names and shapes."""
+    le, AutoDraftModel, AutoDraftModelConfig, DRAFT_REGISTRY = ref
+    from specforge.modeling.draft.dflash import DFlashDraftModel
+    from specforge_b200.dflash import B200DFlashDraftModel
+    path = os.path.join(REF, "configs", "qwen3-8b-dflash.json")
+    config = AutoDraftModelConfig.from_file(path)
+    config.vocab_size, config.hidden_size, config.intermediate_size = 1024, 256, 512      # shrink: shapes scale with these only
+    config.num_attention_heads, config.num_key_value_heads, config.head_dim = 8, 2, 32
+    ref_sd = {k: tuple(v.shape) for k, v in DFlashDraftModel(config).state_dict().items()}
+    monkeypatch.setitem(DRAFT_REGISTRY, "DFlashDraftModel", B200DFlashDraftModel)
+    ours = AutoDraftModel.from_config(config)
+    assert isinstance(ours, B200DFlashDraftModel)
+    assert ours.state_dict_spec() == ref_sd
+    assert ours.block_size == 16 and ours.mask_token_id == 151669 and list(ours.target_layer_ids) == [1, 9, 17, 25, 33]
+    assert ours.dims.num_target_feats == 5 and ours.dims.num_layers == 5
