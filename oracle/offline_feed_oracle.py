@@ -12,16 +12,19 @@ import torch
 
 
 def normalize_offline_sample(raw: Dict[str, torch.Tensor], max_len: int) -> Dict[str, torch.Tensor]:
-    """algorithms/eagle3/data.py:10-27 (same as data/preprocessing.py:642-665): truncate to max_len, swap names
-    (hidden_state <- aux_hidden_state, target <- hidden_state), zero the last kept loss-mask position, all-ones mask."""
-    hidden_state = raw["aux_hidden_state"].squeeze(0)[:max_len].unsqueeze(0)
-    target = raw["hidden_state"].squeeze(0)[:max_len].unsqueeze(0)
-    input_ids = raw["input_ids"][:max_len].unsqueeze(0)
-    loss_mask = raw["loss_mask"][:max_len].clone().unsqueeze(0)
-    if loss_mask.numel() > 0:
-        loss_mask[0, -1] = 0
-    return {"attention_mask": torch.ones_like(loss_mask, dtype=torch.long), "loss_mask": loss_mask, "target": target,
-            "hidden_state": hidden_state, "input_ids": input_ids}
+    """algorithms/eagle3/data.py:10-27 (same as data/preprocessing.py:642-665): keep the first max_len tokens of every
+    feature, rename (the stored final-layer state becomes `target`, the stored auxiliary layers become `hidden_state`),
+    zero the LAST kept loss-mask position, attention mask of ones; every tensor gets a leading batch axis of 1."""
+    def head(t: torch.Tensor) -> torch.Tensor:           # [1, L, W] or [L] -> first max_len tokens, batch axis restored
+        t = t.squeeze(0) if t.dim() == 3 else t
+        return t[:max_len].unsqueeze(0)
+
+    out = {"input_ids": head(raw["input_ids"]), "loss_mask": head(raw["loss_mask"]).clone(),
+           "target": head(raw["hidden_state"]), "hidden_state": head(raw["aux_hidden_state"])}
+    if out["loss_mask"].numel():
+        out["loss_mask"][0, -1] = 0
+    out["attention_mask"] = torch.ones_like(out["loss_mask"], dtype=torch.long)
+    return out
 
 
 def collate_with_padding(features: List[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:

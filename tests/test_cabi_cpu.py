@@ -81,3 +81,11 @@ def test_dflash_param_layout_and_workspace(L):
     assert 20e9 < ws < 80e9, ws
     bad = SfDflashConfig(4, 2048, 512, 16, 4096, 5, 12288, 32, 8, 100, 5, 151936, 151669, 41000, 1e-6, 0.0)
     assert L.sf_dflash_workspace_bytes(bad) == 0 and b"multiples of 8" in L.sf_last_error()
+
+
+def test_debug_option_names(L):
+    L.sf_debug_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    for name in (b"no_pdl", b"loss_side", b"no_overlap", b"no_swiglu_fusion", b"gemm_group_m", b"gemm_group_m_midk", b"gemm_group_m_wgrad"):
+        assert L.sf_debug_option(name, 0) == 0, name
+    assert L.sf_debug_option(b"no_such_switch", 1) != 0
+    assert b"unknown option" in L.sf_last_error()
