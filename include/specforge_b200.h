@@ -33,7 +33,7 @@ extern "C" {
 const char* sf_version(void);
 const char* sf_last_error(void);
 /* Tuning / A-B switch by name ("no_pdl", "loss_side", "no_overlap", "no_swiglu_fusion", "gemm_group_m",
- * "gemm_group_m_midk", "gemm_group_m_wgrad"); each defaults to its SF_<NAME> environment variable.  Diagnostic only. */
+ * "gemm_group_m_midk", "gemm_group_m_wgrad", "dflash_attn_tc"); each defaults to its SF_<NAME> environment variable.  Diagnostic only. */
 int sf_debug_option(const char* name, int value);
 long long sf_launch_count(void);      /* kernels launched by this library since the last reset */
 void sf_launch_count_reset(void);

@@ -34,6 +34,14 @@ CASES = {
                             torch.bfloat16, "prefix5", 3),
     # many tokens are 7 or 8 and the frozen head is biased towards them -> non-trivial accuracy numerator
     "dflash_biased_head_f32": (dict(num_anchors=7), 2, 40, torch.float32, "biased", 4),
+    # shapes the tensor-core block attention covers (group 4 x block 16 = 64 rows per anchor block, head_dim 64 / 128);
+    # written as dflashtc_* so the default GPU suite does not pick them up before that path has been run once
+    "dflashtc_d64_bf16": (dict(hidden_size=256, intermediate_size=512, num_heads=4, num_kv_heads=1, head_dim=64, num_layers=2,
+                               num_target_feats=2, vocab_size=512, mask_token_id=511, block_size=16, num_anchors=6), 2, 160,
+                          torch.bfloat16, "prefix5", 5),
+    "dflashtc_d128_drop_bf16": (dict(hidden_size=512, intermediate_size=512, num_heads=8, num_kv_heads=2, head_dim=128, num_layers=1,
+                                     num_target_feats=2, vocab_size=512, mask_token_id=511, block_size=16, num_anchors=7), 2, 130,
+                                torch.bfloat16, "short_row", 6),
 }
 
 

@@ -558,6 +558,7 @@ static int attn_check(const AttnArgs& a) {
     return 0;
 }
 int attn_fwd(const AttnArgs& a, cudaStream_t st) {
+    if (opt(OPT_DFLASH_ATTN_TC) == 1 && attn_tc_supported(a)) return attn_fwd_tc(a, st);   // experimental tcgen05 path
     if (int rc = attn_check(a)) return rc;
     const int R = (a.nh / a.nkv) * a.bs;
     const int smem = (int)attn_smem_fwd(R, a.d);

@@ -79,3 +79,22 @@ def test_dflash_deterministic_accumulate_and_eval():
     eng.forward(batch, anchors, keep, need_grad=False)
     assert torch.equal(eng.loss, l1)
     assert torch.isfinite(g1).all() and float(g1.abs().sum()) > 0
+
+
+TC_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "dflashtc_*.pt")))
+
+
+@pytest.mark.skipif(os.environ.get("SF_DFLASH_TC_TESTS") != "1", reason="tensor-core DFlash attention has not been run on a GPU yet "
+                    "(written after the round's GPU budget was spent); set SF_DFLASH_TC_TESTS=1 to exercise it")
+@pytest.mark.parametrize("tc", [0, 1], ids=["cuda_core", "tcgen05"])
+@pytest.mark.parametrize("path", TC_GOLDEN, ids=lambda p: os.path.basename(p)[:-3])
+def test_dflash_tc_shapes(path, tc):
+    import ctypes
+    from specforge_b200._lib import lib
+    L = lib()
+    L.sf_debug_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    assert L.sf_debug_option(b"dflash_attn_tc", tc) == 0
+    try:
+        test_dflash_step_matches_reference_and_oracle(path)
+    finally:
+        L.sf_debug_option(b"dflash_attn_tc", 0)

@@ -8,11 +8,11 @@ import torch
 
 from oracle import dflash_oracle as D
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "dflash_*.pt")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "dflash*.pt")))   # dflash_* and dflashtc_*
 
 
 def test_goldens_present():
-    assert len(GOLDEN) >= 6
+    assert len(GOLDEN) >= 8
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-3])
