@@ -40,6 +40,8 @@ int headnorm_rope_bwd(const void* x, int64_t ldx, int n_heads, int d, const void
 int attn_fwd(const AttnArgs& a, cudaStream_t st);
 bool attn_tc_supported(const AttnArgs& a);          // sf_dflash_attn_tc.cu (experimental, off by default)
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t st);
+bool attn_tc_bwd_supported(const AttnArgs& a);      // sf_dflash_attn_tc_bwd.cu (experimental, off by default)
+int attn_bwd_tc(const AttnArgs& a, cudaStream_t st);
 int attn_bwd(const AttnArgs& a, cudaStream_t st);
 int ce(void* logits, int64_t ld, int V, const int32_t* tgt, const float* w, const float* lw, float* sums, int write_grad,
        float* row_loss, float* row_correct, int64_t M, cudaStream_t st);

@@ -569,6 +569,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
     return 0;
 }
 int attn_bwd(const AttnArgs& a, cudaStream_t st) {
+    if (opt(OPT_DFLASH_ATTN_TC) == 1 && attn_tc_bwd_supported(a)) return attn_bwd_tc(a, st);   // experimental tcgen05 path
     if (int rc = attn_check(a)) return rc;
     const int R = (a.nh / a.nkv) * a.bs;
     const int smem = (int)attn_smem_bwd(R, a.d);
