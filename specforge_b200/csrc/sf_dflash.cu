@@ -66,7 +66,7 @@ struct Plan {
     int64_t pos, tgt, nid, w, lw, sums, row_loss, row_correct;
     int64_t ctx_raw, ctx, x, hn, qkv, kvc, qr, krn, krc, attn, lse, x1, hn2, gu, act, hf, logits;
     // backward
-    int64_t dxa, dxb, dtmp, dgu, dact, dattn, dqr, dkrn, dvn, dkrc, dvc, dqkv, dkvc, delta, dctx32, dctx, norm_ws, head_ws;
+    int64_t dxa, dxb, dtmp, dgu, dact, dattn, dqr, dkrn, dkrc, dqkv, dkvc, delta, dctx32, dctx, norm_ws, head_ws;
     int64_t total;
 };
 static Plan make_plan(const sf_dflash_config& c) {
@@ -89,8 +89,8 @@ static Plan make_plan(const sf_dflash_config& c) {
     p.hf = take(Mq * x.H * 2); p.logits = take(Mq * (int64_t)x.V * 2);
     p.dxa = take(Mq * x.H * 2); p.dxb = take(Mq * x.H * 2); p.dtmp = take(Mq * x.H * 2);
     p.dgu = take(Mq * 2 * x.I * 2); p.dact = take(Mq * x.I * 2); p.dattn = take(Mq * x.A * 2);
-    p.dqr = take(Mq * x.A * 2); p.dkrn = take(Mq * x.KV * 2); p.dvn = take(Mq * x.KV * 2);
-    p.dkrc = take(Mc * x.KV * 2); p.dvc = take(Mc * x.KV * 2);
+    p.dqr = take(Mq * x.A * 2); p.dkrn = take(Mq * x.KV * 2);      // dV goes straight into d(qkv) / d(kv_c)
+    p.dkrc = take(Mc * x.KV * 2);
     p.dqkv = take(Mq * x.QKV * 2); p.dkvc = take(Mc * 2 * x.KV * 2);
     p.delta = take(Mq * x.nh * 4);
     p.dctx32 = take(Mc * x.H * 4); p.dctx = take(Mc * x.H * 2);
