@@ -134,6 +134,12 @@ class DFlashEngine:
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._frozen = None
         self._batch = None
+        # optimizer state (same members as Eagle3Engine, so B200TrainingBackend drives either engine)
+        self.grads_bf16 = torch.zeros(self.n_params, dtype=torch.bfloat16, device=self.device)
+        self.master = self.exp_avg = self.exp_avg_sq = None
+        self.opt_step = 0
+        self._scratch = torch.zeros(1024, dtype=torch.float32, device=self.device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     def _cfg(self, B, S, N, rope_rows) -> SfDflashConfig:
         d = self.dims
@@ -205,11 +211,46 @@ class DFlashEngine:
                                       self.metrics.data_ptr(), self.loss.data_ptr(), int(need_grad), self._stream()), "sf_dflash_forward")
         return self.loss, self.metrics
 
-    def backward(self, accumulate: bool = False) -> None:
+    def backward(self, accumulate: bool = False, loss_scale: float = 1.0, on_ready=None) -> None:
+        """`loss_scale` must be 1 (the backend scales on the way to bf16); `on_ready` is accepted for interface parity with
+        Eagle3Engine and ignored: the backend then all-reduces the whole buffer in step()."""
+        if loss_scale != 1.0:
+            raise ValueError("DFlashEngine.backward: loss_scale != 1 is not supported")
         if self._batch is None:
             raise RuntimeError("backward() without a preceding forward(need_grad=True)")
         check(lib().sf_dflash_backward(self._call_cfg, self.params.data_ptr(), self._frozen, self._batch, self._ws_ptr, self.workspace_bytes,
                                        self.grads_f32.data_ptr(), int(accumulate), self._stream()), "sf_dflash_backward")
+
+
+    def grads_to_bf16(self, scale: Optional[torch.Tensor] = None, first: int = 0, count: Optional[int] = None) -> torch.Tensor:
+        """fp32 accumulators -> the bf16 gradient buffer (optionally times a DEVICE scalar, no host sync)."""
+        L = lib()
+        L.sf_grads_to_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+        sp = None
+        if scale is not None:
+            scale = scale.detach().to(self.device, torch.float32).reshape(1)
+            self._scale_keep = scale
+            sp = scale.data_ptr()
+        count = self.n_params - first if count is None else count
+        check(L.sf_grads_to_bf16(self.grads_f32.data_ptr() + 4 * first, self.grads_bf16.data_ptr() + 2 * first, count, sp, self._stream()),
+              "sf_grads_to_bf16")
+        return self.grads_bf16
+
+    def optimizer_step(self, lr: float, *, grad_scale: float = 1.0, max_grad_norm: float = 0.5, betas=(0.9, 0.999), eps: float = 1e-8,
+                       weight_decay: float = 0.0) -> torch.Tensor:
+        """Fused clip + AdamW on the flat buffers (optimizer.py:95-168 semantics, see sf_optimizer_step)."""
+        L = lib()
+        L.sf_optimizer_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                                        c_float, c_float, c_float, ctypes.c_int, c_void_p, c_void_p, c_void_p]
+        if self.master is None:
+            self.master = self.params.float()
+            self.exp_avg = torch.zeros_like(self.master)
+            self.exp_avg_sq = torch.zeros_like(self.master)
+        self.opt_step += 1
+        check(L.sf_optimizer_step(self.grads_bf16.data_ptr(), self.master.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                  self.params.data_ptr(), self.n_params, grad_scale, max_grad_norm, lr, betas[0], betas[1], eps, weight_decay,
+                                  self.opt_step, self.grad_norm.data_ptr(), self._scratch.data_ptr(), self._stream()), "sf_optimizer_step")
+        return self.grad_norm
 
 
 # ------------------------------------------------------------------------------------------------ draft-registry seam
@@ -307,3 +348,74 @@ class B200DFlashDraftModel(torch.nn.Module):
             raise RuntimeError(f"state_dict mismatch: missing={missing} unexpected={unexpected}")
         self.engine.load_params({n: state_dict[n] for n in self._names if n in state_dict} | {n: self._flat[n] for n in missing})
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+
+# ------------------------------------------------------------------------------------------------ strategy seam
+class _DFlashStepFn(torch.autograd.Function):
+    """loss = f(flat params): forward / backward run in the CUDA library, the fp32 flat gradient stays in the engine."""
+
+    @staticmethod
+    def forward(ctx, flat_params, strategy, batch_tensors, anchors, keep, need_grad):
+        loss, _ = strategy.engine.forward(batch_tensors, anchors, keep, need_grad=need_grad)
+        ctx.strategy = strategy
+        return loss.clone().reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        st = ctx.strategy
+        st._last_grad_out = grad_out.detach()
+        st.engine.backward(accumulate=st._micro_in_window > 0)
+        st._micro_in_window += 1
+        return None, None, None, None, None, None
+
+
+class _DFlashTrainable(torch.nn.Module):
+    def __init__(self, draft_model):
+        super().__init__()
+        self.draft_model = draft_model
+
+
+class B200DFlashTrainStrategy:
+    """`DFlashTrainStrategy` (training/strategies/base.py:415-452) on the CUDA step: same name, required features and
+    `StepOutput` fields (`accuracy`, `accuracy_denom`, `ratio_metrics["acc"]`, `loss_terms`).  Anchors are drawn here with
+    the reference's procedure (`OnlineDFlashModel._sample_anchor_positions`), on the batch's device, from `generator`."""
+    name = "dflash"
+    required_features = {"input_ids", "hidden_states", "loss_mask"}
+
+    def __init__(self, draft_model: "B200DFlashDraftModel", *, target_embed_weight: torch.Tensor, target_head_weight: torch.Tensor,
+                 num_anchors: int = 512, generator: Optional[torch.Generator] = None):
+        if draft_model.engine is None:
+            raise RuntimeError("bind_engine() must be called on the draft model first")
+        self.draft_model, self.engine = draft_model, draft_model.engine
+        self.num_anchors, self.generator = num_anchors, generator
+        self.engine.set_frozen(embed_tokens=target_embed_weight, lm_head=target_head_weight)
+        self._module = _DFlashTrainable(draft_model)
+        self._micro_in_window = 0
+        self._last_grad_out: Optional[torch.Tensor] = None
+        self._is_boundary = True
+        self.grad_ready_hook = None
+        self.return_autograd_grads = False
+
+    def trainable_module(self) -> torch.nn.Module:
+        return self._module
+
+    def validate_batch(self, batch) -> None:
+        missing = {f for f in self.required_features if f not in batch.tensors}
+        if missing:
+            raise ValueError(f"{self.name} batch missing required features {sorted(missing)}; present={sorted(batch.tensors)}")
+
+    def forward_loss(self, batch, ctx=None):
+        from .contracts import StepOutput
+        self.validate_batch(batch)
+        t = batch.tensors
+        anchors, keep = sample_anchor_positions(t["loss_mask"].to(self.engine.device).float(), self.num_anchors, generator=self.generator)
+        need_grad = torch.is_grad_enabled()
+        eng = self.engine
+        flat = eng.params if not need_grad else eng.params.detach().requires_grad_(True)
+        loss = _DFlashStepFn.apply(flat, self, t, anchors, keep, need_grad)
+        m = eng.metrics.clone()            # loss_num, loss_den, correct, accuracy_den (device, no host sync)
+        return StepOutput(loss=loss, metrics={"accuracy": m[2] / m[3], "accuracy_denom": m[3]},
+                          ratio_metrics={"acc": (m[2], m[3])}, loss_terms=(m[0], m[1]))
+
+    def checkpoint_state_filter(self, state_dict):
+        return {k.replace("draft_model.", ""): v for k, v in state_dict.items() if "draft_model." in k}

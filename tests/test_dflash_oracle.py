@@ -77,3 +77,54 @@ def test_product_anchor_sampler_equals_oracle_under_same_rng():
     torch.manual_seed(11)
     a2, k2 = D.sample_anchor_positions(lm, 9)
     assert torch.equal(a1, a2) and torch.equal(k1, k2)
+
+
+def test_dflash_strategy_host_logic_with_a_fake_engine():
+    """B200DFlashTrainStrategy: StepOutput contract of the reference's DFlashTrainStrategy (strategies/base.py:415-452) and the
+    micro-batch accumulation protocol the backend relies on — checked on CPU with a stand-in engine."""
+    from specforge_b200.contracts import TrainBatch
+    from specforge_b200.dflash import B200DFlashTrainStrategy
+
+    class FakeEngine:
+        device = torch.device("cpu")
+
+        def __init__(self):
+            self.params = torch.zeros(8, dtype=torch.bfloat16)
+            self.metrics = torch.tensor([6.0, 3.0, 2.0, 4.0])
+            self.loss = torch.tensor([2.0])
+            self.calls = []
+
+        def set_frozen(self, **kw):
+            self.frozen = kw
+
+        def forward(self, batch, anchors, keep, need_grad=True):
+            self.calls.append(("fwd", tuple(anchors.shape), need_grad))
+            return self.loss, self.metrics
+
+        def backward(self, accumulate=False):
+            self.calls.append(("bwd", accumulate))
+
+    class FakeDraft:
+        engine = FakeEngine()
+
+    st = B200DFlashTrainStrategy(FakeDraft(), target_embed_weight=torch.zeros(4, 4), target_head_weight=torch.zeros(4, 4), num_anchors=5,
+                                 generator=torch.Generator().manual_seed(0))
+    assert st.name == "dflash" and st.required_features == {"input_ids", "hidden_states", "loss_mask"}
+    batch = TrainBatch(sample_ids=["0", "1"], strategy="dflash",
+                       tensors={"input_ids": torch.zeros(2, 12, dtype=torch.long), "hidden_states": torch.zeros(2, 12, 8),
+                                "loss_mask": torch.ones(2, 12)}, metadata={})
+    out = st.forward_loss(batch)
+    assert float(out.loss) == 2.0 and out.loss.requires_grad
+    assert float(out.metrics["accuracy"]) == 0.5 and float(out.metrics["accuracy_denom"]) == 4.0
+    assert [float(v) for v in out.ratio_metrics["acc"]] == [2.0, 4.0] and [float(v) for v in out.loss_terms] == [6.0, 3.0]
+    (out.loss / 2).backward()
+    out2 = st.forward_loss(batch)
+    (out2.loss / 2).backward()
+    eng = FakeDraft.engine
+    assert eng.calls == [("fwd", (2, 5), True), ("bwd", False), ("fwd", (2, 5), True), ("bwd", True)]
+    assert float(st._last_grad_out) == 0.5
+    with torch.no_grad():
+        st.forward_loss(batch)
+    assert eng.calls[-1] == ("fwd", (2, 5), False)
+    with pytest.raises(ValueError):
+        st.forward_loss(TrainBatch(sample_ids=["0"], strategy="dflash", tensors={"input_ids": torch.zeros(1, 4)}, metadata={}))
