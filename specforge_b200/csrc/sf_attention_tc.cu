@@ -3,17 +3,17 @@
 // Same semantics as sf_attention.cu (block-0 causal flash attention whose running softmax state is seeded with
 // the T-1 diagonal scores; reference specforge/modeling/draft/llama3_eagle.py:717-785).
 //
-// CTA = (128 query rows) x (one or two query heads of the same GQA group) x batch element.  Both heads share
-// every K/V tile, so K/V smem traffic is halved, and the two softmax warpgroups ping-pong against the single MMA
-// issuer: while warpgroup A exponentiates S_a(t), the tensor core runs P_b(t-1)·V and Q_b·K(t)^T.
-//   warp 0     TMA producer   (Q tiles once, K/V tiles through 2-stage rings; 3-D tensor maps [cols, S, B] so rows
-//                              past the end of a sequence are zero-filled, never another sequence's data)
-//   warp 1     MMA issuer     (S = Q K^T  -> TMEM;  O_tile = P V -> TMEM; one thread)
-//   warp 2     TMEM allocator
-//   warps 4-7  softmax warpgroup for head a: one thread per query row (TMEM lane), running max/sum in registers,
-//   warps 8-11 same for head b               P written as bf16 into a SWIZZLE_128B K-major smem tile (the A operand
-//                                            of the PV MMA), O accumulated in registers from the per-tile TMEM result
-//                                            with the deferred rescale alpha_{t-1} (off the critical path).
+// CTA = (128 query rows) x (one or two query heads of the same GQA group) x batch element.  Both heads share every K/V tile
+// (K/V smem traffic halved); each head has its own MMA issuer thread and softmax warpgroup, so one head's exponentials run
+// under the other head's MMAs.
+//   warp 0     TMA producer   Q tiles once + the K ring (4 stages; 3-D tensor maps [cols, S, B]: rows past the end of a
+//                             sequence are zero-filled, never another sequence's data)
+//   warp 3     TMA producer   V ring (own thread: a late PV never delays the K loads)
+//   warps 1,2  MMA issuers    one thread per head: S = Q K^T -> TMEM (double-buffered), O += P V -> TMEM (accumulated
+//                             across all kv tiles); warp 2 also allocates the 512 TMEM columns
+//   warps 4-7  softmax warpgroup of head a: one thread per query row (= TMEM lane), running max / sum in registers, P written
+//   warps 8-11 same for head b               as bf16 into a SWIZZLE_128B K-major smem tile (the A operand of the PV MMA); O
+//                                            stays in TMEM and is rescaled lazily (only when the running max grew by > 2^8).
 #include "sf_gemm.cuh"   // CUtensorMap, make_* helpers
 #include "sf_host.h"
 #include <cudaTypedefs.h>

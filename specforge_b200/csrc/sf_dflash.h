@@ -46,7 +46,6 @@ int attn_bwd(const AttnArgs& a, cudaStream_t st);
 int ce(void* logits, int64_t ld, int V, const int32_t* tgt, const float* w, const float* lw, float* sums, int write_grad,
        float* row_loss, float* row_correct, int64_t M, cudaStream_t st);
 int finalize_loss(const float* sums, float* metrics, float* loss, cudaStream_t st);
-int add(const void* x, const void* y, void* o, int64_t n, cudaStream_t st);
 
 }  // namespace dflash
 }  // namespace sf

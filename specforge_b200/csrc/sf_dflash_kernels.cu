@@ -504,12 +504,6 @@ __global__ void finalize_kernel(const float* __restrict__ sums, float* __restric
     loss[0] = sums[2] / sums[0];
 }
 
-// out = a + b (bf16), fp32 add
-__global__ void add_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ o, int64_t n) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        o[i] = __float2bfloat16_rn(bf(x[i]) + bf(y[i]));
-}
-
 // ------------------------------------------------------------------ host wrappers
 static int64_t attn_smem_fwd(int R, int d) { return (int64_t)(R * (d + 1) + kTK * (d + 1) + kTK * d + R * (kTK + 1) + 3 * R) * 4; }
 static int64_t attn_smem_bwd(int R, int d) { return (int64_t)(2 * R * (d + 1) + 2 * kTK * (d + 1) + 2 * R * (kTK + 1) + 2 * R) * 4; }
@@ -598,11 +592,5 @@ int finalize_loss(const float* sums, float* metrics, float* loss, cudaStream_t s
     SF_CUDA_CHECK_LAUNCH("dflash finalize");
     return 0;
 }
-int add(const void* x, const void* y, void* o, int64_t n, cudaStream_t st) {
-    add_kernel<<<148 * 8, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (__nv_bfloat16*)o, n);
-    SF_CUDA_CHECK_LAUNCH("dflash add");
-    return 0;
-}
-
 }  // namespace dflash
 }  // namespace sf
