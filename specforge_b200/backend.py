@@ -55,6 +55,16 @@ class B200TrainingBackend:
         self.overlap_allreduce = True
 
     @property
+    def parallel_config(self):
+        """What the reference controller reads off a backend (training/controller.py:379-380,413-414,692; the reference
+        type is training/backend.py:31-54): pure data parallelism — every group is the data-parallel group."""
+        from types import SimpleNamespace
+        pg = self.process_group
+        return SimpleNamespace(world_size=self.world_size, tp_size=1, sp_ulysses_size=1, sp_ring_size=1, sharding_strategy="NO_SHARD",
+                               param_dtype=torch.bfloat16, fsdp_process_group=pg, dp_group=pg, draft_dp_group=pg, tp_group=None,
+                               sp_ulysses_group=None, sp_ring_group=None, draft_sp_group=None, device_mesh=None, tp_device_mesh=None, extra={})
+
+    @property
     def world_size(self) -> int:
         return dist.get_world_size(self.process_group) if dist.is_available() and dist.is_initialized() else 1
 

@@ -99,3 +99,14 @@ def test_lr_schedule_matches_reference_formula():
     mid = warm + (1000 - warm) // 2
     assert s.lr_at(mid) == pytest.approx(1e-4 * (1 + math.cos(math.pi * (mid - warm) / (1000 - warm))) / 2)
     assert LRSchedule(1e-4, 1000, 0.015, "constant").lr_at(500) == 1e-4
+
+
+def test_backend_exposes_what_the_reference_controller_reads():
+    """training/controller.py reads backend.parallel_config.fsdp_process_group, backend.optimizer.get_learning_rate() and
+    backend.optimizer_state_is_replicated."""
+    from specforge_b200.backend import B200TrainingBackend
+    b = B200TrainingBackend(lr=1e-3, total_steps=1000, warmup_ratio=0.1)
+    pc = b.parallel_config
+    assert pc.world_size == 1 and pc.tp_size == 1 and pc.sharding_strategy == "NO_SHARD" and pc.fsdp_process_group is None
+    assert b.optimizer_state_is_replicated is True
+    assert b.optimizer.get_learning_rate() == pytest.approx(1e-3 / 100)
