@@ -34,6 +34,12 @@ CASES = {
                             torch.bfloat16, "prefix5", 3),
     # many tokens are 7 or 8 and the frozen head is biased towards them -> non-trivial accuracy numerator
     "dflash_biased_head_f32": (dict(num_anchors=7), 2, 40, torch.float32, "biased", 4),
+    # D-PACE objectives (dflash_family_model.py:247-279): detached confidence weights, loss normalised by the batch size
+    "dflash_dpace_f32": (dict(loss_type="dpace", dpace_alpha=0.5, block_size=8, num_anchors=5), 2, 48, torch.float32, "holes", 7),
+    "dflash_dpace_cumconf_f32": (dict(loss_type="dpace-cumulative-confidence-only", dpace_alpha=0.3, block_size=8, num_anchors=5), 2, 48,
+                                 torch.float32, "holes", 8),
+    "dflash_dpace_contval_f32": (dict(loss_type="dpace-continuation-value-only", dpace_alpha=0.7, block_size=8, num_anchors=5), 2, 48,
+                                 torch.float32, "prefix5", 9),
     # shapes the tensor-core block attention covers (group 4 x block 16 = 64 rows per anchor block, head_dim 64 / 128);
     # written as dflashtc_* so the default GPU suite does not pick them up before that path has been run once
     "dflashtc_d64_bf16": (dict(hidden_size=256, intermediate_size=512, num_heads=4, num_kv_heads=1, head_dim=64, num_layers=2,
@@ -86,7 +92,8 @@ def main():
         emb.requires_grad_(False)
         head.requires_grad_(False)
         model = OnlineDFlashModel(draft, head, emb, mask_token_id=c.mask_token_id, block_size=c.block_size, attention_backend="eager",
-                                  num_anchors=c.num_anchors, loss_decay_gamma=c.loss_decay_gamma, objective_chunk_blocks=0)
+                                  num_anchors=c.num_anchors, loss_decay_gamma=c.loss_decay_gamma, objective_chunk_blocks=0,
+                                  loss_type=c.loss_type, dpace_alpha=c.dpace_alpha)
         if lmk == "biased":
             head_w[7] *= 6.0
             head_w[8] = -head_w[7]          # the hidden states of all slots are similar: one of the two always wins

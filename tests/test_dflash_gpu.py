@@ -18,6 +18,8 @@ def test_dflash_step_matches_reference_and_oracle(path):
     from oracle import dflash_oracle as D
     from specforge_b200.dflash import DFlashDims, DFlashEngine
     g = torch.load(path, weights_only=False)
+    if g["config"].get("loss_type", "dflash") != "dflash":
+        pytest.skip("D-PACE objectives are pinned in the oracle only; the CUDA path implements loss_type='dflash'")
     c = D.DFlashConfig(**g["config"])
     dims = DFlashDims(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size, num_heads=c.num_heads, num_kv_heads=c.num_kv_heads,
                       head_dim=c.head_dim, num_layers=c.num_layers, num_target_feats=c.num_target_feats, vocab_size=c.vocab_size,
