@@ -428,6 +428,120 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_dflash(args):
+    """BASELINE config 4 (next row, NOT the headline metric): DFlash draft step, Qwen3-8B dims, 4 sequences x 2048 tokens per
+    GPU, 512 anchors x block 16, full-vocabulary frozen head; fwd + loss + bwd + all-reduce + clip/AdamW through
+    B200DFlashTrainStrategy / B200TrainingBackend.  Same JSON line layout as the EAGLE3 workload."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from specforge_b200._lib import lib
+    from specforge_b200.backend import B200TrainingBackend
+    from specforge_b200.contracts import TrainBatch
+    from specforge_b200.dflash import B200DFlashDraftModel, B200DFlashTrainStrategy
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = lib()
+    L.sf_profile_gemm.restype = None
+    L.sf_profile_gemm_collect.restype = ctypes.c_longlong
+    L.sf_profile_gemm_collect.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    Bd, Sd, Nd, bs, H, V, F = 4, 2048, 512, 16, 4096, 151936, 5
+    cfg = dict(hidden_size=H, intermediate_size=12288, num_attention_heads=32, num_key_value_heads=8, head_dim=128, num_hidden_layers=5,
+               vocab_size=V, block_size=bs, rms_norm_eps=1e-6, rope_theta=1000000.0, max_position_embeddings=40960,
+               dflash_config={"mask_token_id": 151669, "target_layer_ids": [1, 9, 17, 25, 33]}, layer_types=["full_attention"] * 5)
+    draft = B200DFlashDraftModel(cfg)
+    eng = draft.bind_engine(batch=Bd, seq_len=Sd, num_anchors=Nd, device=dev, seed=0)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    embed = (torch.randn(V, H, device=dev, generator=gen) * 0.02).bfloat16()
+    head = (torch.randn(V, H, device=dev, generator=gen) * 0.02).bfloat16()
+    strategy = B200DFlashTrainStrategy(draft, target_embed_weight=embed, target_head_weight=head, num_anchors=Nd,
+                                       generator=torch.Generator(device=dev).manual_seed(100 + rank))
+    backend = B200TrainingBackend(lr=1e-4, max_grad_norm=1.0, total_steps=100000, warmup_ratio=0.015)
+    backend.attach(strategy)
+    backend.prepare_model(strategy.trainable_module())
+    dgen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    dev_t = {"input_ids": torch.randint(0, V - 1000, (Bd, Sd), device=dev, generator=dgen),
+             "hidden_states": torch.randn(Bd, Sd, F * H, device=dev, generator=dgen).bfloat16(),
+             "loss_mask": torch.ones(Bd, Sd, device=dev)}
+    host_t = {k: v.cpu().pin_memory() for k, v in dev_t.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host_t.values())
+    ids = [str(i) for i in range(Bd)]
+    mk = lambda t: TrainBatch(sample_ids=ids, strategy="dflash", tensors=t, metadata={})
+
+    def step(batch, read_loss):
+        out = strategy.forward_loss(batch)
+        backend.backward(out.loss, is_boundary=True)
+        backend.step()
+        return float(out.loss.item()) if read_loss else None
+
+    def timed(batches, read_loss):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last, n = None, 0
+        for b in batches:
+            last = step(b, read_loss)
+            n += 1
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / max(1, n), last
+
+    from specforge_b200.feed import DevicePrefetcher
+    for _ in range(max(3, args.warmup)):
+        step(mk(dev_t), False)
+    L.sf_launch_count_reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_step, _ = timed((mk(dev_t) for _ in range(args.steps)), False)
+    clocks = sampler.stop()
+    launches = int(L.sf_launch_count())
+    L.sf_profile_gemm(1)
+    ms_prof, _ = timed((mk(dev_t) for _ in range(args.steps)), False)
+    gms, gfl = ctypes.c_double(), ctypes.c_double()
+    L.sf_profile_gemm_collect(ctypes.byref(gms), ctypes.byref(gfl))
+    L.sf_profile_gemm(0)
+    for b in DevicePrefetcher((mk(host_t) for _ in range(3)), device=dev):
+        step(b, True)
+    ms_e2e, last_loss = timed(DevicePrefetcher((mk(host_t) for _ in range(args.steps)), device=dev), True)
+    sustained, burst, peak_src = peaks()
+    A, KV, I, Lr, Mq, Mc = 4096, 1024, 12288, 5, Bd * Nd * bs, Bd * Sd
+    fwd = 2 * Mc * F * H * H + Lr * (2 * Mq * H * (A + 2 * KV) + 2 * Mc * H * 2 * KV + 2 * Mq * A * H + 6 * Mq * H * I) + 2 * Mq * H * V
+    flops = 3 * fwd - 2 * Mq * H * V + 3.5 * Lr * 4 * Bd * 32 * 128 * Nd * bs * (Sd / 2 + bs)     # no wgrad for the frozen head
+    achieved = (gfl.value / 1e12) / (gms.value / 1e3) if gms.value > 0 else 0.0
+    line = {"metric": "DFlash draft-step samples/sec (Qwen3-8B, 5 layers, block 16, 512 anchors, seq 2048)", "value": world * Bd / (ms_step / 1e3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE config 4 per GPU: Qwen3-8B DFlash draft step (fwd + loss + bwd + grad all-reduce + clip/AdamW)",
+                       "batch_per_gpu": Bd, "global_batch": world * Bd, "seq_len": Sd, "block_size": bs, "num_anchors": Nd,
+                       "parallelism": f"dp{world}", "l2": "inputs_exceed_l2", "attention": "tcgen05" if os.environ.get("SF_DFLASH_ATTN_TC") == "1" else "cuda-core (first correct version)"},
+            "e2e": {"value": world * Bd / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e, "last_loss": last_loss},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "sf::gemm_kernel (tcgen05)", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                         "frac": achieved / sustained if sustained else None, "peak_burst": burst, "peak_source": peak_src,
+                         "gemm_ms_per_step": gms.value / args.steps, "ms_per_step_with_events": ms_prof,
+                         "step_tflops_algorithmic": flops / 1e12 / (ms_step / 1e3),
+                         "step_frac_of_burst": flops / 1e12 / (ms_step / 1e3) / burst if burst else None, "traffic": None}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     wd = int(os.environ.get("SF_BENCH_WATCHDOG", "0"))
     if wd > 0:   # diagnostic: dump every thread's Python stack and exit if the run takes longer than `wd` seconds
@@ -442,10 +556,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="eagle3", choices=["eagle3", "dflash"],
+                    help="eagle3 = the headline metric (BASELINE config 2); dflash = BASELINE config 4 (next row, opt-in)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "dflash":
+        run_dflash(args)
     else:
         run_ours(args)
 
