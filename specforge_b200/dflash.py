@@ -54,18 +54,28 @@ class DFlashDims:
     loss_decay_gamma: Optional[float] = None
 
 
-def sample_anchor_positions(loss_mask: torch.Tensor, num_anchors: int, generator: Optional[torch.Generator] = None):
+def sample_anchor_positions(loss_mask: torch.Tensor, num_anchors: int, generator: Optional[torch.Generator] = None,
+                            fixed_width: bool = False):
     """Anchors whose clean token and first target are supervised (dflash_family_model.py:179-210); returns
     (anchors [B, W] sorted, 0 where dropped; keep [B, W] bool).  Same tensor ops and RNG call as the reference, so with the
-    same generator state it draws the same anchors."""
+    same generator state it draws the same anchors.
+
+    The reference narrows W to min(num_anchors, max candidates in the batch), which costs a device->host sync per step
+    (`.item()`).  `fixed_width=True` keeps W = num_anchors and lets `keep` drop the surplus blocks instead: the kept anchors,
+    and therefore loss, metrics and gradients, are identical (dropped blocks contribute nothing), with no sync."""
     B, S = loss_mask.shape
     dev = loss_mask.device
     n_cand = max(S - 1, 0)
     valid = (loss_mask[:, :n_cand] > 0.5) & (loss_mask[:, 1:n_cand + 1] > 0.5)
     counts = valid.sum(dim=1)
-    width = min(num_anchors, int(counts.max().item()))
-    if width == 0:
-        raise ValueError("DFlash-family training requires two consecutive supervised tokens")
+    if fixed_width:
+        width = min(num_anchors, n_cand)
+        if width == 0:
+            raise ValueError("DFlash-family training requires two consecutive supervised tokens")
+    else:
+        width = min(num_anchors, int(counts.max().item()))
+        if width == 0:
+            raise ValueError("DFlash-family training requires two consecutive supervised tokens")
     r = torch.rand(valid.shape, device=dev, generator=generator)
     r.masked_fill_(~valid, 2.0)
     cand = r.argsort(dim=1)[:, :width]
@@ -383,11 +393,12 @@ class B200DFlashTrainStrategy:
     required_features = {"input_ids", "hidden_states", "loss_mask"}
 
     def __init__(self, draft_model: "B200DFlashDraftModel", *, target_embed_weight: torch.Tensor, target_head_weight: torch.Tensor,
-                 num_anchors: int = 512, generator: Optional[torch.Generator] = None):
+                 num_anchors: int = 512, generator: Optional[torch.Generator] = None, sync_free_anchors: bool = True):
         if draft_model.engine is None:
             raise RuntimeError("bind_engine() must be called on the draft model first")
         self.draft_model, self.engine = draft_model, draft_model.engine
         self.num_anchors, self.generator = num_anchors, generator
+        self.sync_free_anchors = sync_free_anchors      # see sample_anchor_positions(fixed_width=...)
         self.engine.set_frozen(embed_tokens=target_embed_weight, lm_head=target_head_weight)
         self._module = _DFlashTrainable(draft_model)
         self._micro_in_window = 0
@@ -408,7 +419,8 @@ class B200DFlashTrainStrategy:
         from .contracts import StepOutput
         self.validate_batch(batch)
         t = batch.tensors
-        anchors, keep = sample_anchor_positions(t["loss_mask"].to(self.engine.device).float(), self.num_anchors, generator=self.generator)
+        anchors, keep = sample_anchor_positions(t["loss_mask"].to(self.engine.device).float(), self.num_anchors, generator=self.generator,
+                                                fixed_width=self.sync_free_anchors)
         need_grad = torch.is_grad_enabled()
         eng = self.engine
         flat = eng.params if not need_grad else eng.params.detach().requires_grad_(True)

@@ -373,3 +373,41 @@ class Eagle3ShardLoader:
         finally:
             stop.set()
             t.join(timeout=5)
+
+
+def _main(argv: Optional[Sequence[str]] = None) -> int:
+    """python -m specforge_b200.shards pack <hidden_states_dir> <out.sfpk> [--records-per-shard N]
+       python -m specforge_b200.shards info <shard.sfpk> [--verify]"""
+    import argparse
+    ap = argparse.ArgumentParser(prog="python -m specforge_b200.shards", description="SFPK packed shards of offline feature records")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    p = sub.add_parser("pack", help="repack the .ckpt/.ckpt.gz files written by scripts/prepare_hidden_states.py")
+    p.add_argument("src")
+    p.add_argument("out")
+    p.add_argument("--records-per-shard", type=int, default=0)
+    q = sub.add_parser("info", help="print the feature table and record lengths of a shard")
+    q.add_argument("shard")
+    q.add_argument("--verify", action="store_true", help="recompute every record's CRC-32")
+    a = ap.parse_args(argv)
+    if a.cmd == "pack":
+        for name in pack_offline_dir(a.src, a.out, records_per_shard=a.records_per_shard):
+            rd = ShardReader(name)
+            print(f"{name}: {len(rd)} records, {os.path.getsize(name) / 1e6:.1f} MB")
+            rd.close()
+        return 0
+    rd = ShardReader(a.shard)
+    print(f"{a.shard}: {len(rd)} records")
+    for name, dt, width in rd.features:
+        print(f"  {name:24s} {str(dt):16s} x{width}")
+    toks = [rd.tokens(i) for i in range(len(rd))]
+    if toks:
+        print(f"  tokens/record: min {min(toks)} max {max(toks)} total {sum(toks)}")
+    bad = [i for i in range(len(rd)) if a.verify and not rd.verify(i)]
+    if a.verify:
+        print("  CRC: " + ("all records ok" if not bad else f"MISMATCH in records {bad}"))
+    rd.close()
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(_main())

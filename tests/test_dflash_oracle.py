@@ -128,3 +128,29 @@ def test_dflash_strategy_host_logic_with_a_fake_engine():
     assert eng.calls[-1] == ("fwd", (2, 5), False)
     with pytest.raises(ValueError):
         st.forward_loss(TrainBatch(sample_ids=["0"], strategy="dflash", tensors={"input_ids": torch.zeros(1, 4)}, metadata={}))
+
+
+def test_sync_free_anchor_sampling_keeps_the_same_anchors():
+    """fixed_width=True pads with dropped blocks instead of narrowing the anchor table: kept anchors are the reference's."""
+    from specforge_b200.dflash import sample_anchor_positions
+    lm = (torch.rand(4, 50, generator=torch.Generator().manual_seed(5)) > 0.3).float()
+    lm[1, 6:] = 0
+    lm[2, 4:] = 0                         # every row has fewer than 40 candidates -> the reference narrows the table
+    torch.manual_seed(21)
+    a_ref, k_ref = D.sample_anchor_positions(lm, 40)
+    torch.manual_seed(21)
+    a_fix, k_fix = sample_anchor_positions(lm, 40, fixed_width=True)
+    assert a_fix.shape[1] == 40 and a_ref.shape[1] < 40
+    for b in range(4):
+        assert torch.equal(a_fix[b][k_fix[b]], a_ref[b][k_ref[b]])
+        assert not bool(a_fix[b][~k_fix[b]].any())
+    # and the objective is unchanged by the extra dropped blocks
+    c = D.DFlashConfig(num_anchors=40)
+    P = D.init_params(c, seed=2)
+    g = torch.Generator().manual_seed(9)
+    batch = {"input_ids": torch.randint(0, 250, (4, 50), generator=g), "hidden_states": torch.randn(4, 50, 128, generator=g), "loss_mask": lm}
+    emb, head = torch.randn(256, 64, generator=g) * 0.5, torch.randn(256, 64, generator=g) * 0.2
+    l_ref, _, t_ref = D.forward_loss(P, c, batch, a_ref, k_ref, emb, head)
+    l_fix, _, t_fix = D.forward_loss(P, c, batch, a_fix, k_fix, emb, head)
+    torch.testing.assert_close(l_fix, l_ref, rtol=1e-6, atol=1e-7)
+    assert float(t_fix["acc_den"]) == float(t_ref["acc_den"]) and float(t_fix["correct"]) == float(t_ref["correct"])

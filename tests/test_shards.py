@@ -121,3 +121,12 @@ def test_corruption_is_detected(tmp_path):
         ShardReader(shard)
     with pytest.raises(SfError):
         ShardReader(str(tmp_path / "missing.sfpk"))
+
+
+def test_pack_and_info_cli(tmp_path, capsys):
+    from specforge_b200.shards import _main
+    _write_reference_files(str(tmp_path / "feat"), [9, 20, 3], seed=2)
+    assert _main(["pack", str(tmp_path / "feat"), str(tmp_path / "x.sfpk")]) == 0
+    assert _main(["info", str(tmp_path / "x.sfpk"), "--verify"]) == 0
+    out = capsys.readouterr().out
+    assert "3 records" in out and "aux_hidden_state" in out and "all records ok" in out
