@@ -154,3 +154,58 @@ def test_sync_free_anchor_sampling_keeps_the_same_anchors():
     l_fix, _, t_fix = D.forward_loss(P, c, batch, a_fix, k_fix, emb, head)
     torch.testing.assert_close(l_fix, l_ref, rtol=1e-6, atol=1e-7)
     assert float(t_fix["acc_den"]) == float(t_ref["acc_den"]) and float(t_fix["correct"]) == float(t_ref["correct"])
+
+
+@pytest.mark.parametrize("g,bs", [(4, 16), (8, 16), (8, 8), (4, 32)])
+def test_tensor_core_tiling_reproduces_the_dflash_mask(g, bs):
+    """Index arithmetic of csrc/sf_dflash_attn_tc*.cu restated in Python (unit = 128 rows = 128/R blocks x g heads x bs slots,
+    CTA = 2 units; context tiles with a per-row key limit, then one own-keys tile with a block-diagonal mask; the context
+    dK/dV kernel iterates the contiguous range of kept blocks beyond the tile start) against oracle.dflash_mask."""
+    torch.manual_seed(g * 100 + bs)
+    B, S, N = 2, 200, 11
+    lm = (torch.rand(B, S) > 0.15).float()
+    lm[1, 40:] = 0                                   # row 1 has few candidates -> dropped blocks at the end
+    anchors, keep = D.sample_anchor_positions(lm, N)
+    N = anchors.shape[1]
+    want = D.dflash_mask(anchors, keep, S, bs)       # [B, N*bs, S + N*bs]
+    R, BKV = g * bs, 64
+    BPU = 128 // R
+    BPC = 2 * BPU
+    assert 256 // g <= BKV
+    got = torch.zeros_like(want)
+    for b in range(B):
+        for cta in range((N + BPC - 1) // BPC):
+            n0 = cta * BPC
+            kept_anchors = [int(anchors[b, n]) for n in range(n0, min(n0 + BPC, N)) if keep[b, n]]
+            n_ctx = (max(kept_anchors, default=0) + BKV - 1) // BKV
+            for x in range(2):
+                for r in range(128):
+                    blk = x * BPU + r // R
+                    n = n0 + blk
+                    hg, o = (r % R) // bs, r % bs
+                    if n >= N or hg != 0:            # the mask does not depend on the head: check head 0 of the group
+                        continue
+                    kept = bool(keep[b, n])
+                    a_r = int(anchors[b, n]) if kept else 0
+                    q = n * bs + o
+                    for t in range(n_ctx):           # context tiles
+                        for cc in range(BKV):
+                            key = t * BKV + cc
+                            if kept and key < a_r and key < S:
+                                got[b, q, key] = True
+                    for cc in range(BKV):            # own tile: key column cc is draft row n0*bs + cc
+                        if kept and cc // bs == blk and n0 * bs + cc < N * bs:
+                            got[b, q, S + n0 * bs + cc] = True
+    assert torch.equal(got, want)
+    # context-key-stationary backward: per 128-key tile, the kept blocks with anchor > k0 form [n_lo, n_hi)
+    for b in range(B):
+        for k0 in range(0, S, 128):
+            n_hi = n_lo = 0
+            for n in range(N):
+                if not keep[b, n]:
+                    break
+                n_hi = n + 1
+                if int(anchors[b, n]) <= k0:
+                    n_lo = n + 1
+            attends = [n for n in range(N) if keep[b, n] and bool(want[b, n * bs, k0:min(k0 + 128, S)].any())]
+            assert attends == list(range(n_lo, n_hi))
