@@ -224,6 +224,17 @@ int sf_dflash_backward(const sf_dflash_config* cfg, const void* params_flat, con
                        const sf_dflash_batch* batch, void* workspace, size_t workspace_bytes, float* grads_flat_f32,
                        int accumulate, void* stream);
 
+/* The DFlash block attention alone (contiguous [rows, heads*d] bf16 tensors; q/kn/vn/out/dq/dkn/dvn have B*N*bs rows, kc/vc/dkc/dvc
+ * B*S rows; lse / delta_ws are [B*N*bs, nh] fp32).  impl: 0 = CUDA-core tiles, 1 = tcgen05 (experimental), -1 = the step's choice.
+ * Reference semantics: dflash_family_model.py:47-89 (mask) + dflash.py:185-213 (attention, dropped blocks give zeros). */
+int sf_dflash_attention_fwd(const void* q, const void* kn, const void* vn, const void* kc, const void* vc, void* out, float* lse,
+                            const int32_t* anchors, const uint8_t* keep, int B, int S, int N, int bs, int nh, int nkv, int d,
+                            int impl, void* stream);
+int sf_dflash_attention_bwd(const void* q, const void* kn, const void* vn, const void* kc, const void* vc, const void* out,
+                            const float* lse, const void* dout, const int32_t* anchors, const uint8_t* keep, void* dq, void* dkn,
+                            void* dvn, void* dkc, void* dvc, float* delta_ws, int B, int S, int N, int bs, int nh, int nkv, int d,
+                            int impl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -316,3 +316,42 @@ extern "C" int sf_dflash_backward(const sf_dflash_config* cfg, const void* param
     SF_TRY(setup(c, cfg, params_flat, workspace, workspace_bytes, stream));
     return backward(c, *frozen, *batch, grads_flat_f32, accumulate);
 }
+
+// ---- op-level entry points: the DFlash block attention alone, on contiguous tensors (tests / tools; `impl` picks the kernels:
+// 0 = CUDA-core tiles, 1 = tcgen05, -1 = whatever the step would use)
+static AttnArgs op_args(const void* q, const void* kn, const void* vn, const void* kc, const void* vc, void* out, float* lse,
+                        const int32_t* anchors, const uint8_t* keep, int B, int S, int N, int bs, int nh, int nkv, int d) {
+    AttnArgs a{};
+    const int64_t A = (int64_t)nh * d, KV = (int64_t)nkv * d;
+    a.q = (const __nv_bfloat16*)q; a.ldq = A; a.kn = (const __nv_bfloat16*)kn; a.ldkn = KV; a.vn = (const __nv_bfloat16*)vn; a.ldvn = KV;
+    a.kc = (const __nv_bfloat16*)kc; a.ldkc = KV; a.vc = (const __nv_bfloat16*)vc; a.ldvc = KV;
+    a.out = (__nv_bfloat16*)out; a.ldo = A; a.lse = lse; a.anchors = anchors; a.keep = keep;
+    a.B = B; a.S = S; a.N = N; a.bs = bs; a.nh = nh; a.nkv = nkv; a.d = d; a.scale = 1.0f / sqrtf((float)d);
+    return a;
+}
+extern "C" int sf_dflash_attention_fwd(const void* q, const void* kn, const void* vn, const void* kc, const void* vc, void* out, float* lse,
+                                       const int32_t* anchors, const uint8_t* keep, int B, int S, int N, int bs, int nh, int nkv, int d,
+                                       int impl, void* stream) {
+    if (!q || !kn || !vn || !kc || !vc || !out || !lse || !anchors || !keep) return set_error(-22, "null argument");
+    const AttnArgs a = op_args(q, kn, vn, kc, vc, out, lse, anchors, keep, B, S, N, bs, nh, nkv, d);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (impl == 1) return attn_tc_supported(a) ? attn_fwd_tc(a, st) : set_error(-22, "dflash attention: shape not covered by the tcgen05 path");
+    if (impl == 0) { const int keepopt = opt(OPT_DFLASH_ATTN_TC); if (keepopt == 1) return set_error(-22, "unset dflash_attn_tc to force the CUDA-core kernels"); }
+    return attn_fwd(a, st);
+}
+extern "C" int sf_dflash_attention_bwd(const void* q, const void* kn, const void* vn, const void* kc, const void* vc, const void* out,
+                                       const float* lse, const void* dout, const int32_t* anchors, const uint8_t* keep, void* dq, void* dkn,
+                                       void* dvn, void* dkc, void* dvc, float* delta_ws, int B, int S, int N, int bs, int nh, int nkv, int d,
+                                       int impl, void* stream) {
+    if (!q || !kn || !vn || !kc || !vc || !out || !lse || !dout || !dq || !dkn || !dvn || !dkc || !dvc || !delta_ws) return set_error(-22, "null argument");
+    AttnArgs a = op_args(q, kn, vn, kc, vc, const_cast<void*>(out), const_cast<float*>(lse), anchors, keep, B, S, N, bs, nh, nkv, d);
+    const int64_t A = (int64_t)nh * d, KV = (int64_t)nkv * d;
+    a.dout = (const __nv_bfloat16*)dout; a.lddo = A; a.delta = delta_ws;
+    a.dq = (__nv_bfloat16*)dq; a.lddq = A; a.dkn = (__nv_bfloat16*)dkn; a.lddkn = KV; a.dvn = (__nv_bfloat16*)dvn; a.lddvn = KV;
+    a.dkc = (__nv_bfloat16*)dkc; a.lddkc = KV; a.dvc = (__nv_bfloat16*)dvc; a.lddvc = KV;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (impl == 1) return attn_tc_bwd_supported(a) ? attn_bwd_tc(a, st) : set_error(-22, "dflash attention: shape not covered by the tcgen05 path");
+    if (impl == 0 && opt(OPT_DFLASH_ATTN_TC) == 1) return set_error(-22, "unset dflash_attn_tc to force the CUDA-core kernels");
+    return attn_bwd(a, st);
+}
+

@@ -130,15 +130,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             }
         } else if (warp == 3 && lane == 0) {
             // ================= V producer =================
-            const int A = p.nh * D, KV = p.nkv * D;
             for (int t = 0; t < n_kv; ++t) {
                 const int s = t % C::kStages;
                 mbar_wait(b_vempty(s), ((t / C::kStages) & 1) ^ 1u, 12);
                 mbar_expect_tx(b_vfull(s), C::KV_BYTES);
                 for (int kb = 0; kb < C::NB; ++kb) {
                     const uint32_t dst = sbase + C::OFF_V + s * C::KV_BYTES + kb * (C::BKV * 128);
-                    if (t < n_ctx) tma_load_3d(dst, &tm_vc, b_vfull(s), KV + kvh * D + kb * 64, t * C::BKV, b);          // [k | v] rows
-                    else           tma_load_3d(dst, &tm_vn, b_vfull(s), A + KV + kvh * D + kb * 64, n0 * p.bs, b);      // [q | k | v] rows
+                    if (t < n_ctx) tma_load_3d(dst, &tm_vc, b_vfull(s), kvh * D + kb * 64, t * C::BKV, b);
+                    else           tma_load_3d(dst, &tm_vn, b_vfull(s), kvh * D + kb * 64, n0 * p.bs, b);
                 }
             }
         } else if ((warp == 1 || warp == 2) && lane == 0) {
@@ -303,14 +302,13 @@ static int fwd_tc_t(const AttnArgs& a, cudaStream_t st) {
     const int g = a.nh / a.nkv, R = g * a.bs;
     const int64_t Q = (int64_t)a.N * a.bs;
     CUtensorMap tq, tkc, tvc, tkn, tvn;
-    SF_TRY_RC(make_tmap_3d_bf16(&tq, a.q, a.ldq, Q, a.B, a.ldq, a.bs));
-    SF_TRY_RC(make_tmap_3d_bf16(&tkc, a.kc, a.ldkc, a.S, a.B, a.ldkc, C::BKV));
-    // the V operands are views into the fused projection rows: map the whole row, pick the head by column coordinate
-    const __nv_bfloat16* vc_row = a.vc - (int64_t)a.nkv * D;                         // [k | v] rows, ld = 2*KV
-    const __nv_bfloat16* vn_row = a.vn - ((int64_t)a.nh * D + (int64_t)a.nkv * D);   // [q | k | v] rows, ld = QKV
-    SF_TRY_RC(make_tmap_3d_bf16(&tvc, vc_row, a.ldvc, a.S, a.B, a.ldvc, C::BKV));
-    SF_TRY_RC(make_tmap_3d_bf16(&tkn, a.kn, a.ldkn, Q, a.B, a.ldkn, C::BKV));
-    SF_TRY_RC(make_tmap_3d_bf16(&tvn, vn_row, a.ldvn, Q, a.B, a.ldvn, C::BKV));
+    SF_TRY_RC(make_tmap_3d_bf16(&tq, a.q, (int64_t)a.nh * D, Q, a.B, a.ldq, a.bs));
+    SF_TRY_RC(make_tmap_3d_bf16(&tkc, a.kc, (int64_t)a.nkv * D, a.S, a.B, a.ldkc, C::BKV));
+    // V operands may be views into fused projection rows (row stride ld > nkv*D): the map covers the nkv*D columns of the view
+    const int64_t KVc = (int64_t)a.nkv * D;
+    SF_TRY_RC(make_tmap_3d_bf16(&tvc, a.vc, KVc, a.S, a.B, a.ldvc, C::BKV));
+    SF_TRY_RC(make_tmap_3d_bf16(&tkn, a.kn, KVc, Q, a.B, a.ldkn, C::BKV));
+    SF_TRY_RC(make_tmap_3d_bf16(&tvn, a.vn, KVc, Q, a.B, a.ldvn, C::BKV));
     TcParams p{};
     p.out = a.out; p.ldo = a.ldo; p.lse = a.lse; p.anchors = a.anchors; p.keep = a.keep;
     p.B = a.B; p.S = a.S; p.N = a.N; p.bs = a.bs; p.nh = a.nh; p.nkv = a.nkv; p.g = g;

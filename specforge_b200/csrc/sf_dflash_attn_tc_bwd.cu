@@ -124,15 +124,14 @@ df_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 }
             }
         } else if (warp == 3 && lane == 0) {
-            const int A = p.nh * D, KV = p.nkv * D;
             for (int t = 0; t < n_kv; ++t) {
                 const int sv = t % C::kVStages;
                 mbar_wait(b_vempty(sv), ((t / C::kVStages) & 1) ^ 1u, 42);
                 mbar_expect_tx(b_vfull(sv), C::KT_BYTES);
                 for (int kbk = 0; kbk < C::NB; ++kbk) {
                     const uint32_t dst = sbase + C::OFF_V + sv * C::KT_BYTES + kbk * (C::BKV * 128);
-                    if (t < n_ctx) tma_load_3d(dst, &tm_vc, b_vfull(sv), KV + kvh * D + kbk * 64, t * C::BKV, b);
-                    else           tma_load_3d(dst, &tm_vn, b_vfull(sv), A + KV + kvh * D + kbk * 64, n0 * p.bs, b);
+                    if (t < n_ctx) tma_load_3d(dst, &tm_vc, b_vfull(sv), kvh * D + kbk * 64, t * C::BKV, b);
+                    else           tma_load_3d(dst, &tm_vn, b_vfull(sv), kvh * D + kbk * 64, n0 * p.bs, b);
                 }
             }
         } else if (warp == 1 && lane == 0) {
@@ -359,11 +358,10 @@ df_bwd_ctx_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
         } else if (warp == 0 && lane == 0) {
             // ================= TMA producer =================
-            const int KV = p.nkv * D;
             mbar_expect_tx(b_kvfull, 2 * C::KT_BYTES);
             for (int kbk = 0; kbk < C::NB; ++kbk) {
                 tma_load_3d(sbase + C::OFF_K + kbk * (C::BK * 128), &tm_kc, b_kvfull, kvh * D + kbk * 64, k0, b);
-                tma_load_3d(sbase + C::OFF_V + kbk * (C::BK * 128), &tm_vc, b_kvfull, KV + kvh * D + kbk * 64, k0, b);
+                tma_load_3d(sbase + C::OFF_V + kbk * (C::BK * 128), &tm_vc, b_kvfull, kvh * D + kbk * 64, k0, b);
             }
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % C::kStages;
@@ -599,16 +597,15 @@ static int bwd_tc_t(const AttnArgs& a, cudaStream_t st) {
     const int g = a.nh / a.nkv, R = g * a.bs;
     const int64_t Q = (int64_t)a.N * a.bs, Mq = (int64_t)a.B * Q, A = (int64_t)a.nh * D;
     CUtensorMap tq, tdo, tkc64, tkc128, tvc64, tvc128, tkn, tvn;
-    const __nv_bfloat16* vc_row = a.vc - (int64_t)a.nkv * D;
-    const __nv_bfloat16* vn_row = a.vn - (A + (int64_t)a.nkv * D);
-    SF_TRY_RC(make_tmap_3d_bf16(&tq, a.q, a.ldq, Q, a.B, a.ldq, a.bs));
+    const int64_t KVc = (int64_t)a.nkv * D;      // maps cover the nkv*D columns of each (possibly strided) view
+    SF_TRY_RC(make_tmap_3d_bf16(&tq, a.q, A, Q, a.B, a.ldq, a.bs));
     SF_TRY_RC(make_tmap_3d_bf16(&tdo, a.dout, A, Q, a.B, a.lddo, a.bs));
-    SF_TRY_RC(make_tmap_3d_bf16(&tkc64, a.kc, a.ldkc, a.S, a.B, a.ldkc, 64));
-    SF_TRY_RC(make_tmap_3d_bf16(&tkc128, a.kc, a.ldkc, a.S, a.B, a.ldkc, 128));
-    SF_TRY_RC(make_tmap_3d_bf16(&tvc64, vc_row, a.ldvc, a.S, a.B, a.ldvc, 64));
-    SF_TRY_RC(make_tmap_3d_bf16(&tvc128, vc_row, a.ldvc, a.S, a.B, a.ldvc, 128));
-    SF_TRY_RC(make_tmap_3d_bf16(&tkn, a.kn, a.ldkn, Q, a.B, a.ldkn, 64));
-    SF_TRY_RC(make_tmap_3d_bf16(&tvn, vn_row, a.ldvn, Q, a.B, a.ldvn, 64));
+    SF_TRY_RC(make_tmap_3d_bf16(&tkc64, a.kc, KVc, a.S, a.B, a.ldkc, 64));
+    SF_TRY_RC(make_tmap_3d_bf16(&tkc128, a.kc, KVc, a.S, a.B, a.ldkc, 128));
+    SF_TRY_RC(make_tmap_3d_bf16(&tvc64, a.vc, KVc, a.S, a.B, a.ldvc, 64));
+    SF_TRY_RC(make_tmap_3d_bf16(&tvc128, a.vc, KVc, a.S, a.B, a.ldvc, 128));
+    SF_TRY_RC(make_tmap_3d_bf16(&tkn, a.kn, KVc, Q, a.B, a.ldkn, 64));
+    SF_TRY_RC(make_tmap_3d_bf16(&tvn, a.vn, KVc, Q, a.B, a.ldvn, 64));
     TcBwdParams p{};
     p.lse = a.lse; p.delta = a.delta; p.anchors = a.anchors; p.keep = a.keep;
     p.dq = a.dq; p.lddq = a.lddq; p.dkc = a.dkc; p.lddkc = a.lddkc; p.dvc = a.dvc; p.lddvc = a.lddvc;
