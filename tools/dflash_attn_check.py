@@ -25,12 +25,12 @@ def dense_reference(q, kn, vn, kc, vc, anchors, keep, B, S, N, bs, nh, nkv, d, d
     k = torch.cat([kcf.view(B, S, nkv, d), knf.view(B, Q, nkv, d)], dim=1).transpose(1, 2).repeat_interleave(g, dim=1)
     v = torch.cat([vcf.view(B, S, nkv, d), vnf.view(B, Q, nkv, d)], dim=1).transpose(1, 2).repeat_interleave(g, dim=1)
     s = (qh @ k.transpose(-1, -2)) * d ** -0.5
-    s = s.masked_fill(~mask.unsqueeze(1), float("-inf"))
-    p = torch.softmax(s, dim=-1)
-    p = torch.nan_to_num(p, nan=0.0)                                                                       # dropped blocks: zeros
+    row_ok = mask.any(dim=-1).unsqueeze(1).unsqueeze(-1)                                                   # dropped blocks see nothing
+    s = torch.where(row_ok, s.masked_fill(~mask.unsqueeze(1), float("-inf")), torch.zeros_like(s))         # (no NaNs in autograd)
+    p = torch.softmax(s, dim=-1) * row_ok
     o = (p @ v).transpose(1, 2).reshape(B * Q, nh * d)
     o.backward(dout.float())
-    lse = torch.logsumexp(s, dim=-1).transpose(1, 2).reshape(B * Q, nh)
+    lse = torch.logsumexp(s.masked_fill(~mask.unsqueeze(1), float("-inf")), dim=-1).transpose(1, 2).reshape(B * Q, nh)
     return o.detach(), lse.detach(), [t.grad for t in leaves]
 
 
@@ -66,7 +66,7 @@ def main():
     nh = nkv * a.g
     gen = torch.Generator().manual_seed(0)
     lm = (torch.rand(B, S, generator=gen) > 0.1).float()
-    lm[-1, S // 4:] = 0                                     # the last sequence has few candidates -> dropped blocks
+    lm[-1, max(4, N // 2):] = 0                              # the last sequence has fewer candidates than N -> dropped blocks
     anchors, keep = D.sample_anchor_positions(lm, N, generator=gen)
     N = anchors.shape[1]
     Mq, Mc = B * N * bs, B * S
