@@ -250,6 +250,8 @@ class ShardReader:
 
 
 class Eagle3ShardLoader:
+    RAW_KEYS = EAGLE3_KEYS
+    STRATEGY = "eagle3"
     """Iterates TrainBatches for the EAGLE3 offline strategy from SFPK shard(s).
 
     Batch contents follow the reference exactly: per sample `normalize_offline_sample` (first max_len tokens; target <-
@@ -274,8 +276,8 @@ class Eagle3ShardLoader:
         self._where: List[Tuple[int, int]] = [(i, r) for i, rd in enumerate(self.readers) for r in range(len(rd))]
         for rd in self.readers:
             names = {n for n, _, _ in rd.features}
-            if not set(EAGLE3_KEYS) <= names:
-                raise KeyError(f"{rd.path}: shard lacks EAGLE3 features {sorted(set(EAGLE3_KEYS) - names)}")
+            if not set(self.RAW_KEYS) <= names:
+                raise KeyError(f"{rd.path}: shard lacks features {sorted(set(self.RAW_KEYS) - names)}")
 
     def set_epoch(self, epoch: int) -> None:
         self.epoch = epoch
@@ -302,19 +304,25 @@ class Eagle3ShardLoader:
             (ri, _), = by_reader.items()
             slot = self._ring[self._ring_pos]
             self._ring_pos = (self._ring_pos + 1) % len(self._ring)
-            raw = self.readers[ri].read_batch([self._where[gi][1] for gi in sample_indices], self.max_len, S, EAGLE3_KEYS,
+            raw = self.readers[ri].read_batch([self._where[gi][1] for gi in sample_indices], self.max_len, S, self.RAW_KEYS,
                                               self.pin, self.threads, out=slot)
             slot.update(raw)
         else:                                        # a batch straddling shards: gather per shard, then place the rows
             raw = {}
             for ri, poss in by_reader.items():
-                part = self.readers[ri].read_batch([self._where[sample_indices[p]][1] for p in poss], self.max_len, S, EAGLE3_KEYS,
+                part = self.readers[ri].read_batch([self._where[sample_indices[p]][1] for p in poss], self.max_len, S, self.RAW_KEYS,
                                                    False, self.threads)
                 for k, v in part.items():
                     if k not in raw:
                         raw[k] = torch.empty((B,) + tuple(v.shape[1:]), dtype=v.dtype, pin_memory=self.pin and torch.cuda.is_available())
                     raw[k][poss] = v
-        lens_t = torch.tensor(lens, dtype=torch.int64)
+        ids = [f"{self.run_id}:{gi:08d}" for gi in sample_indices]
+        tensors, metadata = self._finish(raw, torch.tensor(lens, dtype=torch.int64), S)
+        return TrainBatch(sample_ids=ids, strategy=self.STRATEGY, tensors=tensors, metadata=metadata)
+
+    def _finish(self, raw: Dict[str, torch.Tensor], lens_t: torch.Tensor, S: int):
+        """Per-sample normalisation left after the gather (algorithms/eagle3/data.py:10-27): rename, attention mask of ones
+        over each sample's tokens, last kept loss-mask position zeroed."""
         pos = torch.arange(S, dtype=torch.int64).unsqueeze(0)
         attention_mask = (pos < lens_t.unsqueeze(1)).to(torch.int64)
         loss_mask = raw["loss_mask"]
@@ -323,8 +331,7 @@ class Eagle3ShardLoader:
             loss_mask[live.nonzero().squeeze(1), (lens_t[live] - 1)] = 0
         tensors = {"input_ids": raw["input_ids"], "attention_mask": attention_mask, "loss_mask": loss_mask,
                    "hidden_state": raw["aux_hidden_state"], "target": raw["hidden_state"]}
-        ids = [f"{self.run_id}:{gi:08d}" for gi in sample_indices]
-        return TrainBatch(sample_ids=ids, strategy="eagle3", tensors=tensors, metadata={"target_repr": "hidden_state"})
+        return tensors, {"target_repr": "hidden_state"}
 
     def _batches(self) -> Iterator[TrainBatch]:
         order = self._order()
@@ -373,6 +380,25 @@ class Eagle3ShardLoader:
         finally:
             stop.set()
             t.join(timeout=5)
+
+
+DFLASH_KEYS = ("input_ids", "loss_mask", "hidden_states")
+
+
+class DFlashShardLoader(Eagle3ShardLoader):
+    """TrainBatches for the DFlash-family offline strategy: `normalize_offline_sample` (first max_len tokens of input_ids /
+    loss_mask / hidden_states, no renaming, a sample without two consecutive supervised tokens is an error,
+    algorithms/common/dflash_family_data.py:37-70) + `pad_and_concatenate_features` (zero padding to the longest sample,
+    algorithms/common/collation.py:24-70)."""
+    RAW_KEYS = DFLASH_KEYS
+    STRATEGY = "dflash"
+
+    def _finish(self, raw: Dict[str, torch.Tensor], lens_t: torch.Tensor, S: int):
+        lm = raw["loss_mask"]
+        ok = ((lm[:, :-1] > 0) & (lm[:, 1:] > 0)).any(dim=1) if S > 1 else torch.zeros(lm.shape[0], dtype=torch.bool)
+        if not bool(ok.all()):
+            raise ValueError("offline DFlash-family samples require two consecutive supervised tokens")
+        return {"input_ids": raw["input_ids"], "loss_mask": lm, "hidden_states": raw["hidden_states"]}, {}
 
 
 def _main(argv: Optional[Sequence[str]] = None) -> int:

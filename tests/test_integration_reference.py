@@ -90,3 +90,27 @@ def test_dflash_registry_binding_and_state_dict_contract(ref, monkeypatch):
     assert ours.state_dict_spec() == ref_sd
     assert ours.block_size == 16 and ours.mask_token_id == 151669 and list(ours.target_layer_ids) == [1, 9, 17, 25, 33]
     assert ours.dims.num_target_feats == 5 and ours.dims.num_layers == 5
+
+
+def test_dflash_shard_batches_equal_the_reference_input_pipe(ref, tmp_path):
+    """DFlash-family offline pipe: SFPK batches == the reference's normalize_offline_sample + build_collator() on the same
+    files (algorithms/common/dflash_family_data.py); also pins the oracle restatement."""
+    import torch
+    from specforge.algorithms.common.dflash_family_data import build_collator, normalize_offline_sample
+    from specforge.runtime.data_plane.feature_store import load_feature_file
+    from oracle import offline_feed_oracle as FO
+    from specforge_b200.shards import DFLASH_KEYS, DFlashShardLoader, list_feature_files, pack_offline_dir
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_shards import _write_dflash_files
+    _write_dflash_files(str(tmp_path / "feat"), [30, 7, 52, 19, 40, 33], seed=6)
+    files = list_feature_files(str(tmp_path / "feat"))
+    (shard,) = pack_offline_dir(str(tmp_path / "feat"), str(tmp_path / "d.sfpk"), keys=DFLASH_KEYS)
+    collate = build_collator()
+    same = lambda a, b: torch.equal(a.view(torch.int16), b.view(torch.int16)) if a.dtype == torch.bfloat16 else torch.equal(a, b)
+    for bi, batch in enumerate(DFlashShardLoader([shard], batch_size=3, max_len=36)):
+        raws = [load_feature_file(p) for p in files[3 * bi:3 * bi + 3]]
+        want = collate([normalize_offline_sample(r, 36) for r in raws])
+        mine = FO.pad_and_concatenate([FO.normalize_offline_dflash_sample(r, 36) for r in raws])
+        for k in ("input_ids", "loss_mask", "hidden_states"):
+            assert batch.tensors[k].shape == want[k].shape and batch.tensors[k].dtype == want[k].dtype, k
+            assert same(batch.tensors[k], want[k]) and same(mine[k], want[k]), k

@@ -130,3 +130,41 @@ def test_pack_and_info_cli(tmp_path, capsys):
     assert _main(["info", str(tmp_path / "x.sfpk"), "--verify"]) == 0
     out = capsys.readouterr().out
     assert "3 records" in out and "aux_hidden_state" in out and "all records ok" in out
+
+
+def _write_dflash_files(root, lengths, W=24, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    recs = []
+    os.makedirs(os.path.join(root, "rows_0-2000"), exist_ok=True)
+    for i, L in enumerate(lengths):
+        lm = (torch.rand(L, generator=g) > 0.3).long()
+        lm[:2] = 1                                                   # two consecutive supervised tokens in every sample
+        hs = torch.randn(L, W, generator=g).bfloat16()
+        rec = {"input_ids": torch.randint(0, 1000, (L,), generator=g), "loss_mask": lm,
+               "hidden_states": hs if i % 2 else hs.unsqueeze(0)}     # both stored layouts ([seq, W] and [1, seq, W])
+        torch.save(rec, os.path.join(root, "rows_0-2000", f"data_{i}.ckpt"))
+        recs.append(rec)
+    return recs
+
+
+def test_dflash_batches_equal_reference_normalise_and_collate(tmp_path):
+    from specforge_b200.shards import DFLASH_KEYS, DFlashShardLoader, pack_offline_dir
+    lengths = [30, 7, 52, 19, 40, 33]
+    recs = _write_dflash_files(str(tmp_path / "feat"), lengths, seed=4)
+    order = _ref_order(str(tmp_path / "feat"))
+    (shard,) = pack_offline_dir(str(tmp_path / "feat"), str(tmp_path / "d.sfpk"), keys=DFLASH_KEYS)
+    for bi, batch in enumerate(DFlashShardLoader([shard], batch_size=3, max_len=36)):
+        srcs = order[3 * bi:3 * bi + 3]
+        want = FO.pad_and_concatenate([FO.normalize_offline_dflash_sample(recs[s], 36) for s in srcs])
+        assert batch.strategy == "dflash" and set(batch.tensors) == set(want)
+        for k, w in want.items():
+            g = batch.tensors[k]
+            assert g.dtype == w.dtype and g.shape == w.shape, k
+            assert torch.equal(g.view(torch.int16) if g.dtype == torch.bfloat16 else g, w.view(torch.int16) if w.dtype == torch.bfloat16 else w), k
+    # a sample without two consecutive supervised tokens is refused, like the reference normaliser does
+    bad = dict(recs[0]); bad["loss_mask"] = torch.zeros_like(bad["loss_mask"]); bad["loss_mask"][::2] = 1
+    os.makedirs(str(tmp_path / "bad" / "rows_0-2000"))
+    torch.save(bad, str(tmp_path / "bad" / "rows_0-2000" / "data_0.ckpt"))
+    (bshard,) = pack_offline_dir(str(tmp_path / "bad"), str(tmp_path / "b.sfpk"), keys=DFLASH_KEYS)
+    with pytest.raises(ValueError):
+        next(iter(DFlashShardLoader([bshard], batch_size=1, max_len=36, prefetch=0)))
