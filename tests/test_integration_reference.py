@@ -114,3 +114,20 @@ def test_dflash_shard_batches_equal_the_reference_input_pipe(ref, tmp_path):
         for k in ("input_ids", "loss_mask", "hidden_states"):
             assert batch.tensors[k].shape == want[k].shape and batch.tensors[k].dtype == want[k].dtype, k
             assert same(batch.tensors[k], want[k]) and same(mine[k], want[k]), k
+
+
+def test_checkpoint_keys_satisfy_the_reference_sglang_exporter(ref):
+    """What `backend.state_dict()["model"]` holds (reference-named draft weights, embedding dropped by
+    checkpoint_state_filter) passes the exporter's serving-key validation (export/to_sglang.py:37-53)."""
+    import torch
+    from specforge.export.to_sglang import WEIGHT_MAPS, _serving_state
+    from specforge_b200.draft import B200Eagle3DraftModel
+    cfg = dict(hidden_size=256, intermediate_size=512, num_attention_heads=4, num_key_value_heads=2, head_dim=64, vocab_size=1024,
+               draft_vocab_size=256, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=512)
+    spec = B200Eagle3DraftModel(cfg).state_dict_spec()
+    trainer_side = {"draft_model." + k: torch.empty(0) for k in spec}                       # what the trainable module's state_dict carries
+    kept = {k.replace("draft_model.", ""): v for k, v in trainer_side.items() if "embed" not in k.lower()}   # checkpoint_state_filter
+    out = _serving_state(kept, WEIGHT_MAPS["LlamaForCausalLMEagle3"])
+    assert {"fc.weight", "norm.weight", "lm_head.weight", "t2d", "d2t"} <= set(out) and "embed_tokens.weight" not in out
+    with pytest.raises(ValueError):
+        _serving_state(trainer_side, {})                                                       # unfiltered keys are refused
