@@ -527,7 +527,7 @@ def run_dflash(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "BASELINE config 4 per GPU: Qwen3-8B DFlash draft step (fwd + loss + bwd + grad all-reduce + clip/AdamW)",
                        "batch_per_gpu": Bd, "global_batch": world * Bd, "seq_len": Sd, "block_size": bs, "num_anchors": Nd,
-                       "parallelism": f"dp{world}", "l2": "inputs_exceed_l2", "attention": "tcgen05" if os.environ.get("SF_DFLASH_ATTN_TC") == "1" else "cuda-core (first correct version)"},
+                       "parallelism": f"dp{world}", "l2": "inputs_exceed_l2", "attention": "cuda-core (A/B baseline)" if os.environ.get("SF_DFLASH_ATTN_TC") == "-1" else "tcgen05"},
             "e2e": {"value": world * Bd / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e, "last_loss": last_loss},
             "gpu_launches": launches, "clocks": clocks,

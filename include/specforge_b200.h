@@ -33,7 +33,8 @@ extern "C" {
 const char* sf_version(void);
 const char* sf_last_error(void);
 /* Tuning / A-B switch by name ("no_pdl", "loss_side", "no_overlap", "no_swiglu_fusion", "gemm_group_m",
- * "gemm_group_m_midk", "gemm_group_m_wgrad", "dflash_attn_tc"); each defaults to its SF_<NAME> environment variable.  Diagnostic only. */
+ * "gemm_group_m_midk", "gemm_group_m_wgrad", "dflash_attn_tc" (-1: CUDA-core DFlash attention instead of tcgen05)); each defaults to
+ * its SF_<NAME> environment variable.  Diagnostic only. */
 int sf_debug_option(const char* name, int value);
 long long sf_launch_count(void);      /* kernels launched by this library since the last reset */
 void sf_launch_count_reset(void);
@@ -225,7 +226,7 @@ int sf_dflash_backward(const sf_dflash_config* cfg, const void* params_flat, con
                        int accumulate, void* stream);
 
 /* The DFlash block attention alone (contiguous [rows, heads*d] bf16 tensors; q/kn/vn/out/dq/dkn/dvn have B*N*bs rows, kc/vc/dkc/dvc
- * B*S rows; lse / delta_ws are [B*N*bs, nh] fp32).  impl: 0 = CUDA-core tiles, 1 = tcgen05 (experimental), -1 = the step's choice.
+ * B*S rows; lse / delta_ws are [B*N*bs, nh] fp32).  impl: 0 = CUDA-core tiles, 1 = tcgen05, -1 = the step's choice (tcgen05 where the shape is covered).
  * Reference semantics: dflash_family_model.py:47-89 (mask) + dflash.py:185-213 (attention, dropped blocks give zeros). */
 int sf_dflash_attention_fwd(const void* q, const void* kn, const void* vn, const void* kc, const void* vc, void* out, float* lse,
                             const int32_t* anchors, const uint8_t* keep, int B, int S, int N, int bs, int nh, int nkv, int d,

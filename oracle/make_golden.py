@@ -63,7 +63,33 @@ CASES = {
     "qwen25_05b_cfg1": (dict(hidden_size=896, intermediate_size=4864, num_heads=14, num_kv_heads=2, head_dim=64,
                              vocab_size=151936, draft_vocab_size=16000, rms_norm_eps=1e-6, rope_theta=1000000.0,
                              max_position_embeddings=32768, ttt_length=3), 1, 128, 0, None),
+    # ---- full model dims of the BASELINE configs at B=1 (the sizes the headline numbers are quoted on; minutes on CPU).
+    # head_std = 1/sqrt(H_t): teacher logits ~ N(0, 1), i.e. a broad soft-label distribution instead of a one-hot.
+    # BASELINE config 2: Qwen3-8B draft (configs/qwen3-8b-eagle3.json), S=2048, TTT=7
+    "qwen3_8b_cfg2_b1": (dict(hidden_size=4096, intermediate_size=12288, num_heads=32, num_kv_heads=8, head_dim=128,
+                              vocab_size=151936, draft_vocab_size=32000, rms_norm_eps=1e-6, rope_theta=1000000.0,
+                              max_position_embeddings=40960, ttt_length=7), 1, 2048, 0, None, dict(head_std=1.0 / 64)),
+    # BASELINE config 3: Llama3-8B draft (configs/llama3-8B-eagle3.json: I=14336, V=128256, eps 1e-5, default theta,
+    # max_position_embeddings=2048 -> S+T rows fit in the initial 2068-row RoPE cache), padded batch
+    "llama3_8b_cfg3_b1": (dict(hidden_size=4096, intermediate_size=14336, num_heads=32, num_kv_heads=8, head_dim=128,
+                               vocab_size=128256, draft_vocab_size=32000, rms_norm_eps=1e-5, rope_theta=10000.0,
+                               max_position_embeddings=2048, ttt_length=7), 1, 2048, 129, None, dict(head_std=1.0 / 64)),
+    # BASELINE config 5: Qwen3-30B-A3B EAGLE3.1 draft (configs/qwen3-30B-A3B-eagle3.1.json: H=2048, nkv=4, fc_norm),
+    # S=4096; max_position_embeddings raised from 2048 to 8192 on BOTH sides (the reference
+    # rebuilds its RoPE cache from a bf16 arange past max_position_embeddings+20, which is garbage we do not reproduce)
+    "qwen3_30b_a3b_cfg5_b1": (dict(hidden_size=2048, intermediate_size=12288, num_heads=32, num_kv_heads=4, head_dim=128,
+                                   vocab_size=151936, draft_vocab_size=32000, rms_norm_eps=1e-6, rope_theta=1000000.0,
+                                   max_position_embeddings=8192, ttt_length=7, fc_norm=True), 1, 4096, 0, None,
+                              dict(head_std=2048 ** -0.5)),
 }
+
+
+def logits_sample_index(S: int, DV: int):
+    """Rows / columns of the per-step logits kept in the big goldens: 12 rows (start, middle, end of the sequence) x
+    (first 512 columns + every 61st column)."""
+    rows = list(range(0, 4)) + list(range(S // 2, S // 2 + 4)) + list(range(S - 4, S))
+    cols = list(range(0, min(512, DV))) + list(range(512, DV, 61))
+    return torch.tensor(rows), torch.tensor(cols)
 
 
 def build_reference(cfg: O.Eagle3Config, P, t2d, d2t, head_w, lk_loss_type, workdir):
@@ -123,13 +149,15 @@ def run_case(name):
     from specforge.optimizer import BF16Optimizer
     from specforge.runtime.contracts import TrainBatch
 
-    kw, B, S, pad_tail, lk = CASES[name]
+    kw, B, S, pad_tail, lk = CASES[name][:5]
+    extra = CASES[name][5] if len(CASES[name]) > 5 else {}
+    head_std = float(extra.get("head_std", 1.0))
     cfg = O.Eagle3Config(**kw)
     torch.manual_seed(0)
     P = O.init_params(cfg, seed=0)
     t2d, d2t = O.make_vocab_map(cfg.vocab_size, cfg.draft_vocab_size, seed=0)
     g = torch.Generator().manual_seed(1234)
-    head_w = torch.randn(cfg.vocab_size, cfg.target_hidden_size, generator=g).to(torch.bfloat16)
+    head_w = (torch.randn(cfg.vocab_size, cfg.target_hidden_size, generator=g) * head_std).to(torch.bfloat16)
     batch = O.make_batch(cfg, B, S, seed=0, pad_tail=pad_tail)
     with tempfile.TemporaryDirectory() as wd:
         draft, model, strategy = build_reference(cfg, P, t2d, d2t, head_w, lk, wd)
@@ -148,7 +176,7 @@ def run_case(name):
         new_w = {n: p.detach().clone() for n, p in draft.named_parameters() if p.requires_grad}
     big = cfg.hidden_size > 256
     gold = {
-        "case": name, "cfg": kw, "B": B, "S": S, "pad_tail": pad_tail, "lk_loss_type": lk, "head_seed": 1234,
+        "case": name, "cfg": kw, "B": B, "S": S, "pad_tail": pad_tail, "lk_loss_type": lk, "head_seed": 1234, "head_std": head_std,
         "loss": out.loss.detach().float(),
         "plosses": torch.stack([p.float() for p in out.metrics["plosses"]]),
         "acces": torch.stack([a.float() for a in out.metrics["acces"]]),
@@ -158,6 +186,10 @@ def run_case(name):
         "logits_slice": torch.stack([l[:, :8, :64] for l in logits_seen]),
         "grad_norm": gnorm.float(), "lr_used": lr_used,
     }
+    if cfg.hidden_size >= 2048:   # full-size cases: a spread sample of every step's logits [T, B, rows, cols]
+        ri, ci = logits_sample_index(S, cfg.draft_vocab_size)
+        gold["logits_rows"], gold["logits_cols"] = ri, ci
+        gold["logits_sample"] = torch.stack([l[:, ri][:, :, ci] for l in logits_seen])
     if big:
         gold["grad_stats"] = {n: torch.stack([g_.float().norm(), g_.float().abs().max(), g_.float().flatten()[:16].norm()])
                               for n, g_ in grads.items()}

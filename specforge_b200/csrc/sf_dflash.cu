@@ -336,8 +336,7 @@ extern "C" int sf_dflash_attention_fwd(const void* q, const void* kn, const void
     const AttnArgs a = op_args(q, kn, vn, kc, vc, out, lse, anchors, keep, B, S, N, bs, nh, nkv, d);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (impl == 1) return attn_tc_supported(a) ? attn_fwd_tc(a, st) : set_error(-22, "dflash attention: shape not covered by the tcgen05 path");
-    if (impl == 0) { const int keepopt = opt(OPT_DFLASH_ATTN_TC); if (keepopt == 1) return set_error(-22, "unset dflash_attn_tc to force the CUDA-core kernels"); }
-    return attn_fwd(a, st);
+    return impl == 0 ? attn_fwd_cc(a, st) : attn_fwd(a, st);
 }
 extern "C" int sf_dflash_attention_bwd(const void* q, const void* kn, const void* vn, const void* kc, const void* vc, const void* out,
                                        const float* lse, const void* dout, const int32_t* anchors, const uint8_t* keep, void* dq, void* dkn,
@@ -351,7 +350,6 @@ extern "C" int sf_dflash_attention_bwd(const void* q, const void* kn, const void
     a.dkc = (__nv_bfloat16*)dkc; a.lddkc = KV; a.dvc = (__nv_bfloat16*)dvc; a.lddvc = KV;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (impl == 1) return attn_tc_bwd_supported(a) ? attn_bwd_tc(a, st) : set_error(-22, "dflash attention: shape not covered by the tcgen05 path");
-    if (impl == 0 && opt(OPT_DFLASH_ATTN_TC) == 1) return set_error(-22, "unset dflash_attn_tc to force the CUDA-core kernels");
-    return attn_bwd(a, st);
+    return impl == 0 ? attn_bwd_cc(a, st) : attn_bwd(a, st);
 }
 

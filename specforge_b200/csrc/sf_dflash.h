@@ -37,10 +37,12 @@ int headnorm_rope_fwd(const void* x, int64_t ldx, int n_heads, int d, const void
 int headnorm_rope_bwd(const void* x, int64_t ldx, int n_heads, int d, const void* w, const void* cos_t, const void* sin_t,
                       const int32_t* pos, int S, float eps, const void* g, int64_t ldg, void* dx, int64_t lddx, float* dw,
                       int accumulate, float* partial_ws, int64_t M, cudaStream_t st);
-int attn_fwd(const AttnArgs& a, cudaStream_t st);
-bool attn_tc_supported(const AttnArgs& a);          // sf_dflash_attn_tc.cu (experimental, off by default)
+int attn_fwd(const AttnArgs& a, cudaStream_t st);       // dispatch: tcgen05 where supported, else CUDA cores
+int attn_fwd_cc(const AttnArgs& a, cudaStream_t st);    // CUDA-core tiles (sf_dflash_kernels.cu)
+int attn_bwd_cc(const AttnArgs& a, cudaStream_t st);
+bool attn_tc_supported(const AttnArgs& a);          // sf_dflash_attn_tc.cu (default where the shape is covered)
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t st);
-bool attn_tc_bwd_supported(const AttnArgs& a);      // sf_dflash_attn_tc_bwd.cu (experimental, off by default)
+bool attn_tc_bwd_supported(const AttnArgs& a);      // sf_dflash_attn_tc_bwd.cu (default where the shape is covered)
 int attn_bwd_tc(const AttnArgs& a, cudaStream_t st);
 int attn_bwd(const AttnArgs& a, cudaStream_t st);
 int ce(void* logits, int64_t ld, int V, const int32_t* tgt, const float* w, const float* lw, float* sums, int write_grad,

@@ -1,9 +1,9 @@
 // sf_dflash_attn_tc.cu — DFlash block attention on tcgen05 / TMEM / TMA, forward.
 //
-// STATUS: written at the end of round 1 WITHOUT GPU time left to run it.  It is compiled into the library but only reached
-// when sf_debug_option("dflash_attn_tc", 1) (or SF_DFLASH_ATTN_TC=1) is set; the default DFlash path keeps the CUDA-core
-// kernels of sf_dflash_kernels.cu, which are the ones that passed parity.  First job of the next round: switch it on under
-// tests/test_dflash_gpu.py (goldens tests/golden/dflashtc_*.pt have the shapes it supports) and debug.
+// STATUS: default DFlash attention wherever attn_tc_supported() covers the shape (round 2: first run on a B200 matched the
+// dense fp32 reference and the CUDA-core kernels at d = 64 / 128, with dropped blocks, S up to 1100 — profiles/
+// r02_dflash_attn_tc_check.txt; goldens tests/golden/dflashtc_*.pt).  sf_debug_option("dflash_attn_tc", -1) or
+// SF_DFLASH_ATTN_TC=-1 falls back to the CUDA-core kernels of sf_dflash_kernels.cu for A/B runs.
 //
 // Derived from attn_fwd_tc_kernel (sf_attention_tc.cu) — same warp roles, rings, TMEM plan and lazy-rescale softmax.
 // What changes is the tiling of the problem.  A DFlash query row (block n, slot o, head h) may see the context keys

@@ -1,8 +1,7 @@
 // sf_dflash_attn_tc_bwd.cu — DFlash block attention backward on tcgen05 / TMEM / TMA.
 //
-// STATUS: like sf_dflash_attn_tc.cu this was written after the round's GPU budget was spent; it compiles, is only reached
-// with sf_debug_option("dflash_attn_tc", 1), and has NOT been executed yet.  tests/test_dflash_gpu.py::test_dflash_tc_shapes
-// (SF_DFLASH_TC_TESTS=1) is its parity check.
+// STATUS: default together with sf_dflash_attn_tc.cu (same evidence: profiles/r02_dflash_attn_tc_check.txt and
+// tests/test_dflash_gpu.py::test_dflash_tc_shapes).
 //
 // Derived from attn_bwd_dq_tc_kernel / attn_bwd_dkv_tc_kernel (sf_attention_tc_bwd.cu): same warp roles, rings, TMEM plans.
 //   df_bwd_dq_tc   CTA = one unit (128 query rows = 128/R anchor blocks x g heads x bs slots), kv head, sequence.

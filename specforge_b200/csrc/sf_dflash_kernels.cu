@@ -551,8 +551,17 @@ static int attn_check(const AttnArgs& a) {
     if ((a.d + 256 / R - 1) / (256 / R) > kMaxCols) return set_error(-22, "dflash attention: head_dim %d too large for %d rows", a.d, R);
     return 0;
 }
+// The tcgen05 kernels (sf_dflash_attn_tc*.cu) are the default wherever their tiling covers the shape; the CUDA-core kernels
+// below remain for the other shapes and as the A/B baseline (sf_debug_option("dflash_attn_tc", -1) / SF_DFLASH_ATTN_TC=-1).
 int attn_fwd(const AttnArgs& a, cudaStream_t st) {
-    if (opt(OPT_DFLASH_ATTN_TC) == 1 && attn_tc_supported(a)) return attn_fwd_tc(a, st);   // experimental tcgen05 path
+    if (opt(OPT_DFLASH_ATTN_TC) >= 0 && attn_tc_supported(a)) return attn_fwd_tc(a, st);
+    return attn_fwd_cc(a, st);
+}
+int attn_bwd(const AttnArgs& a, cudaStream_t st) {
+    if (opt(OPT_DFLASH_ATTN_TC) >= 0 && attn_tc_bwd_supported(a)) return attn_bwd_tc(a, st);
+    return attn_bwd_cc(a, st);
+}
+int attn_fwd_cc(const AttnArgs& a, cudaStream_t st) {
     if (int rc = attn_check(a)) return rc;
     const int R = (a.nh / a.nkv) * a.bs;
     const int smem = (int)attn_smem_fwd(R, a.d);
@@ -562,8 +571,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
     SF_CUDA_CHECK_LAUNCH("dflash attn_fwd");
     return 0;
 }
-int attn_bwd(const AttnArgs& a, cudaStream_t st) {
-    if (opt(OPT_DFLASH_ATTN_TC) == 1 && attn_tc_bwd_supported(a)) return attn_bwd_tc(a, st);   // experimental tcgen05 path
+int attn_bwd_cc(const AttnArgs& a, cudaStream_t st) {
     if (int rc = attn_check(a)) return rc;
     const int R = (a.nh / a.nkv) * a.bs;
     const int smem = (int)attn_smem_bwd(R, a.d);
