@@ -106,6 +106,12 @@ int sf_eagle3_forward(const sf_eagle3_config* cfg, const void* params_flat, cons
                       const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float* metrics,
                       float* loss, int need_grad, void* stream);
 
+/* Location of a named tensor of the last step inside the workspace: "h" bf16 [T+1, M, H], "qkv" bf16 [T, M, (nh+2nkv)d] (after
+ * RoPE), "attn" bf16 [T, M, nh*d], "hf" bf16 [T, M, H], "logits" bf16 [T, M, DV] (the logits after need_grad=0, d(loss)/d(logits)
+ * after need_grad=1), "teacher_xg" bf16 [B, S+T, DV], "teacher_stats" f32 [B, S+T, 4], "teacher_ids" i64 [B, S+T],
+ * "position_mask" i32 [B, S].  For parity tests (logits vs the reference's lm_head output) and forward-only inspection. */
+int sf_eagle3_workspace_view(const sf_eagle3_config* cfg, const char* name, int64_t* offset_bytes, int64_t* size_bytes);
+
 /* Full backward of the step just run by sf_eagle3_forward(need_grad=1) on the same workspace.
  * grads_flat_f32 (+)= loss_scale * dLoss/dParams  (accumulate != 0 adds into the buffer). */
 int sf_eagle3_backward(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,

@@ -459,6 +459,28 @@ extern "C" size_t sf_eagle3_workspace_bytes(const sf_eagle3_config* cfg) {
     if (!cfg || validate(*cfg)) return 0;
     return (size_t)make_plan(*cfg).total;
 }
+// Where a named tensor of the last step lives inside the caller's workspace (parity tests, forward-only draft-model methods).
+extern "C" int sf_eagle3_workspace_view(const sf_eagle3_config* cfg, const char* name, int64_t* offset_bytes, int64_t* size_bytes) {
+    if (!cfg || !name || !offset_bytes || !size_bytes) return set_error(-22, "null argument");
+    SF_TRY(validate(*cfg));
+    const Plan p = make_plan(*cfg);
+    const Dims x = dims_of(*cfg);
+    const int64_t T = x.T, M = x.M, PR = (int64_t)x.B * (x.S + T);
+    struct Ent { const char* n; int64_t off, bytes; } tab[] = {
+        {"h", p.h, (T + 1) * M * x.H * 2},            // bf16 [T+1, M, H]   h_0 = fc output, h_{j+1} = step j output
+        {"qkv", p.qkv, T * M * x.QKV * 2},            // bf16 [T, M, (nh+2nkv)*d]  after RoPE
+        {"attn", p.attn, T * M * x.A * 2},            // bf16 [T, M, nh*d]
+        {"hf", p.hf, T * M * x.H * 2},                // bf16 [T, M, H]     norm(h_{j+1}) (aliases h[1:] when !norm_output)
+        {"logits", p.logits, T * M * x.DV * 2},       // bf16 [T, M, DV]    logits after forward(need_grad=0); d(loss)/d(logits) after need_grad=1
+        {"teacher_xg", p.xg, PR * x.DV * 2},          // bf16 [B, S+T, DV]  gathered teacher logits
+        {"teacher_stats", p.tstats, PR * 16},         // f32  [B, S+T, 4]   {md, 1/dd, cs, 0}
+        {"teacher_ids", p.ids, PR * 8},               // i64  [B, S+T]      argmax of the full-vocab teacher logits
+        {"position_mask", p.pos_mask, M * 4},         // i32  [B, S]
+    };
+    for (const Ent& e : tab)
+        if (!strcmp(e.n, name)) { *offset_bytes = e.off; *size_bytes = e.bytes; return 0; }
+    return set_error(-22, "workspace view '%s' unknown", name);
+}
 extern "C" int sf_eagle3_forward(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,
                                  const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float* metrics,
                                  float* loss, int need_grad, void* stream) {
