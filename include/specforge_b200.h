@@ -144,6 +144,12 @@ int sf_optimizer_step(const void* grads_bf16, float* master, float* exp_avg, flo
  * epi: 0 bf16, 1 bf16 + residual R, 2 fp32, 3 fp32 accumulate; cta_group: 0 auto, 1, 2. */
 int sf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D, int64_t ldd,
                  const void* R, int64_t ldr, int M, int N, int K, int epi, int cta_group, void* stream);
+/* Same with the fused-SwiGLU epilogues (llama3_eagle.py:1547): epi 4 — B = [gate ; up] weight [2*n_half, K], D = gu [M, 2*n_half]
+ * (bf16 gate | up, kept for backward), D2 = act [M, n_half] = bf16(bf16(silu(gate)) * up), N = 2*n_half, n_half % 128 == 0, M > 128;
+ * epi 5 — acc = d(act) [M, n_half], R = gu [M, 2*n_half], D = d(gu) [M, 2*n_half], N = n_half. */
+int sf_gemm_bf16_ex(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D, int64_t ldd,
+                    const void* R, int64_t ldr, void* D2, int64_t ldd2, int n_half, int M, int N, int K, int epi, int cta_group,
+                    void* stream);
 int sf_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* out, int64_t ldo, int64_t M, int H, float eps,
                    void* stream);
 /* dw (+)= column sums via per-block partials in `scratch` (sf_rmsnorm_bwd_scratch_bytes(H) bytes): deterministic. */

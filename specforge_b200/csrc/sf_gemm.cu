@@ -84,6 +84,10 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     // weight-gradient GEMMs (K = T*M) cannot keep an A panel in L2 at all and want the squarest wave (8 x 9 tiles).
     const int gm = opt(OPT_GEMM_GROUP_M), gmk = opt(OPT_GEMM_GROUP_M_MIDK), gmw = opt(OPT_GEMM_GROUP_M_WGRAD);
     p.group_m = g.K > 32768 ? (gmw > 0 ? gmw : 8) : g.K > 4608 ? (gmk > 0 ? gmk : 16) : (gm > 0 ? gm : 16);
+    p.stages = opt(OPT_GEMM_STAGES) > 0 ? opt(OPT_GEMM_STAGES) : Cfg::kStages;
+    if (p.stages < 2) p.stages = 2;
+    if (p.stages > Cfg::kMaxStages) p.stages = Cfg::kMaxStages;
+    const int smem_bytes = Cfg::smem_bytes(p.stages);
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int clusters = num_sms() / G;
     if (tiles < clusters) clusters = tiles;
@@ -91,14 +95,14 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     auto kern = gemm_kernel<G, AM, BM, BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(Cfg::kMaxStages));
         if (e != cudaSuccess) return set_error(-22, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * G);
     cfg.blockDim = dim3(Cfg::kThreads);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -184,5 +188,16 @@ extern "C" int sf_gemm_bf16(const void* A, int64_t lda, int a_major, const void*
     sf::GemmDesc g;
     g.A = A; g.lda = lda; g.a_major = a_major; g.B = B; g.ldb = ldb; g.b_major = b_major;
     g.D = D; g.ldd = ldd; g.R = R; g.ldr = ldr; g.M = M; g.N = N; g.K = K; g.epi = epi; g.cta_group = cta_group;
+    return sf::gemm(g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Every epilogue, including the fused SwiGLU ones (epi 4: D = gu [M, 2*n_half], D2 = act [M, n_half]; epi 5: R = gu, D = d(gu)).
+extern "C" int sf_gemm_bf16_ex(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major,
+                               void* D, int64_t ldd, const void* R, int64_t ldr, void* D2, int64_t ldd2, int n_half,
+                               int M, int N, int K, int epi, int cta_group, void* stream) {
+    sf::GemmDesc g;
+    g.A = A; g.lda = lda; g.a_major = a_major; g.B = B; g.ldb = ldb; g.b_major = b_major;
+    g.D = D; g.ldd = ldd; g.R = R; g.ldr = ldr; g.M = M; g.N = N; g.K = K; g.epi = epi; g.cta_group = cta_group;
+    g.D2 = D2; g.ldd2 = ldd2; g.n_half = n_half;
     return sf::gemm(g, reinterpret_cast<cudaStream_t>(stream));
 }

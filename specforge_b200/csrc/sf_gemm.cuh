@@ -46,6 +46,7 @@ struct GemmParams {
     void* D2; int ldd2;   // EPI_SWIGLU: act output
     int n_half;           // EPI_SWIGLU / EPI_SWIGLU_BWD: I (columns of gate == columns of up)
     int group_m;          // M-blocks per raster group (L2 reuse window of the A operand)
+    int stages;           // depth of the TMA -> MMA smem ring (6 or 7 x 32 KB)
 };
 
 template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN>
@@ -59,10 +60,12 @@ struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int kStages = (192 * 1024) / STAGE_BYTES;
+    static constexpr int kStages = (192 * 1024) / STAGE_BYTES;      // default ring depth
+    static constexpr int kMaxStages = (224 * 1024) / STAGE_BYTES;   // deepest ring that fits the 227 KB of a CTA
     static constexpr int kAccStages = 2;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/; }
+    static constexpr int SMEM_BYTES = smem_bytes(kStages);
     static constexpr int kThreads = 256;
     static_assert(kBlockN * kAccStages <= 512, "TMEM overflow");
     static_assert(kBlockN % 64 == 0 && kBlockN <= 256, "bad BLOCK_N");
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmParams p) {
     using Cfg = GemmCfg<kCtaGroup, kAMajor, kBMajor, kBlockN>;
-    constexpr int kStages = Cfg::kStages;
+    const int kStages = p.stages;
     constexpr int BLOCK_K = Cfg::BLOCK_K;
 
     extern __shared__ uint8_t smem_raw[];

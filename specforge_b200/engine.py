@@ -83,6 +83,8 @@ def _declare():
     l.sf_eagle3_backward_ex.restype = ctypes.c_int
     l.sf_eagle3_backward_ex.argtypes = [POINTER(SfConfig), c_void_p, POINTER(SfFrozen), POINTER(SfBatch), c_void_p, c_size_t,
                                         c_float, c_void_p, ctypes.c_int, GRAD_READY_FN, c_void_p, c_void_p]
+    l.sf_eagle3_workspace_view.restype = ctypes.c_int
+    l.sf_eagle3_workspace_view.argtypes = [POINTER(SfConfig), ctypes.c_char_p, POINTER(c_int64), POINTER(c_int64)]
     l.sf_grads_to_bf16.restype = ctypes.c_int
     l.sf_grads_to_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     l.sf_optimizer_step.restype = ctypes.c_int
@@ -341,6 +343,28 @@ class Eagle3Engine:
                                       self.workspace_bytes, self.metrics.data_ptr(), self.loss.data_ptr(), int(need_grad),
                                       self._stream()), "sf_eagle3_forward")
         return self.loss, self.metrics
+
+    _VIEW_DTYPES = {"teacher_stats": torch.float32, "teacher_ids": torch.int64, "position_mask": torch.int32}
+
+    def workspace_view(self, name: str) -> torch.Tensor:
+        """A named tensor of the LAST step inside the workspace (sf_eagle3_workspace_view), shaped for the batch that ran:
+        "logits" [T, B*S, DV] (logits after forward(need_grad=False); d(loss)/d(logits) after need_grad=True), "h" [T+1, B*S, H],
+        "qkv", "attn", "hf", "teacher_xg" [B, S+T, DV], "teacher_stats" [B, S+T, 4], "teacher_ids" [B, S+T], "position_mask" [B, S].
+        A view, not a copy: it is overwritten by the next step."""
+        off, size = c_int64(), c_int64()
+        cfg = self._call_cfg
+        check(lib().sf_eagle3_workspace_view(cfg, name.encode(), ctypes.byref(off), ctypes.byref(size)), "sf_eagle3_workspace_view")
+        base = self._ws_ptr - self.workspace.data_ptr()
+        raw = self.workspace[base + off.value: base + off.value + size.value]
+        dt = self._VIEW_DTYPES.get(name, torch.bfloat16)
+        t = raw.view(dt)
+        d, B, S, T = self.dims, cfg.batch, cfg.seq_len, self.T
+        M = B * S
+        A, KV = d.num_heads * d.head_dim, d.num_kv_heads * d.head_dim
+        shape = {"h": (T + 1, M, d.hidden_size), "qkv": (T, M, A + 2 * KV), "attn": (T, M, A), "hf": (T, M, d.hidden_size),
+                 "logits": (T, M, d.draft_vocab_size), "teacher_xg": (B, S + T, d.draft_vocab_size), "teacher_stats": (B, S + T, 4),
+                 "teacher_ids": (B, S + T), "position_mask": (B, S)}[name]
+        return t.view(shape)
 
     def backward(self, loss_scale: float = 1.0, accumulate: bool = False, on_ready=None) -> None:
         """Full backward.  on_ready(first_elem, n_elems) is called (on the host, in stream order of the producing

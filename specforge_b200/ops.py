@@ -34,6 +34,37 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major=MAJOR_K, b_major=MAJOR_K, 
     return out
 
 
+def gemm_swiglu(x: torch.Tensor, w_gate_up: torch.Tensor):
+    """(gu, act) = fused gate/up projection + SwiGLU (EPI_SWIGLU): x [M, K], w_gate_up [2I, K] -> gu [M, 2I], act [M, I]."""
+    import ctypes
+    l = lib()
+    M, K = x.shape
+    I = w_gate_up.shape[0] // 2
+    gu = torch.empty(M, 2 * I, dtype=torch.bfloat16, device=x.device)
+    act = torch.empty(M, I, dtype=torch.bfloat16, device=x.device)
+    l.sf_gemm_bf16_ex.restype = ctypes.c_int
+    check(l.sf_gemm_bf16_ex(ctypes.c_void_p(x.data_ptr()), ctypes.c_int64(x.stride(0)), 0, ctypes.c_void_p(w_gate_up.data_ptr()),
+                            ctypes.c_int64(w_gate_up.stride(0)), 0, ctypes.c_void_p(gu.data_ptr()), ctypes.c_int64(2 * I), None,
+                            ctypes.c_int64(0), ctypes.c_void_p(act.data_ptr()), ctypes.c_int64(I), I, M, 2 * I, K, 4, 0,
+                            ctypes.c_void_p(_stream())), "sf_gemm_bf16_ex")
+    return gu, act
+
+
+def gemm_swiglu_bwd(dy: torch.Tensor, w_down: torch.Tensor, gu: torch.Tensor):
+    """d(gu) [M, 2I] = SwiGLU backward of d(act) = dy [M, H] @ w_down [H, I] (EPI_SWIGLU_BWD; d(act) never reaches HBM)."""
+    import ctypes
+    l = lib()
+    M, H = dy.shape
+    I = w_down.shape[1]
+    dgu = torch.empty(M, 2 * I, dtype=torch.bfloat16, device=dy.device)
+    l.sf_gemm_bf16_ex.restype = ctypes.c_int
+    check(l.sf_gemm_bf16_ex(ctypes.c_void_p(dy.data_ptr()), ctypes.c_int64(dy.stride(0)), 0, ctypes.c_void_p(w_down.data_ptr()),
+                            ctypes.c_int64(w_down.stride(0)), 1, ctypes.c_void_p(dgu.data_ptr()), ctypes.c_int64(2 * I),
+                            ctypes.c_void_p(gu.data_ptr()), ctypes.c_int64(2 * I), None, ctypes.c_int64(0), I, M, I, H, 5, 0,
+                            ctypes.c_void_p(_stream())), "sf_gemm_bf16_ex")
+    return dgu
+
+
 def _declare_ops():
     import ctypes
     from ctypes import POINTER, c_float, c_int, c_int64, c_void_p

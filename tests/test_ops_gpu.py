@@ -44,6 +44,62 @@ def test_gemm(G, am, bm, M, N, K, epi):
     assert (got - ref).abs().max().item() <= tol * scale * (2 if epi == 1 else 1) + 1e-4
 
 
+def test_gemm_step_shapes():
+    """The shapes the headline step runs that the small cases above do not reach: the K = T*M = 114 688 weight-gradient
+    contraction (MN-major x MN-major, fp32 accumulate in TMEM, EPI_F32_ACCUM) and an N = 151 936 target-head row block."""
+    from specforge_b200 import ops
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(0)
+    # wgrad: dW [4096, 4096] += dY^T X over 114 688 tokens (o_proj's weight gradient at config 2)
+    K, M, N = 114688, 4096, 4096
+    a = (torch.randn(K, M, device=dev, generator=g) * 0.05).bfloat16()       # dY, MN-major operand [K, rows]
+    b = (torch.randn(K, N, device=dev, generator=g) * 0.5).bfloat16()        # X
+    out0 = torch.randn(M, N, device=dev, generator=g)
+    out = out0.clone()
+    ops.gemm(a, b, a_major=1, b_major=1, out=out, epi=3)
+    ref = out0.double()
+    for k0 in range(0, K, 16384):                                            # fp64 reference in K chunks
+        ref += a[k0:k0 + 16384].double().t() @ b[k0:k0 + 16384].double()
+    err = (out.double() - ref).abs().max().item()
+    # fp32 accumulation of 1.1e5 products in TMEM (7168 dependent UMMA adds per element): stated bound 5e-4 of the largest entry
+    print(f"wgrad K=114688 fp32-accumulate: max|err| {err:.3e} of max|ref| {ref.abs().max().item():.3e}")
+    assert err <= 5e-4 * ref.abs().max().item(), (err, ref.abs().max().item())
+    del a, b, out, out0, ref
+    # target head: [2048, 4096] x [151936, 4096]^T, bf16 out
+    M, N, K = 2048, 151936, 4096
+    x = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * (K ** -0.5)).bfloat16()
+    y = ops.gemm(x, w)
+    ref = x.float() @ w.float().t()
+    scale = ref.abs().max().item()
+    assert (y.float() - ref).abs().max().item() <= 2 ** -7 * scale
+    # bit-level agreement with the bf16 rounding of the exact product except where fp32 accumulation order moves a tie
+    assert (y != ref.bfloat16()).float().mean().item() < 2e-2
+
+
+def test_gemm_fused_swiglu_epilogues():
+    """EPI_SWIGLU / EPI_SWIGLU_BWD directly (a13: LlamaMLP, llama3_eagle.py:1518-1549) against the unfused kernels and an fp32
+    restatement: act = bf16(bf16(silu(g)) * u) from the bf16-rounded gate/up outputs; d(gu) from d(act) = dY W_down."""
+    from specforge_b200 import ops
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(1)
+    M, H, I = 1024, 512, 1280                      # I % 128 == 0; 5 n-blocks of 256 with a ragged last block
+    x = torch.randn(M, H, device=dev, generator=g).bfloat16()
+    w = (torch.randn(2 * I, H, device=dev, generator=g) * H ** -0.5).bfloat16()
+    gu, act = ops.gemm_swiglu(x, w)
+    gu_ref = ops.gemm(x, w)
+    assert torch.equal(gu, gu_ref)                                           # same accumulation, same rounding
+    assert torch.equal(act, ops.swiglu_fwd(gu_ref))                          # the unfused kernel on the same gu
+    ref = torch.nn.functional.silu(gu.float()[:, :I]).bfloat16().float() * gu.float()[:, I:]
+    assert (act.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    dy = (torch.randn(M, H, device=dev, generator=g) * 0.1).bfloat16()
+    wd = (torch.randn(H, I, device=dev, generator=g) * I ** -0.5).bfloat16()
+    dgu = ops.gemm_swiglu_bwd(dy, wd, gu)
+    dact = ops.gemm(dy, wd, b_major=1)                                       # bf16 d(act) as the unfused path stores it
+    dgu_ref = ops.swiglu_bwd(gu, dact)
+    assert (dgu.float() - dgu_ref.float()).abs().max().item() <= 2 ** -6 * dgu_ref.float().abs().max().item()
+
+
 def test_rmsnorm_fwd_bwd():
     from oracle import eagle3_oracle as O
     from specforge_b200 import ops
@@ -102,7 +158,8 @@ def test_swiglu_and_rope():
 
 
 @pytest.mark.parametrize("hd,nh,nkv,S,J,pad", [(128, 4, 1, 160, 0, 0), (128, 4, 1, 160, 3, 9), (64, 14, 2, 128, 2, 0),
-                                               (128, 8, 2, 333, 6, 40), (64, 4, 4, 64, 1, 0)])
+                                               (128, 8, 2, 333, 6, 40), (64, 4, 4, 64, 1, 0),
+                                               (128, 32, 8, 2048, 6, 200)])   # config-2 head geometry, full S, padded
 def test_ttt_attention_fwd_bwd(hd, nh, nkv, S, J, pad):
     """vs the oracle's eager TTT attention (llama3_eagle.py:717-785) in fp32 with autograd."""
     from oracle import eagle3_oracle as O

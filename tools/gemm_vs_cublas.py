@@ -52,7 +52,12 @@ def main():
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--out", default="gpurun_out/gemm_vs_cublas.json")
     ap.add_argument("--only", default=None)
+    ap.add_argument("--variants", nargs="*", default=[], help="sf_debug_option settings to time as extra arms, e.g. gemm_stages=7")
     a = ap.parse_args()
+    import ctypes
+    from specforge_b200._lib import lib
+    L = lib()
+    L.sf_debug_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
     dev = "cuda"
     torch.manual_seed(0)
     res = []
@@ -74,13 +79,21 @@ def main():
             torch.matmul(Aref, Bref, out=ref_out)    # bf16 output (cuBLAS has no fp32-out bf16 GEMM through torch)
 
         t_ours, t_cub = [], []
+        t_var = {v: [] for v in a.variants}
         for _ in range(a.rounds):
             t_ours.append(bench_block(ours, a.ms))
+            for v in a.variants:
+                nm, val = v.split("=")
+                assert L.sf_debug_option(nm.encode(), int(val)) == 0, v
+                t_var[v].append(bench_block(ours, a.ms))
+                L.sf_debug_option(nm.encode(), 0)
             t_cub.append(bench_block(cublas, a.ms))
         fl = 2.0 * m * n * k / 1e9
         r = {"shape": name, "M": m, "N": n, "K": k, "ours_tflops": [round(fl / t, 1) for t in t_ours],
              "cublas_tflops": [round(fl / t, 1) for t in t_cub],
              "ratio_median": round(sorted(t_cub)[len(t_cub) // 2] / sorted(t_ours)[len(t_ours) // 2], 4)}
+        for v in a.variants:
+            r[v] = [round(fl / t, 1) for t in t_var[v]]
         print(json.dumps(r), flush=True)
         res.append(r)
         del Aop, Bop, out, ref_out
