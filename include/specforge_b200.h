@@ -150,6 +150,8 @@ int sf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t
 int sf_gemm_bf16_ex(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D, int64_t ldd,
                     const void* R, int64_t ldr, void* D2, int64_t ldd2, int n_half, int M, int N, int K, int epi, int cta_group,
                     void* stream);
+/* out[i, :] = table[ids[i], :] (bf16 [V, H] table, int64 ids; embed_input_ids, llama3_eagle.py:1759-1760) */
+int sf_embedding_gather(const void* table, int64_t V, int H, const int64_t* ids, int64_t n, void* out, void* stream);
 int sf_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* out, int64_t ldo, int64_t M, int H, float eps,
                    void* stream);
 /* dw (+)= column sums via per-block partials in `scratch` (sf_rmsnorm_bwd_scratch_bytes(H) bytes): deterministic. */

@@ -64,7 +64,7 @@ struct Plan {
     int64_t xg, tstats, ids, pos_mask, loss_mask32, key_mask, kvlen, d2t_idx, row_ws, sd_ws, metrics, misc;
     // union region: forward temporaries / backward buffers
     int64_t u_base;
-    int64_t tgt_shift, tlogits;                       // forward temporaries
+    int64_t tgt_shift, tlogits, tpart, lstats, t2d_bits, t2d_prefix;   // forward temporaries
     int64_t dh_tot, dgu, dhmid, dqkv, d_hf, d_act, d_hn2, d_attn, d_xcat, dh_carry, dk_acc, dv_acc, dq_diag, delta, d_hs3n, norm_ws;
     int64_t total;
 };
@@ -102,6 +102,10 @@ static Plan make_plan(const sf_eagle3_config& c) {
     // forward temporaries
     p.tgt_shift = take(M * x.Ht * 2);
     p.tlogits = take(M * (int64_t)x.V * 2);
+    p.tpart = take(5 * (int64_t)((x.V + 255) / 256) * M * 4);      // EPI_TEACHER partials [5][n-blocks][M]
+    p.lstats = take(3 * (int64_t)((x.DV + 255) / 256) * M * 4);    // EPI_BF16_STATS partials of one step's lm_head GEMM
+    p.t2d_bits = take((int64_t)((x.V + 31) / 32) * 4);
+    p.t2d_prefix = take((int64_t)((x.V + 31) / 32) * 4);
     const int64_t fwd_end = o;
     // backward buffers alias the forward temporaries
     o = p.u_base;
@@ -218,10 +222,28 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
     SideStream* side = (overlap_enabled() && dev < 16 && g_side[dev].init()) ? &g_side[dev] : nullptr;
     cudaStream_t ls = st;   // stream of the loss-side work
     if (side) ls = side->stream;
-    // The target-head GEMM is issued in two row halves: the teacher statistics of the first half run on the side stream
-    // under the second half's GEMM, those of the second half under the draft's fc / QKV GEMMs.
+    const bool fuse_teacher = opt(OPT_NO_TEACHER_FUSION) != 1;
+    if (fuse_teacher) {
+        // The teacher's row statistics (argmax / logsumexp over the full vocabulary, softmax statistics and gather of the draft
+        // vocabulary) are computed by the target-head GEMM's own epilogue from the accumulators in TMEM: the [M, V] logits are
+        // never written (eagle3/model.py:487-501; core/compact_teacher.py:57-150 is the same streaming reduction).
+        SF_TRY(t2d_index(fz.t2d, x.V, c.at<uint32_t>(p.t2d_bits), c.at<int>(p.t2d_prefix), st));
+        GemmDesc g;
+        g.A = c.bf(p.tgt_shift); g.lda = x.Ht; g.a_major = MAJOR_K; g.B = fz.target_head; g.ldb = x.Ht; g.b_major = MAJOR_K;
+        g.D = nullptr; g.ldd = 0; g.R = nullptr; g.ldr = 0; g.M = (int)M; g.N = x.V; g.K = x.Ht; g.epi = EPI_TEACHER; g.cta_group = 0;
+        g.stats = c.at<float>(p.tpart); g.t2d_bits = c.at<uint32_t>(p.t2d_bits); g.t2d_prefix = c.at<int>(p.t2d_prefix);
+        g.xg = c.bf(p.xg); g.S = x.S; g.T = T; g.DV = x.DV;
+        SF_TRY(gemm(g, st));
+        SF_TRY(teacher_merge(c.at<float>(p.tpart), (x.V + 255) / 256, M, fz.t2d, c.at<int>(p.loss_mask32), c.at<float>(p.tstats),
+                             c.at<int64_t>(p.ids), c.at<int>(p.pos_mask), c.bf(p.xg), x.B, x.S, T, x.DV, st));
+        side = nullptr;   // nothing left to overlap: the side stream is only used by the unfused path below
+        ls = st;
+    }
+    // Unfused path (sf_debug_option("no_teacher_fusion", 1), kept for A/B runs): the target-head GEMM writes the logits and is
+    // issued in two row halves; the teacher statistics of the first half run on the side stream under the second half's GEMM,
+    // those of the second half under the draft's fc / QKV GEMMs.
     const int64_t Mh = (side && M >= 1024) ? (M / 2) / 256 * 256 : M;
-    for (int half = 0; half < (Mh < M ? 2 : 1); ++half) {
+    for (int half = 0; !fuse_teacher && half < (Mh < M ? 2 : 1); ++half) {
         const int64_t r0 = half ? Mh : 0, nr = half ? M - Mh : Mh;
         SF_TRY(mm(c, c.bf(p.tgt_shift, r0 * x.Ht), x.Ht, MAJOR_K, fz.target_head, x.Ht, MAJOR_K, c.bf(p.tlogits, r0 * x.V), x.V,
                   nullptr, 0, nr, x.V, x.Ht, EPI_BF16));
@@ -287,7 +309,16 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         // logits = lm_head(norm(h_{j+1}))   (llama3_eagle.py:1772-1777)
         if (cfg.norm_output)
             SF_TRY(rmsnorm_fwd(h_out, x.H, nullptr, x.S, 0, c.W[SF_P_NORM], hf, x.H, M, x.H, cfg.rms_eps, nullptr, st));
-        SF_TRY(mm(c, hf, x.H, MAJOR_K, c.W[SF_P_LM_HEAD], x.H, MAJOR_K, logits, x.DV, nullptr, 0, M, x.DV, x.H, EPI_BF16));
+        const bool fuse_stats = opt(OPT_NO_LOSS_STATS_FUSION) != 1 && !(side && loss_on_side());   // one partials buffer: the loss must run in stream order
+        if (fuse_stats) {   // logits + per-tile (max, sum-exp, argmax) partials: the loss kernel's first pass over the row disappears
+            GemmDesc g;
+            g.A = hf; g.lda = x.H; g.a_major = MAJOR_K; g.B = c.W[SF_P_LM_HEAD]; g.ldb = x.H; g.b_major = MAJOR_K;
+            g.D = logits; g.ldd = x.DV; g.R = nullptr; g.ldr = 0; g.M = (int)M; g.N = x.DV; g.K = x.H; g.epi = EPI_BF16_STATS; g.cta_group = 0;
+            g.stats = c.at<float>(p.lstats);
+            SF_TRY(gemm(g, st));
+        } else {
+            SF_TRY(mm(c, hf, x.H, MAJOR_K, c.W[SF_P_LM_HEAD], x.H, MAJOR_K, logits, x.DV, nullptr, 0, M, x.DV, x.H, EPI_BF16));
+        }
         // loss / metrics / d(logits) in place   (eagle3/model.py:142-199, core/loss.py, core/lk_loss.py)
         const float step_weight = powf(cfg.ploss_decay, (float)j);
         // The loss runs on the main stream: it is issue- and power-hungry enough that co-running it with a GEMM slows
@@ -305,7 +336,8 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         }
         SF_TRY(loss_step(logits, x.DV, c.bf(p.xg), c.at<float>(p.tstats), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask),
                          c.at<int>(p.loss_mask32), fz.d2t, x.B, x.S, T, x.DV, j, step_weight, need_grad, cfg.lk_loss_type,
-                         cfg.kl_scale, cfg.kl_decay, c.at<float>(p.row_ws), c.at<float>(p.metrics), on_side ? 1 : 0, on_side ? ls : st));
+                         cfg.kl_scale, cfg.kl_decay, c.at<float>(p.row_ws), c.at<float>(p.metrics),
+                         fuse_stats ? c.at<float>(p.lstats) : nullptr, (x.DV + 255) / 256, on_side ? ls : st));
     }
     total_loss_kernel<<<1, 64, 0, st>>>(c.at<float>(p.metrics), T, cfg.ploss_decay, loss_out ? loss_out : c.at<float>(p.misc), metrics_out);
     SF_CUDA_CHECK_LAUNCH("total_loss");
@@ -534,6 +566,10 @@ extern "C" int sf_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* o
 extern "C" int sf_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const void* dy, int64_t lddy, const void* add, void* dx,
                               float* dw, float* scratch, int64_t M, int H, float eps, void* stream) {
     return rmsnorm_bwd(x, ldx, nullptr, 1, 0, w, dy, lddy, add, nullptr, dx, dw, scratch, M, H, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int sf_embedding_gather(const void* table, int64_t V, int H, const int64_t* ids, int64_t n, void* out, void* stream) {
+    if (!table || !ids || !out) return set_error(-22, "null argument");
+    return embedding_gather(table, V, H, ids, n, out, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int64_t sf_rmsnorm_bwd_scratch_bytes(int H) { return rmsnorm_bwd_ws_bytes(H); }
 extern "C" int sf_swiglu_fwd(const void* gu, void* act, int64_t M, int I, void* stream) {

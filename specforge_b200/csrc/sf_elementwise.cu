@@ -338,6 +338,22 @@ add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __rest
     }
 }
 
+// out[i, :] = table[ids[i], :]   (frozen embedding lookup; ids outside [0, V) give zeros)
+__global__ void __launch_bounds__(256)
+embedding_gather_kernel(const __nv_bfloat16* __restrict__ table, int64_t V, int H, const int64_t* __restrict__ ids, int64_t n,
+                        __nv_bfloat16* __restrict__ out) {
+    const int c8n = H / 8;
+    const int64_t total = n * c8n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / c8n;
+        const int c = (int)(i % c8n);
+        const int64_t tok = ids[r];
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (tok >= 0 && tok < V) v = __ldg(reinterpret_cast<const uint4*>(table + tok * H) + c);
+        reinterpret_cast<uint4*>(out + r * H)[c] = v;
+    }
+}
+
 static inline int grid_for(int64_t total, int threads = 256, int max_blocks = 148 * 16) {
     int64_t b = (total + threads - 1) / threads;
     if (b > max_blocks) b = max_blocks;
@@ -408,6 +424,13 @@ int swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t M, int I, cu
     swiglu_bwd_kernel<<<grid_for(M * (I / 8)), 256, 0, st>>>((const __nv_bfloat16*)gu, (const __nv_bfloat16*)dact,
                                                             (__nv_bfloat16*)dgu, M, I);
     SF_CUDA_CHECK_LAUNCH("swiglu_bwd");
+    return 0;
+}
+int embedding_gather(const void* table, int64_t V, int H, const int64_t* ids, int64_t n, void* out, cudaStream_t st) {
+    if (H % 8) return set_error(-22, "embedding: H=%d must be a multiple of 8", H);
+    if (n <= 0) return 0;
+    embedding_gather_kernel<<<grid_for(n * (H / 8)), 256, 0, st>>>((const __nv_bfloat16*)table, V, H, ids, n, (__nv_bfloat16*)out);
+    SF_CUDA_CHECK_LAUNCH("embedding_gather");
     return 0;
 }
 int add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t st) {

@@ -34,6 +34,17 @@ enum : int {
     // Backward: acc = d(act) tile [128 x 256] over columns j of I; R = gu [M, 2I]; D = d(gu) [M, 2I]:
     // d(gate) = d(act) * u * silu'(g), d(up) = d(act) * silu(g).
     EPI_SWIGLU_BWD = 5,
+    // Row statistics fused into the epilogue (the reductions of _compute_target_p / LogSoftmaxLoss pass A move into the GEMM
+    // that produces the row).  Per (row, n-block) the epilogue emits partial online-softmax state over the bf16-ROUNDED outputs
+    // x = bf16(acc):  stats[k][n_blk][row], k = 0 max, 1 sum exp(x - max), 2 first index of the max (int bits); a small merge
+    // kernel combines the n-blocks in ascending order (first index wins ties = torch.argmax).
+    //   EPI_BF16_STATS: D(bf16) = acc as EPI_BF16, plus the three partials          (draft lm_head -> loss pass A)
+    //   EPI_TEACHER:    no D at all.  Columns flagged in t2d_bits are appended, in vocabulary order, to xg[orow, :] (the gathered
+    //                   draft-vocab teacher logits, orow = row + (row / S) * T = the [B, S+T, DV] padded layout), with two more
+    //                   partials k = 3 max, 4 sum exp over the draft-vocab columns only.  The [M, V] teacher logits never exist
+    //                   (eagle3/model.py:487-501; this is also core/compact_teacher.py:57-150's streaming logsumexp/argmax).
+    EPI_BF16_STATS = 6,
+    EPI_TEACHER = 7,
 };
 
 struct GemmParams {
@@ -47,6 +58,11 @@ struct GemmParams {
     int n_half;           // EPI_SWIGLU / EPI_SWIGLU_BWD: I (columns of gate == columns of up)
     int group_m;          // M-blocks per raster group (L2 reuse window of the A operand)
     int stages;           // depth of the TMA -> MMA smem ring (6 or 7 x 32 KB)
+    // EPI_BF16_STATS / EPI_TEACHER
+    float* stats;                  // [3 or 5][num_n_blocks][M]
+    const uint32_t* t2d_bits;      // [ceil(N / 32)] bit e of word w: column 32 w + e is in the draft vocabulary
+    const int* t2d_prefix;         // [ceil(N / 32)] draft-vocab columns before column 32 w
+    __nv_bfloat16* xg; int S, T, DV;
 };
 
 template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN>
@@ -60,7 +76,7 @@ struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int kStages = (192 * 1024) / STAGE_BYTES;      // default ring depth
+    static constexpr int kStages = (224 * 1024) / STAGE_BYTES;      // default ring depth: 7 x 32 KB (in-step A/B on one box: -1.8 % step time vs 6)
     static constexpr int kMaxStages = (224 * 1024) / STAGE_BYTES;   // deepest ring that fits the 227 KB of a CTA
     static constexpr int kAccStages = 2;
     static constexpr int TMEM_COLS = 512;
@@ -70,6 +86,228 @@ struct GemmCfg {
     static_assert(kBlockN * kAccStages <= 512, "TMEM overflow");
     static_assert(kBlockN % 64 == 0 && kBlockN <= 256, "bad BLOCK_N");
 };
+
+// The epilogue of one thread: its row of the [128 x kBlockN] accumulator block at TMEM address t_row (lane = row), processed in
+// 32-column chunks; shared by the 256 x 256 (gemm_kernel) and 512 x 256 (gemm_wide_kernel) tilings.
+template <int kBlockN>
+__device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const int row, const bool row_ok, const int n_blk,
+                                                   const int n0, const uint32_t t_row) {
+            if (p.epi == EPI_SWIGLU) {
+                // columns [0,128) of the accumulator = gate(j0 + .), [128,256) = up(j0 + .)
+                const int j0 = n_blk * (kBlockN / 2);
+                __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
+                __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.D2) + (size_t)row * p.ldd2;
+#pragma unroll 1
+                for (int c = 0; c < kBlockN / 64; ++c) {
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, g);
+                    tmem_ld_32x32b_x32(t_row + kBlockN / 2 + c * 32, u);
+                    tmem_ld_wait();
+                    const int col = j0 + c * 32;
+                    if (!row_ok || col >= p.n_half) continue;
+                    uint32_t og[16], ou[16], oa[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        og[e] = pack_bf16x2(__uint_as_float(g[2 * e]), __uint_as_float(g[2 * e + 1]));
+                        ou[e] = pack_bf16x2(__uint_as_float(u[2 * e]), __uint_as_float(u[2 * e + 1]));
+                        const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&og[e]);
+                        const __nv_bfloat162 ub = *reinterpret_cast<const __nv_bfloat162*>(&ou[e]);
+                        const float g0 = __bfloat162float(gb.x), g1 = __bfloat162float(gb.y);
+                        const float s0 = __bfloat162float(__float2bfloat16_rn(g0 / (1.f + __expf(-g0))));
+                        const float s1 = __bfloat162float(__float2bfloat16_rn(g1 / (1.f + __expf(-g1))));
+                        oa[e] = pack_bf16x2(s0 * __bfloat162float(ub.x), s1 * __bfloat162float(ub.y));
+                    }
+                    // host guarantees n_half % 128 == 0: every 32-column chunk is whole
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        reinterpret_cast<uint4*>(gu + col)[q] = make_uint4(og[q * 4], og[q * 4 + 1], og[q * 4 + 2], og[q * 4 + 3]);
+                        reinterpret_cast<uint4*>(gu + p.n_half + col)[q] = make_uint4(ou[q * 4], ou[q * 4 + 1], ou[q * 4 + 2], ou[q * 4 + 3]);
+                        reinterpret_cast<uint4*>(act + col)[q] = make_uint4(oa[q * 4], oa[q * 4 + 1], oa[q * 4 + 2], oa[q * 4 + 3]);
+                    }
+                }
+            } else if (p.epi == EPI_SWIGLU_BWD) {
+                const __nv_bfloat16* gu = p.R + (size_t)row * p.ldr;
+                __nv_bfloat16* dgu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
+#pragma unroll 1
+                for (int c = 0; c < kBlockN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    const int col = n0 + c * 32;
+                    if (!row_ok || col >= p.n_half) continue;
+                    // host guarantees n_half % 32 == 0
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(gu + col) + q);
+                        const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(gu + p.n_half + col) + q);
+                        const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
+                        uint32_t odg[4], odu[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&gw[e]);
+                            const __nv_bfloat162 ub = *reinterpret_cast<const __nv_bfloat162*>(&uw[e]);
+                            float dg[2], du[2];
+#pragma unroll
+                            for (int w = 0; w < 2; ++w) {
+                                const float gg = __bfloat162float(w ? gb.y : gb.x), uu = __bfloat162float(w ? ub.y : ub.x);
+                                const float da = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[q * 8 + e * 2 + w])));
+                                const float sg = 1.f / (1.f + __expf(-gg));
+                                dg[w] = da * uu * (sg * (1.f + gg * (1.f - sg)));
+                                du[w] = da * gg * sg;
+                            }
+                            odg[e] = pack_bf16x2(dg[0], dg[1]);
+                            odu[e] = pack_bf16x2(du[0], du[1]);
+                        }
+                        reinterpret_cast<uint4*>(dgu + col)[q] = make_uint4(odg[0], odg[1], odg[2], odg[3]);
+                        reinterpret_cast<uint4*>(dgu + p.n_half + col)[q] = make_uint4(odu[0], odu[1], odu[2], odu[3]);
+                    }
+                }
+            } else if (p.epi == EPI_BF16_STATS || p.epi == EPI_TEACHER) {
+                const bool gather = p.epi == EPI_TEACHER;
+                float m = -INFINITY, d = 0.f, md = -INFINITY, dd = 0.f;
+                int idx = 0x7fffffff;
+                __nv_bfloat16* xo = nullptr;
+                if (gather && row_ok) xo = p.xg + ((size_t)row + (size_t)(row / p.S) * p.T) * p.DV;
+#pragma unroll 1
+                for (int c = 0; c < kBlockN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    const int col = n0 + c * 32;
+                    if (!row_ok || col >= p.N) continue;
+                    const bool full = (col + 32 <= p.N);
+                    float x[32];
+                    uint32_t o[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&o[e]);
+                        x[2 * e] = __bfloat162float(b2.x);
+                        x[2 * e + 1] = __bfloat162float(b2.y);
+                    }
+                    if (!full) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (col + e >= p.N) x[e] = -INFINITY;
+                    }
+                    if (!gather) {
+                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col;
+                        if (full) {
+                            uint4* dp = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) dp[q] = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (col + e < p.N) dst[e] = __float2bfloat16_rn(x[e]);
+                        }
+                    }
+                    float cm = x[0];
+                    int ci = 0;
+#pragma unroll
+                    for (int e = 1; e < 32; ++e)
+                        if (x[e] > cm) { cm = x[e]; ci = e; }
+                    if (cm > m) { d *= __expf(m - cm); m = cm; idx = col + ci; }
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) d += __expf(x[e] - m);
+                    if (gather) {
+                        const uint32_t mask = __ldg(p.t2d_bits + (col >> 5));
+                        if (mask) {
+                            __nv_bfloat16* dst = xo + __ldg(p.t2d_prefix + (col >> 5));
+                            float dm = -INFINITY;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if ((mask >> e) & 1u) dm = fmaxf(dm, x[e]);
+                            if (dm > md) { dd *= __expf(md - dm); md = dm; }
+                            int cnt = 0;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if ((mask >> e) & 1u) {       // warp-uniform: every lane holds the same columns
+                                    dd += __expf(x[e] - md);
+                                    dst[cnt++] = __float2bfloat16_rn(x[e]);
+                                }
+                        }
+                    }
+                }
+                if (row_ok && n0 < p.N) {
+                    const size_t plane = (size_t)p.num_n_blocks * p.M;
+                    float* sp = p.stats + (size_t)n_blk * p.M + row;
+                    sp[0] = m; sp[plane] = d; sp[2 * plane] = __int_as_float(idx);
+                    if (gather) { sp[3 * plane] = md; sp[4 * plane] = dd; }
+                }
+            } else
+#pragma unroll 1
+            for (int c = 0; c < kBlockN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_row + c * 32, v);
+                tmem_ld_wait();
+                const int col = n0 + c * 32;
+                if (!row_ok || col >= p.N) continue;
+                const bool full = (col + 32 <= p.N);
+                if (p.epi == EPI_BF16 || p.epi == EPI_BF16_RESID) {
+                    __nv_bfloat16* dst =
+                        reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col;
+                    if (full) {
+                        uint32_t o[16];
+                        if (p.epi == EPI_BF16_RESID) {
+                            const uint4* rp =
+                                reinterpret_cast<const uint4*>(p.R + (size_t)row * p.ldr + col);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 r4 = __ldg(rp + q);
+                                const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
+                                    // match the reference's two roundings: linear output -> bf16, then add
+                                    float a0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[q * 8 + e * 2])));
+                                    float a1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[q * 8 + e * 2 + 1])));
+                                    o[q * 4 + e] = pack_bf16x2(a0 + __bfloat162float(rb.x),
+                                                               a1 + __bfloat162float(rb.y));
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                        }
+                        uint4* dp = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            dp[q] = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                    } else {
+                        for (int e = 0; e < 32 && col + e < p.N; ++e) {
+                            float a = __uint_as_float(v[e]);
+                            if (p.epi == EPI_BF16_RESID)
+                                a = __bfloat162float(__float2bfloat16_rn(a)) +
+                                    __bfloat162float(p.R[(size_t)row * p.ldr + col + e]);
+                            dst[e] = __float2bfloat16_rn(a);
+                        }
+                    }
+                } else {
+                    float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col;
+                    if (full) {
+                        float4* dp = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                   __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                            if (p.epi == EPI_F32_ACCUM) {
+                                float4 old = dp[q];
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            dp[q] = o;
+                        }
+                    } else {
+                        for (int e = 0; e < 32 && col + e < p.N; ++e) {
+                            float a = __uint_as_float(v[e]);
+                            if (p.epi == EPI_F32_ACCUM) a += dst[e];
+                            dst[e] = a;
+                        }
+                    }
+                }
+            }
+}
 
 template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN>
 __global__ void __launch_bounds__(256, 1)
@@ -232,148 +470,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + astage * Cfg::BLOCK_N;
             const bool row_ok = row < p.M;
-            if (p.epi == EPI_SWIGLU) {
-                // columns [0,128) of the accumulator = gate(j0 + .), [128,256) = up(j0 + .)
-                const int j0 = n_blk * (Cfg::BLOCK_N / 2);
-                __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
-                __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.D2) + (size_t)row * p.ldd2;
-#pragma unroll 1
-                for (int c = 0; c < Cfg::BLOCK_N / 64; ++c) {
-                    uint32_t g[32], u[32];
-                    tmem_ld_32x32b_x32(t_row + c * 32, g);
-                    tmem_ld_32x32b_x32(t_row + Cfg::BLOCK_N / 2 + c * 32, u);
-                    tmem_ld_wait();
-                    const int col = j0 + c * 32;
-                    if (!row_ok || col >= p.n_half) continue;
-                    uint32_t og[16], ou[16], oa[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        og[e] = pack_bf16x2(__uint_as_float(g[2 * e]), __uint_as_float(g[2 * e + 1]));
-                        ou[e] = pack_bf16x2(__uint_as_float(u[2 * e]), __uint_as_float(u[2 * e + 1]));
-                        const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&og[e]);
-                        const __nv_bfloat162 ub = *reinterpret_cast<const __nv_bfloat162*>(&ou[e]);
-                        const float g0 = __bfloat162float(gb.x), g1 = __bfloat162float(gb.y);
-                        const float s0 = __bfloat162float(__float2bfloat16_rn(g0 / (1.f + __expf(-g0))));
-                        const float s1 = __bfloat162float(__float2bfloat16_rn(g1 / (1.f + __expf(-g1))));
-                        oa[e] = pack_bf16x2(s0 * __bfloat162float(ub.x), s1 * __bfloat162float(ub.y));
-                    }
-                    // host guarantees n_half % 128 == 0: every 32-column chunk is whole
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        reinterpret_cast<uint4*>(gu + col)[q] = make_uint4(og[q * 4], og[q * 4 + 1], og[q * 4 + 2], og[q * 4 + 3]);
-                        reinterpret_cast<uint4*>(gu + p.n_half + col)[q] = make_uint4(ou[q * 4], ou[q * 4 + 1], ou[q * 4 + 2], ou[q * 4 + 3]);
-                        reinterpret_cast<uint4*>(act + col)[q] = make_uint4(oa[q * 4], oa[q * 4 + 1], oa[q * 4 + 2], oa[q * 4 + 3]);
-                    }
-                }
-            } else if (p.epi == EPI_SWIGLU_BWD) {
-                const __nv_bfloat16* gu = p.R + (size_t)row * p.ldr;
-                __nv_bfloat16* dgu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
-#pragma unroll 1
-                for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_row + c * 32, v);
-                    tmem_ld_wait();
-                    const int col = n0 + c * 32;
-                    if (!row_ok || col >= p.n_half) continue;
-                    // host guarantees n_half % 32 == 0
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(gu + col) + q);
-                        const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(gu + p.n_half + col) + q);
-                        const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
-                        uint32_t odg[4], odu[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&gw[e]);
-                            const __nv_bfloat162 ub = *reinterpret_cast<const __nv_bfloat162*>(&uw[e]);
-                            float dg[2], du[2];
-#pragma unroll
-                            for (int w = 0; w < 2; ++w) {
-                                const float gg = __bfloat162float(w ? gb.y : gb.x), uu = __bfloat162float(w ? ub.y : ub.x);
-                                const float da = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[q * 8 + e * 2 + w])));
-                                const float sg = 1.f / (1.f + __expf(-gg));
-                                dg[w] = da * uu * (sg * (1.f + gg * (1.f - sg)));
-                                du[w] = da * gg * sg;
-                            }
-                            odg[e] = pack_bf16x2(dg[0], dg[1]);
-                            odu[e] = pack_bf16x2(du[0], du[1]);
-                        }
-                        reinterpret_cast<uint4*>(dgu + col)[q] = make_uint4(odg[0], odg[1], odg[2], odg[3]);
-                        reinterpret_cast<uint4*>(dgu + p.n_half + col)[q] = make_uint4(odu[0], odu[1], odu[2], odu[3]);
-                    }
-                }
-            } else
-#pragma unroll 1
-            for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(t_row + c * 32, v);
-                tmem_ld_wait();
-                const int col = n0 + c * 32;
-                if (!row_ok || col >= p.N) continue;
-                const bool full = (col + 32 <= p.N);
-                if (p.epi == EPI_BF16 || p.epi == EPI_BF16_RESID) {
-                    __nv_bfloat16* dst =
-                        reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col;
-                    if (full) {
-                        uint32_t o[16];
-                        if (p.epi == EPI_BF16_RESID) {
-                            const uint4* rp =
-                                reinterpret_cast<const uint4*>(p.R + (size_t)row * p.ldr + col);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 r4 = __ldg(rp + q);
-                                const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
-                                    // match the reference's two roundings: linear output -> bf16, then add
-                                    float a0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[q * 8 + e * 2])));
-                                    float a1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[q * 8 + e * 2 + 1])));
-                                    o[q * 4 + e] = pack_bf16x2(a0 + __bfloat162float(rb.x),
-                                                               a1 + __bfloat162float(rb.y));
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e)
-                                o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-                        }
-                        uint4* dp = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            dp[q] = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
-                    } else {
-                        for (int e = 0; e < 32 && col + e < p.N; ++e) {
-                            float a = __uint_as_float(v[e]);
-                            if (p.epi == EPI_BF16_RESID)
-                                a = __bfloat162float(__float2bfloat16_rn(a)) +
-                                    __bfloat162float(p.R[(size_t)row * p.ldr + col + e]);
-                            dst[e] = __float2bfloat16_rn(a);
-                        }
-                    }
-                } else {
-                    float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col;
-                    if (full) {
-                        float4* dp = reinterpret_cast<float4*>(dst);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4 o = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
-                                                   __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
-                            if (p.epi == EPI_F32_ACCUM) {
-                                float4 old = dp[q];
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                            }
-                            dp[q] = o;
-                        }
-                    } else {
-                        for (int e = 0; e < 32 && col + e < p.N; ++e) {
-                            float a = __uint_as_float(v[e]);
-                            if (p.epi == EPI_F32_ACCUM) a += dst[e];
-                            dst[e] = a;
-                        }
-                    }
-                }
-            }
+            gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row_ok, n_blk, n0, t_row);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

@@ -12,7 +12,7 @@ void count_launch(int n = 1);
 
 // Tuning / A-B switches.  Each starts from its environment variable (SF_<NAME>, upper case) and can be changed at run time
 // through sf_debug_option() so that two settings can be alternated inside ONE process (boxes of the pool differ by +-8 %).
-enum Opt { OPT_NO_PDL, OPT_LOSS_SIDE, OPT_NO_OVERLAP, OPT_NO_SWIGLU_FUSION, OPT_GEMM_GROUP_M, OPT_GEMM_GROUP_M_MIDK, OPT_GEMM_GROUP_M_WGRAD, OPT_DFLASH_ATTN_TC, OPT_GEMM_STAGES, OPT_COUNT };
+enum Opt { OPT_NO_PDL, OPT_LOSS_SIDE, OPT_NO_OVERLAP, OPT_NO_SWIGLU_FUSION, OPT_GEMM_GROUP_M, OPT_GEMM_GROUP_M_MIDK, OPT_GEMM_GROUP_M_WGRAD, OPT_DFLASH_ATTN_TC, OPT_GEMM_STAGES, OPT_NO_TEACHER_FUSION, OPT_NO_LOSS_STATS_FUSION, OPT_GEMM_WIDE, OPT_COUNT };
 int opt(Opt o);
 
 struct GemmDesc {
@@ -25,6 +25,9 @@ struct GemmDesc {
     int cta_group;                             // 0 = auto, 1, 2
     void* D2 = nullptr; int64_t ldd2 = 0;      // EPI_SWIGLU: act output [M, I]
     int n_half = 0;                            // EPI_SWIGLU(_BWD): I
+    // EPI_BF16_STATS / EPI_TEACHER (see sf_gemm.cuh): partial row statistics [3 or 5][ceil(N/256)][M], draft-vocab gather
+    float* stats = nullptr; const uint32_t* t2d_bits = nullptr; const int* t2d_prefix = nullptr;
+    void* xg = nullptr; int S = 0, T = 0, DV = 0;
     int overlap_prev = 0;                      // 1: independent of the previous kernel in the stream — programmatic
                                                // dependent launch lets its CTAs start on the SMs the previous GEMM's tail frees
 };
@@ -71,14 +74,19 @@ int swiglu_fwd(const void* gu, void* act, int64_t M, int I, cudaStream_t st);
 int swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t M, int I, cudaStream_t st);
 int shift_left(const void* src, void* dst, int64_t B, int S, int H, cudaStream_t st);
 int add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t st);
+int embedding_gather(const void* table, int64_t V, int H, const int64_t* ids, int64_t n, void* out, cudaStream_t st);
 
 int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, const int* loss_mask, void* xg, float* tstats,
             int64_t* ids, int* position_mask, int B, int S, int T, int V, int DV, int64_t row0, int64_t nrows, int pad,
             int lean, cudaStream_t st);
+int t2d_index(const uint8_t* t2d, int V, uint32_t* bits, int* prefix, cudaStream_t st);
+int teacher_merge(const float* stats, int nb, int64_t M, const uint8_t* t2d, const int* loss_mask, float* tstats, int64_t* ids,
+                  int* position_mask, void* xg, int B, int S, int T, int DV, cudaStream_t st);
+// stats / stats_nb: optional pass-A partials [3][stats_nb][M] left by the lm_head GEMM's EPI_BF16_STATS epilogue
 int loss_step(void* logits, int64_t ld, const void* xg, const float* tstats, const int64_t* tgt_ids,
               const int* position_mask, const int* loss_mask, const int64_t* d2t, int B, int S, int T, int DV, int step,
               float step_weight, int write_grad, int lk_type, float kl_scale, float kl_decay, float* row_ws, float* metrics,
-              int lean, cudaStream_t st);
+              const float* stats, int stats_nb, cudaStream_t st);
 int grad_norm(const void* g, int64_t n, float gscale, float* partials_ws, float* out, cudaStream_t st);
 int adamw(const void* g, float* master, float* m1, float* m2, void* param, int64_t n, const float* gnorm, float max_norm,
           float gscale, float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st);

@@ -155,6 +155,62 @@ teacher_pad_kernel(__nv_bfloat16* __restrict__ xg, float4* __restrict__ tstats, 
     }
 }
 
+// ---- teacher statistics fused into the target-head GEMM epilogue (EPI_TEACHER, sf_gemm.cuh) ----
+// t2d (uint8 [V]) -> bit words + exclusive prefix counts per 32-column word: the epilogue appends the flagged columns of a
+// chunk at xg[row, prefix[word] ...] (vocabulary order = the order of the reference's boolean-mask gather, model.py:492).
+__global__ void __launch_bounds__(1024) t2d_index_kernel(const uint8_t* __restrict__ t2d, int V, uint32_t* __restrict__ bits,
+                                                         int* __restrict__ prefix) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    const int nwords = (V + 31) / 32;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nwords; base += 1024) {
+        const int w = base + threadIdx.x;
+        uint32_t b = 0;
+        if (w < nwords)
+            for (int e = 0; e < 32; ++e) { const int c = w * 32 + e; if (c < V && t2d[c]) b |= 1u << e; }
+        const int cnt = __popc(b);
+        int incl = cnt;                                  // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int i = 0; i < (int)(threadIdx.x >> 5); ++i) woff += wsum[i];
+        const int carry = carry_s;
+        if (w < nwords) { bits[w] = b; prefix[w] = carry + woff + incl - cnt; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+}
+// One thread per row: combines the per-n-block partials (ascending n-block order; strict > keeps the first index) and writes
+// what teacher_kernel writes: tstats = {md, 1/dd, dd * exp(md - lse_full), 0}, ids, position_mask.
+__global__ void __launch_bounds__(256)
+teacher_merge_kernel(const float* __restrict__ stats, int nb, int64_t M, const uint8_t* __restrict__ t2d,
+                     const int* __restrict__ loss_mask, float4* __restrict__ tstats, int64_t* __restrict__ ids,
+                     int* __restrict__ position_mask, int S, int T) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const size_t plane = (size_t)nb * M;
+    float m = -INFINITY, d = 0.f, md = -INFINITY, dd = 0.f;
+    int idx = 0x7fffffff;
+    for (int b = 0; b < nb; ++b) {
+        const float* sp = stats + (size_t)b * M + r;
+        const float pm = sp[0], pd = sp[plane], pmd = sp[3 * plane], pdd = sp[4 * plane];
+        if (pm > m) { d = d * __expf(m - pm) + pd; m = pm; idx = __float_as_int(sp[2 * plane]); }
+        else d += pd * __expf(pm - m);
+        if (pmd > md) { dd = dd * __expf(md - pmd) + pdd; md = pmd; }
+        else if (pmd > -INFINITY) dd += pdd * __expf(pmd - md);
+    }
+    const float lse = m + logf(d);
+    const int64_t orow = r + (r / S) * T;
+    tstats[orow] = make_float4(md, 1.f / dd, dd * __expf(md - lse), 0.f);
+    ids[orow] = idx;
+    position_mask[r] = (t2d[idx] ? 1 : 0) * loss_mask[r];
+}
+
 // ------------------------------------------------------------------ fused loss / metrics / gradient
 // Reference: core/loss.py:15-21,49-170 (soft-label CE, mean over ALL rows, in-place backward),
 // core/lk_loss.py:43-80 (acceptance = sum_v min(p_on_draft, softmax)), eagle3/model.py:161-173 (top-1).
@@ -175,6 +231,7 @@ struct LossParams {
     float grad_coef;      // ploss_decay^step * upstream / M
     int write_grad;
     float* row_loss; float* row_accept; float* row_correct;  // [M]
+    const float* stats; int stats_nb;   // optional pass-A partials from the lm_head GEMM epilogue (EPI_BF16_STATS): [3][nb][M]
 };
 
 __global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
@@ -195,9 +252,28 @@ __global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
         if (threadIdx.x == 0) { p.row_loss[r] = 0.f; p.row_accept[r] = 0.f; p.row_correct[r] = 0.f; }
         return;
     }
-    // pass A: online max / sum-exp, first-index argmax
+    // pass A: online max / sum-exp, first-index argmax — either merged from the partials the lm_head GEMM epilogue left
+    // (no read of the logits row at all) or computed here from the row
     MaxIdx mi{-INFINITY, 0x7fffffff};
     float d = 0.f;
+    if (p.stats) {
+        if (warp == 0) {
+            const size_t plane = (size_t)p.stats_nb * p.M;
+            for (int nb = lane; nb < p.stats_nb; nb += 32) {          // ascending n-blocks per lane
+                const float* sp = p.stats + (size_t)nb * p.M + r;
+                const float pm = __ldg(sp), pd = __ldg(sp + plane);
+                if (pm > mi.v) { d = d * __expf(mi.v - pm) + pd; mi.v = pm; mi.i = __float_as_int(__ldg(sp + 2 * plane)); }
+                else d += pd * __expf(pm - mi.v);
+            }
+            const float my_m = mi.v;
+            mi = warp_argmax(mi);                                     // equal maxima: the smaller index wins
+            d = warp_sum(my_m == -INFINITY ? 0.f : d * __expf(my_m - mi.v));
+            if (lane == 0) { redv[0] = mi.v; redi[0] = mi.i; redd[0] = d; }
+        }
+        __syncthreads();
+        mi.v = redv[0]; mi.i = redi[0]; d = redd[0];
+        __syncthreads();   // red* are reused below
+    } else {
 #pragma unroll 4
     for (int c = threadIdx.x; c < nch; c += 512) {
         float f[8];
@@ -221,6 +297,7 @@ __global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
         mi = warp_argmax(t);
         d = warp_sum(t.v == -INFINITY ? 0.f : td * __expf(t.v - mi.v));
         __syncthreads();   // red* are reused below
+    }
     }
     const float m = mi.v;
     const float inv_d = 1.f / d;
@@ -497,10 +574,27 @@ int teacher(const void* tl, int64_t ld, const int* d2t_idx, const uint8_t* t2d, 
     return 0;
 }
 
+int t2d_index(const uint8_t* t2d, int V, uint32_t* bits, int* prefix, cudaStream_t st) {
+    t2d_index_kernel<<<1, 1024, 0, st>>>(t2d, V, bits, prefix);
+    SF_CUDA_CHECK_LAUNCH("t2d_index");
+    return 0;
+}
+int teacher_merge(const float* stats, int nb, int64_t M, const uint8_t* t2d, const int* loss_mask, float* tstats, int64_t* ids,
+                  int* position_mask, void* xg, int B, int S, int T, int DV, cudaStream_t st) {
+    teacher_merge_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(stats, nb, M, t2d, loss_mask, reinterpret_cast<float4*>(tstats),
+                                                                    ids, position_mask, S, T);
+    SF_CUDA_CHECK_LAUNCH("teacher_merge");
+    if (T > 0) {
+        teacher_pad_kernel<<<sm_count(), 256, 0, st>>>((__nv_bfloat16*)xg, reinterpret_cast<float4*>(tstats), ids, B, S, T, DV);
+        SF_CUDA_CHECK_LAUNCH("teacher_pad");
+    }
+    return 0;
+}
+
 int loss_step(void* logits, int64_t ld, const void* xg, const float* tstats, const int64_t* tgt_ids,
               const int* position_mask, const int* loss_mask, const int64_t* d2t, int B, int S, int T, int DV, int step,
               float step_weight, int write_grad, int lk_type, float kl_scale, float kl_decay, float* row_ws, float* metrics,
-              int lean, cudaStream_t st) {
+              const float* stats, int stats_nb, cudaStream_t st) {
     if (DV % 8 || ld % 8) return set_error(-22, "loss: draft vocab %d / ld must be multiples of 8", DV);
     LossParams p;
     p.logits = (__nv_bfloat16*)logits; p.ld = ld; p.xg = (const __nv_bfloat16*)xg; p.tstats = reinterpret_cast<const float4*>(tstats);
@@ -510,7 +604,7 @@ int loss_step(void* logits, int64_t ld, const void* xg, const float* tstats, con
     p.M = M;
     p.grad_coef = step_weight / (float)M; p.write_grad = (lk_type == 0) ? write_grad : 0;
     p.row_loss = row_ws; p.row_accept = row_ws + M; p.row_correct = row_ws + 2 * M;
-    (void)lean;
+    p.stats = stats; p.stats_nb = stats_nb;
     loss_kernel<<<(unsigned)M, 512, 0, st>>>(p);
     SF_CUDA_CHECK_LAUNCH("loss");
     metrics_reduce_kernel<<<1, 1024, 0, st>>>(p.row_loss, p.row_accept, p.row_correct, position_mask, loss_mask, B, S, step,

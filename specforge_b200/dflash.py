@@ -246,16 +246,19 @@ class DFlashEngine:
               "sf_grads_to_bf16")
         return self.grads_bf16
 
+    def ensure_optimizer_state(self) -> None:
+        if self.master is None:
+            self.master = self.params.float()
+            self.exp_avg = torch.zeros_like(self.master)
+            self.exp_avg_sq = torch.zeros_like(self.master)
+
     def optimizer_step(self, lr: float, *, grad_scale: float = 1.0, max_grad_norm: float = 0.5, betas=(0.9, 0.999), eps: float = 1e-8,
                        weight_decay: float = 0.0) -> torch.Tensor:
         """Fused clip + AdamW on the flat buffers (optimizer.py:95-168 semantics, see sf_optimizer_step)."""
         L = lib()
         L.sf_optimizer_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                         c_float, c_float, c_float, ctypes.c_int, c_void_p, c_void_p, c_void_p]
-        if self.master is None:
-            self.master = self.params.float()
-            self.exp_avg = torch.zeros_like(self.master)
-            self.exp_avg_sq = torch.zeros_like(self.master)
+        self.ensure_optimizer_state()
         self.opt_step += 1
         check(L.sf_optimizer_step(self.grads_bf16.data_ptr(), self.master.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                   self.params.data_ptr(), self.n_params, grad_scale, max_grad_norm, lr, betas[0], betas[1], eps, weight_decay,

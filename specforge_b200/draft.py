@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from .engine import DraftDims, Eagle3Engine, P_NAMES
+from .optimizer import REFERENCE_PARAM_ORDER
 
 
 def dims_from_config(config: Any) -> DraftDims:
@@ -55,11 +56,9 @@ class B200Eagle3DraftModel(nn.Module):
         self.engine: Optional[Eagle3Engine] = None
         d = self.dims
         # placeholders with the reference shapes; re-pointed into the engine's flat buffer by bind_engine()
-        self._param_names = []
-        for name in P_NAMES:
-            if name.startswith("fc_norm") and not d.fc_norm:
-                continue
-            self._param_names.append(name)
+        # registered in the order the reference module yields its parameters (so `parameters()` / optimizer state line up
+        # with LlamaForCausalLMEagle3); the physical order inside the flat buffer is the engine's (P_NAMES)
+        self._param_names = [n for n in REFERENCE_PARAM_ORDER if n in P_NAMES and (d.fc_norm or not n.startswith("fc_norm"))]
         self.embed_tokens_weight = nn.Parameter(torch.empty(0), requires_grad=False)
         self.register_buffer("t2d", torch.ones(d.vocab_size, dtype=torch.bool))
         self.register_buffer("d2t", torch.zeros(d.draft_vocab_size, dtype=torch.int64))
@@ -95,8 +94,10 @@ class B200Eagle3DraftModel(nn.Module):
 
     # ---- engine binding -------------------------------------------------------------------------------
     def bind_engine(self, batch: int, seq_len: int, ttt_length: int, ploss_decay: float = 0.8, device=None,
-                    init_std: float = 0.02, seed: int = 0) -> Eagle3Engine:
-        eng = Eagle3Engine(self.dims, batch=batch, seq_len=seq_len, ttt_length=ttt_length, ploss_decay=ploss_decay, device=device)
+                    init_std: float = 0.02, seed: int = 0, lk_loss_type: Optional[str] = None, kl_scale: float = 1.0,
+                    kl_decay: float = 1.0) -> Eagle3Engine:
+        eng = Eagle3Engine(self.dims, batch=batch, seq_len=seq_len, ttt_length=ttt_length, ploss_decay=ploss_decay,
+                           lk_loss_type=lk_loss_type, kl_scale=kl_scale, kl_decay=kl_decay, device=device)
         g = torch.Generator(device="cpu").manual_seed(seed)
         for name in self._param_names:
             view = eng.param_view(name)
@@ -119,14 +120,15 @@ class B200Eagle3DraftModel(nn.Module):
         return [self._flat_params[n] for n in self._param_names]
 
     # ---- reference-named state dict ---------------------------------------------------------------------
-    def state_dict(self, *args, **kwargs) -> Dict[str, torch.Tensor]:  # noqa: D401 - reference key layout
-        out = {"embed_tokens.weight": self.embed_tokens_weight.detach()}
+    def state_dict(self, *args, destination=None, prefix: str = "", keep_vars: bool = False):  # reference key layout
+        out = destination if destination is not None else {}
+        out[prefix + "t2d"], out[prefix + "d2t"] = self.t2d, self.d2t
+        out[prefix + "embed_tokens.weight"] = self.embed_tokens_weight if keep_vars else self.embed_tokens_weight.detach()
         for n in self._param_names:
-            out[n] = self._flat_params[n].detach()
-        out["t2d"], out["d2t"] = self.t2d, self.d2t
+            out[prefix + n] = self._flat_params[n] if keep_vars else self._flat_params[n].detach()
         return out
 
-    def load_state_dict(self, state: Dict[str, torch.Tensor], strict: bool = True):
+    def load_state_dict(self, state: Dict[str, torch.Tensor], strict: bool = True, assign: bool = False):
         missing = []
         with torch.no_grad():
             for n in self._param_names:
@@ -143,7 +145,11 @@ class B200Eagle3DraftModel(nn.Module):
             raise KeyError(f"missing keys in draft state dict: {missing}")
         if self.engine is not None:
             self.engine.master = None  # fp32 masters are re-derived from the loaded weights
-        return missing
+        self._resync_frozen()
+        spec = self.state_dict_spec()
+        missing += [k for k in ("embed_tokens.weight", "t2d", "d2t") if k not in state]
+        unexpected = [k for k in state if k not in spec and "rotary_emb" not in k]    # RoPE buffers are non-persistent upstream
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     # ---- Eagle3DraftModel helpers -----------------------------------------------------------------------
     def freeze_embedding(self) -> None:
@@ -171,17 +177,129 @@ class B200Eagle3DraftModel(nn.Module):
         else:
             w = torch.load(path, map_location="cpu")[embedding_key]
         self.embed_tokens_weight.data = w.to(self.embed_tokens_weight.device, torch.bfloat16).contiguous()
+        self._resync_frozen()
 
     def load_vocab_mapping(self, file_path: str) -> None:
         m = torch.load(file_path)
         self.t2d.copy_(m["t2d"])
         self.d2t.copy_(m["d2t"])
         self.vocab_mapping_loaded = True
+        self._resync_frozen()
 
     def sync_frozen(self, target_head_weight: torch.Tensor) -> None:
         """Hand the frozen tables (embedding, target head, vocab map) to the engine."""
+        self._target_head_weight = target_head_weight
         self.engine.set_frozen(embed_tokens=self.embed_tokens_weight.data, target_head=target_head_weight, t2d=self.t2d, d2t=self.d2t)
 
-    def forward(self, *args, **kwargs):
-        raise RuntimeError("B200Eagle3DraftModel has no eager forward: drive it through B200Eagle3TrainStrategy.forward_loss "
-                           "(the CUDA path has no PyTorch fallback)")
+    def _resync_frozen(self) -> None:
+        """The engine holds its own copies of the frozen tables (the vocab map as bytes): refresh them whenever a loader
+        rebinds the embedding or rewrites t2d / d2t after the strategy was built (resume, load_embedding, load_vocab_mapping)."""
+        head = getattr(self, "_target_head_weight", None)
+        if self.engine is not None and head is not None:
+            self.sync_frozen(head)
+
+    # ---- Eagle3DraftModel forward surface (modeling/draft/base.py:45-109, llama3_eagle.py:1705-1798), forward-only -------------
+    # Each method is a few calls of the exported C-ABI ops (sf_embedding_gather, sf_rmsnorm_fwd, sf_gemm_bf16, sf_rope,
+    # sf_ttt_attention_fwd, sf_swiglu_fwd) on this module's weights: what eval utilities / export sanity checks call outside
+    # the training step.  No autograd — training goes through B200Eagle3TrainStrategy.forward_loss.
+    def _w(self, name: str) -> torch.Tensor:
+        return self._flat_params[name].detach()
+
+    @torch.no_grad()
+    def embed_input_ids(self, input_ids: torch.Tensor) -> torch.Tensor:
+        from . import ops
+        ids = input_ids.to(self.embed_tokens_weight.device, torch.int64).contiguous()
+        out = ops.embedding_gather(self.embed_tokens_weight.data, ids.view(-1))
+        return out.view(*ids.shape, self.dims.hidden_size)
+
+    @torch.no_grad()
+    def project_hidden_states(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        from . import ops
+        d = self.dims
+        assert hidden_states.size(-1) == d.target_hidden_size * 3
+        lead = hidden_states.shape[:-1]
+        x = hidden_states.to(torch.bfloat16).reshape(-1, 3 * d.target_hidden_size).contiguous()
+        if d.fc_norm:
+            y = torch.empty_like(x)
+            for i in range(3):
+                sl = slice(i * d.target_hidden_size, (i + 1) * d.target_hidden_size)
+                ops.rmsnorm_fwd(x[:, sl], self._w(f"fc_norm.{i}.weight"), d.rms_norm_eps, out=y[:, sl])
+            x = y
+        return ops.gemm(x, self._w("fc.weight")).view(*lead, d.hidden_size)
+
+    @torch.no_grad()
+    def compute_logits(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        from . import ops
+        d = self.dims
+        lead = hidden_states.shape[:-1]
+        x = hidden_states.to(torch.bfloat16).reshape(-1, d.hidden_size).contiguous()
+        if d.norm_output:
+            x = ops.rmsnorm_fwd(x, self._w("norm.weight"), d.rms_norm_eps)
+        return ops.gemm(x, self._w("lm_head.weight")).view(*lead, d.draft_vocab_size)
+
+    @staticmethod
+    def _key_mask(attention_mask, B: int, S: int, device) -> Optional[torch.Tensor]:
+        """[B, S] byte key-padding mask from either the collator's [B, S] mask or the reference's additive [B, 1, S, S] decoder
+        mask (prepare_decoder_attention_mask): its last query row leaves exactly the non-padded keys unmasked."""
+        if attention_mask is None:
+            return None
+        if attention_mask.dim() == 4:
+            km = attention_mask[:, 0, -1, :] == 0
+        else:
+            km = attention_mask.reshape(B, S) != 0
+        return km.to(device=device, dtype=torch.uint8).contiguous()
+
+    @torch.no_grad()
+    def backbone(self, input_embeds: torch.Tensor, hidden_states: torch.Tensor, cache_hidden, attention_mask, position_ids,
+                 past_key_values=None, use_cache: bool = True) -> torch.Tensor:
+        """One decoder-layer pass at TTT step j = len(cache_hidden[0]) (llama3_eagle.py:1625-1650, attention :717-785).  The K / V
+        appended to `cache_hidden` are views of this step's fused, RoPE-rotated [q;k;v] buffer, which later steps read back."""
+        from . import ops
+        d = self.dims
+        B, S, H = hidden_states.shape
+        dev = self.embed_tokens_weight.device
+        if cache_hidden is None:
+            cache_hidden = [[], []]
+        j = len(cache_hidden[0])
+        if position_ids is not None:
+            pos = position_ids.reshape(-1, S)[0]
+            if not torch.equal(pos.to(dev), torch.arange(S, device=dev)):
+                raise NotImplementedError("backbone: only the default position_ids = arange(seq) is implemented on the CUDA path")
+        nh, nkv, hd = d.num_heads, d.num_kv_heads, d.head_dim
+        A, KV = nh * hd, nkv * hd
+        emb = input_embeds.to(dev, torch.bfloat16).reshape(B * S, H).contiguous()
+        h = hidden_states.to(dev, torch.bfloat16).reshape(B * S, H).contiguous()
+        xcat = torch.empty(B * S, 2 * H, dtype=torch.bfloat16, device=dev)
+        ops.rmsnorm_fwd(emb, self._w("midlayer.input_layernorm.weight"), d.rms_norm_eps, out=xcat[:, :H])
+        ops.rmsnorm_fwd(h, self._w("midlayer.hidden_norm.weight"), d.rms_norm_eps, out=xcat[:, H:])
+        o0 = self.engine.offsets["midlayer.self_attn.q_proj.weight"]
+        wqkv = self.engine.params[o0:o0 + (A + 2 * KV) * 2 * H].view(A + 2 * KV, 2 * H)     # physically fused [q;k;v]
+        qkv = ops.gemm(xcat, wqkv)
+        ops.rope_(qkv, nh + nkv, hd, self.engine.rope_cos, self.engine.rope_sin, S, j, inverse=False)
+        blocks = []
+        for kview in cache_hidden[0]:
+            base = kview._base if kview._base is not None else kview
+            if base.dim() != 2 or base.shape != (B * S, A + 2 * KV):
+                raise ValueError("backbone: cache_hidden entries must be the K/V views this method appended at earlier steps")
+            blocks.append(base)
+        blocks.append(qkv)
+        cache_hidden[0].append(qkv.view(B, S, nh + 2 * nkv, hd)[:, :, nh:nh + nkv].permute(0, 2, 1, 3))
+        cache_hidden[1].append(qkv.view(B, S, nh + 2 * nkv, hd)[:, :, nh + nkv:].permute(0, 2, 1, 3))
+        attn, _ = ops.ttt_attention_fwd(blocks, B, S, nh, nkv, hd, key_mask=self._key_mask(attention_mask, B, S, dev))
+        hmid = ops.gemm(attn, self._w("midlayer.self_attn.o_proj.weight"), residual=h, epi=ops.EPI_BF16_RESID)
+        hn2 = ops.rmsnorm_fwd(hmid, self._w("midlayer.post_attention_layernorm.weight"), d.rms_norm_eps)
+        og = self.engine.offsets["midlayer.mlp.gate_proj.weight"]
+        wgu = self.engine.params[og:og + 2 * d.intermediate_size * H].view(2 * d.intermediate_size, H)   # fused [gate;up]
+        act = ops.swiglu_fwd(ops.gemm(hn2, wgu))
+        out = ops.gemm(act, self._w("midlayer.mlp.down_proj.weight"), residual=hmid, epi=ops.EPI_BF16_RESID)
+        return out.view(B, S, H)
+
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, inputs_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                ttt_length: int = 1):
+        """LlamaForCausalLMEagle3.forward (llama3_eagle.py:1705-1757): fc -> one decoder layer -> norm, forward-only."""
+        from . import ops
+        B, S, _ = hidden_states.shape
+        h = self.project_hidden_states(hidden_states)
+        h = self.backbone(inputs_embeds, h, None if ttt_length == 1 else [[], []], attention_mask, None)
+        return ops.rmsnorm_fwd(h.reshape(B * S, -1), self._w("norm.weight"), self.dims.rms_norm_eps).view(B, S, -1)

@@ -408,12 +408,16 @@ class Eagle3Engine:
                                      self._stream()), "sf_grads_to_bf16")
         return self.grads_bf16
 
-    def optimizer_step(self, lr: float, *, grad_scale: float = 1.0, max_grad_norm: float = 0.5, betas=(0.9, 0.999),
-                       eps: float = 1e-8, weight_decay: float = 0.0) -> torch.Tensor:
+    def ensure_optimizer_state(self) -> None:
+        """fp32 masters (cloned from the bf16 weights, optimizer.py:33-41) and zeroed AdamW moments, allocated on first use."""
         if self.master is None:
             self.master = self.params.float()
             self.exp_avg = torch.zeros_like(self.master)
             self.exp_avg_sq = torch.zeros_like(self.master)
+
+    def optimizer_step(self, lr: float, *, grad_scale: float = 1.0, max_grad_norm: float = 0.5, betas=(0.9, 0.999),
+                       eps: float = 1e-8, weight_decay: float = 0.0) -> torch.Tensor:
+        self.ensure_optimizer_state()
         self.opt_step += 1
         check(lib().sf_optimizer_step(self.grads_bf16.data_ptr(), self.master.data_ptr(), self.exp_avg.data_ptr(),
                                       self.exp_avg_sq.data_ptr(), self.params.data_ptr(), self.n_params, grad_scale,

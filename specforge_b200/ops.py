@@ -95,9 +95,22 @@ def _declare_ops():
     return l
 
 
-def rmsnorm_fwd(x, w, eps):
+def embedding_gather(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """out[i] = table[ids[i]]  (frozen-embedding lookup, llama3_eagle.py:1759-1760)."""
+    import ctypes
+    l = lib()
+    l.sf_embedding_gather.restype = ctypes.c_int
+    out = torch.empty(ids.numel(), table.shape[1], dtype=table.dtype, device=table.device)
+    check(l.sf_embedding_gather(ctypes.c_void_p(table.data_ptr()), ctypes.c_int64(table.shape[0]), table.shape[1],
+                                ctypes.c_void_p(ids.data_ptr()), ctypes.c_int64(ids.numel()), ctypes.c_void_p(out.data_ptr()),
+                                ctypes.c_void_p(_stream())), "sf_embedding_gather")
+    return out
+
+
+def rmsnorm_fwd(x, w, eps, out=None):
     l = _declare_ops()
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
     check(l.sf_rmsnorm_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1],
                            eps, _stream()), "sf_rmsnorm_fwd")
     return out

@@ -52,22 +52,42 @@ class B200Eagle3TrainStrategy:
     name = "eagle3"
     required_features = {"input_ids", "attention_mask", "loss_mask", "hidden_state", "target"}
 
-    def __init__(self, draft_model: B200Eagle3DraftModel, *, target_head_weight: torch.Tensor, ploss_decay: float = 0.8,
+    def __init__(self, draft_model, *, target_head_weight: Optional[torch.Tensor] = None, target_head: Optional[nn.Module] = None,
+                 ploss_decay: float = 0.8, compact_teacher: bool = False, compact_teacher_chunk_size: Optional[int] = None,
                  return_autograd_grads: bool = False):
-        if draft_model.engine is None:
+        """`draft_model`: the B200 draft module, or the composite the reference hands a step provider (anything exposing
+        `.draft_model`, algorithms/eagle3/providers.py:45-52).  The frozen head is `target_head_weight` [V, H_t] or the
+        reference's `TargetHead` module (its `fc.weight`, modeling/target/target_head.py:100-101).
+        `compact_teacher` / `compact_teacher_chunk_size` (strategies/base.py:148-215) are accepted and need nothing: the teacher
+        statistics are always streamed inside the target-head GEMM epilogue, the [B, S, V] logits never exist on this path."""
+        composite = draft_model if hasattr(draft_model, "draft_model") else None
+        if composite is not None:
+            draft_model = composite.draft_model
+        if getattr(draft_model, "engine", None) is None:
             raise RuntimeError("bind_engine() must be called on the draft model first")
+        if target_head_weight is None:
+            if target_head is None:
+                raise ValueError("target_repr='hidden_state' requires a target_head to re-run the lm_head projection")
+            target_head_weight = target_head.fc.weight.detach()
+        self.compact_teacher = bool(compact_teacher)
+        self.compact_teacher_chunk_size = compact_teacher_chunk_size
+        self.target_head = target_head
         self.draft_model = draft_model
         self.engine = draft_model.engine
         if abs(self.engine.ploss_decay - ploss_decay) > 1e-12:
             raise ValueError("ploss_decay differs from the value the engine was bound with")
         self.ploss_decay = ploss_decay
         self.return_autograd_grads = return_autograd_grads
-        self._module = _Trainable(draft_model)
+        self._module = composite if composite is not None else _Trainable(draft_model)
+        self.eagle3_model = self._module
         self._micro_in_window = 0
         self._last_grad_out: Optional[torch.Tensor] = None
         self._is_boundary = True            # set by the backend before loss.backward()
         self.grad_ready_hook = None         # backend: called with (first_elem, n_elems) as gradient slices complete
         draft_model.sync_frozen(target_head_weight)
+        backend = getattr(draft_model, "_b200_backend", None)   # a backend prepared before us (Trainer order, trainer.py:421-431)
+        if backend is not None:
+            backend.attach(self)
 
     def trainable_module(self) -> nn.Module:
         return self._module
@@ -79,9 +99,12 @@ class B200Eagle3TrainStrategy:
 
     def forward_loss(self, batch: TrainBatch, ctx: Optional[StepContext] = None) -> StepOutput:
         self.validate_batch(batch)
-        target_repr = batch.metadata.get("target_repr", "hidden_state")
+        target_repr = batch.metadata.get("target_repr", "hidden_state") or "hidden_state"
         if target_repr != "hidden_state":
-            raise ValueError(f"target_repr={target_repr!r}: the CUDA path implements the offline hidden-state teacher only")
+            if self.compact_teacher:
+                raise ValueError("compact teacher is offline-only and requires target_repr='hidden_state'")
+            raise ValueError(f"target_repr={target_repr!r}: the CUDA path implements the offline hidden-state teacher only "
+                             "(online 'logits' / 'pruned_logits' capture is outside the replaced hot path)")
         need_grad = torch.is_grad_enabled()
         eng = self.engine
         flat = eng.params if not need_grad else eng.params.detach().requires_grad_(True)
@@ -102,4 +125,6 @@ class B200Eagle3TrainStrategy:
     def checkpoint_state_filter(self, state_dict: Dict[str, Any]) -> Dict[str, Any]:
         """Same rule as the reference (strategies/base.py:306-319): draft weights without the `draft_model.` prefix,
         frozen embedding dropped."""
-        return {k.replace("draft_model.", ""): v for k, v in state_dict.items() if "embed" not in k.lower()}
+        prefixed = any("draft_model." in k for k in state_dict)     # composite state dict vs the bare draft module's
+        return {k.replace("draft_model.", ""): v for k, v in state_dict.items()
+                if (not prefixed or "draft_model." in k) and "embed" not in k.lower()}

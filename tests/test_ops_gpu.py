@@ -44,6 +44,71 @@ def test_gemm(G, am, bm, M, N, K, epi):
     assert (got - ref).abs().max().item() <= tol * scale * (2 if epi == 1 else 1) + 1e-4
 
 
+def _set_opt(name, value):
+    from specforge_b200._lib import lib
+    L = lib()
+    L.sf_debug_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    assert L.sf_debug_option(name, value) == 0
+
+
+@pytest.mark.parametrize("am,bm", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K,epi", [(1024, 768, 320, 0), (1000, 776, 1096, 1), (520, 264, 200, 3), (2048, 512, 4160, 2)])
+def test_gemm_wide_tiling(am, bm, M, N, K, epi):
+    """The 512 x 256 tiling (sf_gemm_wide.cuh; forced with gemm_wide = 2) against the fp32 reference and, bit for bit, against
+    the 256 x 256 tiling: every output element accumulates the same K sequence in the same order in both."""
+    from specforge_b200 import ops
+    torch.manual_seed(1)
+    dev = _dev()
+    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+    a = A if am == 0 else A.t().contiguous()
+    b = B if bm == 0 else B.t().contiguous()
+    ref = A.float() @ B.float().t()
+    R = out0 = None
+    if epi == 1:
+        R = torch.randn(M, N, device=dev).bfloat16()
+        ref = ref.bfloat16().float() + R.float()
+    if epi == 3:
+        out0 = torch.randn(M, N, device=dev)
+        ref = ref + out0
+    outs = {}
+    try:
+        for wide in (-1, 2):
+            _set_opt(b"gemm_wide", wide)
+            outs[wide] = ops.gemm(a, b, a_major=am, b_major=bm, out=None if out0 is None else out0.clone(), residual=R, epi=epi)
+            torch.cuda.synchronize()
+    finally:
+        _set_opt(b"gemm_wide", 0)
+    got = outs[2].float()
+    tol = 1e-5 if epi >= 2 else 2 ** -7
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= tol * scale * (2 if epi == 1 else 1) + 1e-4
+    assert torch.equal(outs[2], outs[-1])
+
+
+def test_gemm_wide_fused_epilogues():
+    """SwiGLU forward / backward epilogues and the row-statistics epilogue under the 512 x 256 tiling == the 256 x 256 tiling."""
+    from specforge_b200 import ops
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(3)
+    M, H, I = 1536, 512, 1280
+    x = torch.randn(M, H, device=dev, generator=g).bfloat16()
+    w = (torch.randn(2 * I, H, device=dev, generator=g) * H ** -0.5).bfloat16()
+    dy = (torch.randn(M, H, device=dev, generator=g) * 0.1).bfloat16()
+    wd = (torch.randn(H, I, device=dev, generator=g) * I ** -0.5).bfloat16()
+    res = {}
+    try:
+        for wide in (-1, 2):
+            _set_opt(b"gemm_wide", wide)
+            gu, act = ops.gemm_swiglu(x, w)
+            res[wide] = (gu, act, ops.gemm_swiglu_bwd(dy, wd, gu))
+            torch.cuda.synchronize()
+    finally:
+        _set_opt(b"gemm_wide", 0)
+    for t2, t1 in zip(res[2], res[-1]):
+        assert torch.equal(t2, t1)
+
+
 def test_gemm_step_shapes():
     """The shapes the headline step runs that the small cases above do not reach: the K = T*M = 114 688 weight-gradient
     contraction (MN-major x MN-major, fp32 accumulate in TMEM, EPI_F32_ACCUM) and an N = 151 936 target-head row block."""

