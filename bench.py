@@ -77,9 +77,90 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
+def _reference_dir():
+    d = os.path.join(ROOT, "baseline", "_ref")
+    return d if os.path.isdir(os.path.join(d, "specforge")) else None
+
+
+def reference_cpu_step_rate(steps: int, warmup: int):
+    """The UNMODIFIED reference (offline install baseline/_ref) on the host cores, same configuration as the GPU
+    arm except the batch: Eagle3TrainStrategy.forward_loss -> TargetHead -> OnlineEagle3Model(sdpa) -> LlamaForCausalLMEagle3 ->
+    backward -> BF16Optimizer.step, Qwen3-8B draft dims, B = 1 sequence x S = 2048 tokens, TTT = 7, bf16 modules.  Two shims, the ones
+    the reference's own CPU tests use: TORCHDYNAMO_DISABLE=1 and LogSoftmaxLoss -> the reference's torch twin
+    _compute_loss (its Triton kernel cannot launch without a GPU).  Returns (samples/s, ms/step, threads)."""
+    os.environ["TORCHDYNAMO_DISABLE"] = "1"
+    ref = _reference_dir()
+    sys.path.insert(0, ref)
+    import tempfile
+    import torch
+    cores = min(os.cpu_count() or 1, CPU_MAX_THREADS)
+    torch.set_num_threads(cores)
+    import specforge.algorithms.eagle3.model as ref_model
+    from specforge.core.loss import _compute_loss
+
+    class _TorchLogSoftmaxLoss:
+        @staticmethod
+        def apply(logits, target_p, position_mask):
+            return _compute_loss(logits, target_p, position_mask)
+
+    ref_model.LogSoftmaxLoss = _TorchLogSoftmaxLoss
+    from transformers import LlamaConfig
+    from specforge.algorithms.eagle3.model import OnlineEagle3Model
+    from specforge.modeling.draft.llama3_eagle import LlamaForCausalLMEagle3
+    from specforge.modeling.target.target_head import TargetHead
+    from specforge.optimizer import BF16Optimizer
+    from specforge.runtime.contracts import TrainBatch
+    from specforge.training.strategies.base import Eagle3TrainStrategy
+    c = QWEN3_8B
+    hf = LlamaConfig(hidden_size=c["hidden_size"], intermediate_size=c["intermediate_size"], num_attention_heads=c["num_heads"],
+                     num_key_value_heads=c["num_kv_heads"], num_hidden_layers=1, vocab_size=c["vocab_size"], rms_norm_eps=c["rms_norm_eps"],
+                     max_position_embeddings=c["max_position_embeddings"], hidden_act="silu", tie_word_embeddings=False, pad_token_id=0,
+                     rope_theta=c["rope_theta"])
+    hf.head_dim, hf.draft_vocab_size, hf.rope_theta = c["head_dim"], c["draft_vocab_size"], c["rope_theta"]
+    torch.manual_seed(0)
+    draft = LlamaForCausalLMEagle3(hf, attention_backend="sdpa")
+    g = torch.Generator().manual_seed(0)
+    V, H, DV = c["vocab_size"], c["hidden_size"], c["draft_vocab_size"]
+    ids = torch.randperm(V, generator=g)[:DV].sort().values
+    draft.t2d.zero_()
+    draft.t2d[ids] = True
+    draft.d2t.copy_(ids - torch.arange(DV))
+    draft = draft.to(torch.bfloat16)
+    draft.freeze_embedding()
+    model = OnlineEagle3Model(draft_model=draft, length=T, attention_backend="sdpa")
+    with tempfile.TemporaryDirectory() as wd:
+        with open(os.path.join(wd, "config.json"), "w") as f:
+            json.dump({"architectures": ["LlamaForCausalLM"], "model_type": "llama", "hidden_size": H, "vocab_size": V,
+                       "num_hidden_layers": 1, "num_attention_heads": 4, "intermediate_size": 128}, f)
+        head = TargetHead(wd)
+    with torch.no_grad():
+        head.fc.weight.copy_(torch.randn(V, H, generator=g))
+    head.freeze_weights()
+    head = head.eval().to(torch.bfloat16)
+    strategy = Eagle3TrainStrategy(model, target_head=head, ploss_decay=0.8)
+    opt = BF16Optimizer(draft, lr=1e-4, max_grad_norm=0.5, total_steps=100000, warmup_ratio=0.015)
+    times = []
+    for it in range(warmup + steps):
+        gi = torch.Generator().manual_seed(100 + it)
+        t = {"input_ids": torch.randint(0, V, (1, S), generator=gi), "attention_mask": torch.ones(1, S, dtype=torch.long),
+             "loss_mask": torch.ones(1, S, dtype=torch.long), "hidden_state": torch.randn(1, S, 3 * H, generator=gi).bfloat16(),
+             "target": torch.randn(1, S, H, generator=gi).bfloat16()}
+        t["loss_mask"][:, -1] = 0
+        tb = TrainBatch(sample_ids=["0"], strategy="eagle3", tensors=t, metadata={"target_repr": "hidden_state"})
+        t0 = time.perf_counter()
+        out = strategy.forward_loss(tb)
+        out.loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return 1.0 / (ms / 1e3), ms, cores
+
+
 def cpu_reference_step_rate(steps: int, warmup: int, tokens: int = CPU_SAMPLE_TOKENS):
-    """The reference algorithm (oracle port of the PyTorch path, bf16 modules, torch autograd + AdamW on fp32 masters)
-    on the host cores.  Bounded sample: 1 sequence x `tokens` tokens of the config-2 dims, TTT=7; samples/s is scaled by
+    """Fallback when the reference install is absent: the oracle port of the PyTorch path (bf16 modules, torch autograd + AdamW on
+    fp32 masters) on the host cores.  Bounded sample: 1 sequence x `tokens` tokens of the config-2 dims, TTT=7; samples/s is scaled by
     tokens (tokens/2048 of a sample per step)."""
     import torch
     from oracle import eagle3_oracle as O
@@ -111,21 +192,31 @@ def cpu_reference_step_rate(steps: int, warmup: int, tokens: int = CPU_SAMPLE_TO
     return (tokens / S) / (ms / 1e3), ms, cores
 
 
+def cpu_arm(steps: int, warmup: int):
+    """(value, ms, cores, kind, sample): the unmodified reference when its install travelled with the repo, else the port."""
+    if _reference_dir() is not None:
+        val, ms, cores = reference_cpu_step_rate(steps, warmup)
+        return val, ms, cores, "reference", (f"UNMODIFIED reference (baseline/_ref: Eagle3TrainStrategy + OnlineEagle3Model(sdpa) + BF16Optimizer), "
+                                             f"Qwen3-8B draft dims, batch 1 x {S} tokens, TTT={T}, fwd+bwd+optimizer, bf16 modules; "
+                                             f"{steps} timed step(s) after {warmup} warm-up; one step = one sample")
+    val, ms, cores = cpu_reference_step_rate(steps, warmup)
+    return val, ms, cores, "port", (f"oracle port (reference install absent): 1 sequence x {CPU_SAMPLE_TOKENS} tokens of the Qwen3-8B draft dims, "
+                                    f"TTT={T}, fwd+bwd+AdamW, scaled by tokens; {steps} timed step(s) after {warmup} warm-up")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 4))
-    warm = max(1, min(args.warmup, 1))
-    val, ms, cores = cpu_reference_step_rate(steps, warm)
-    sample = (f"1 sequence x {CPU_SAMPLE_TOKENS} tokens of the Qwen3-8B draft dims, TTT=7, fwd+bwd+AdamW, bf16 modules, "
-              f"scaled by tokens ({CPU_SAMPLE_TOKENS}/2048 sample per step); {steps} timed steps after {warm} warm-up")
+    steps = max(1, min(args.steps, 2))          # one reference step at these dims is tens of seconds on the host cores
+    warm = max(0, min(args.warmup, 1))
+    val, ms, cores, kind, sample = cpu_arm(steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: Qwen3-8B EAGLE3 offline draft step, TTT=7, seq 2048 (CPU: bounded sample)",
-                       "ttt_length": T, "seq_len": S},
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "BASELINE config 2: Qwen3-8B EAGLE3 offline draft step, TTT=7, seq 2048 (CPU arm: batch 1 per step)",
+                       "ttt_length": T, "seq_len": S, "batch_per_step": 1, "same_config": kind == "reference"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -419,10 +510,8 @@ def run_ours(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            val, ms, cores = cpu_reference_step_rate(1, 1)
-            line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                                    "sample": f"oracle port of the reference PyTorch path, 1 sequence x {CPU_SAMPLE_TOKENS} tokens of the "
-                                              f"same dims, TTT=7, fwd+bwd+AdamW, 1 timed step after 1 warm-up, scaled by tokens"}
+            val, ms, cores, kind, sample = cpu_arm(1, 0)
+            line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

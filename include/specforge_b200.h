@@ -210,6 +210,9 @@ typedef struct sf_dflash_config {
     int32_t mask_token_id, rope_rows;
     float rms_eps;
     float loss_decay_gamma;           /* <= 0: no decay  (dflash_family_model.py:349-358)                                 */
+    int32_t grad_of_numerator;        /* 0: backward yields d(loss_num / loss_den) (a self-contained step); 1: d(loss_num) —    */
+                                      /* the reference controller's loss_terms contract, which backprops the numerator and then  */
+                                      /* divides the synchronised gradients by the GLOBAL denominator (controller.py:334-398)     */
 } sf_dflash_config;
 /* parameter order inside the flat buffer: for each layer the SF_DF_* slices below (q, k, v contiguous = one fused GEMM
  * operand, likewise gate, up), then fc [H, F*H], hidden_norm [H], norm [H].  Names/shapes: dflash.py:336-375. */

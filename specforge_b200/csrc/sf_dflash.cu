@@ -199,7 +199,7 @@ static int forward(Ctx& c, const sf_dflash_frozen& fz, const sf_dflash_batch& bt
     SF_TRY(rmsnorm_fwd(c.bf(p.x, (int64_t)x.L * Mq * x.H), x.H, nullptr, x.S, 0, c.Wg(2), c.bf(p.hf), x.H, Mq, x.H, cfg.rms_eps, nullptr, st));
     SF_TRY(mm(c, c.bf(p.hf), x.H, MAJOR_K, fz.lm_head, x.H, MAJOR_K, c.bf(p.logits), x.V, nullptr, 0, Mq, x.V, x.H, EPI_BF16));
     SF_TRY(ce(c.bf(p.logits), x.V, x.V, c.at<int32_t>(p.tgt), c.at<float>(p.w), c.at<float>(p.lw), c.at<float>(p.sums), need_grad,
-              c.at<float>(p.row_loss), c.at<float>(p.row_correct), Mq, st));
+              c.at<float>(p.row_loss), c.at<float>(p.row_correct), Mq, cfg.grad_of_numerator, st));
     // metrics = {loss_num, loss_den, correct, acc_den}; loss = loss_num / loss_den
     return finalize_loss(c.at<float>(p.sums), metrics_out, loss_out, st);
 }

@@ -46,7 +46,7 @@ bool attn_tc_bwd_supported(const AttnArgs& a);      // sf_dflash_attn_tc_bwd.cu 
 int attn_bwd_tc(const AttnArgs& a, cudaStream_t st);
 int attn_bwd(const AttnArgs& a, cudaStream_t st);
 int ce(void* logits, int64_t ld, int V, const int32_t* tgt, const float* w, const float* lw, float* sums, int write_grad,
-       float* row_loss, float* row_correct, int64_t M, cudaStream_t st);
+       float* row_loss, float* row_correct, int64_t M, int grad_of_numerator, cudaStream_t st);
 int finalize_loss(const float* sums, float* metrics, float* loss, cudaStream_t st);
 
 }  // namespace dflash

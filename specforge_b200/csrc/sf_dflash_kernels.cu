@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(256) attn_bwd_ctx_kernel(AttnArgs a) {
 __global__ void __launch_bounds__(512) ce_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld, int V, const int32_t* __restrict__ tgt,
                                                  const float* __restrict__ w, const float* __restrict__ lw,
                                                  const float* __restrict__ sums /* [0] = loss_den */, int write_grad,
-                                                 float* __restrict__ row_loss, float* __restrict__ row_correct) {
+                                                 float* __restrict__ row_loss, float* __restrict__ row_correct, int grad_of_numerator) {
     __shared__ float redv[16], redd[16];
     __shared__ int redi[16];
     const int64_t r = blockIdx.x;
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(512) ce_kernel(__nv_bfloat16* __restrict__ log
         row_correct[r] = (am == tg && wr > 0.5f) ? 1.f : 0.f;
     }
     if (write_grad) {
-        const float coef = lwr / sums[0];
+        const float coef = grad_of_numerator ? lwr : lwr / sums[0];
         const float inv = 1.f / dsum;
         __syncthreads();   // row[tg] was read above by thread 0
         for (int c = threadIdx.x; c < V; c += 512) {
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(512) ce_kernel(__nv_bfloat16* __restrict__ log
 // metrics = {loss_num, loss_den, correct, acc_den}; loss = loss_num / loss_den   (sums: see sf_dflash.h)
 __global__ void finalize_kernel(const float* __restrict__ sums, float* __restrict__ metrics, float* __restrict__ loss) {
     metrics[0] = sums[2]; metrics[1] = sums[0]; metrics[2] = sums[3]; metrics[3] = sums[1];
-    loss[0] = sums[2] / sums[0];
+    loss[0] = sums[0] > 0.f ? sums[2] / sums[0] : 0.f;    // no supervised position: 0 rather than 0/0
 }
 
 // ------------------------------------------------------------------ host wrappers
@@ -588,8 +588,8 @@ int attn_bwd_cc(const AttnArgs& a, cudaStream_t st) {
     return 0;
 }
 int ce(void* logits, int64_t ld, int V, const int32_t* tgt, const float* w, const float* lw, float* sums, int write_grad,
-       float* row_loss, float* row_correct, int64_t M, cudaStream_t st) {
-    ce_kernel<<<(unsigned)M, 512, 0, st>>>((__nv_bfloat16*)logits, ld, V, tgt, w, lw, sums, write_grad, row_loss, row_correct);
+       float* row_loss, float* row_correct, int64_t M, int grad_of_numerator, cudaStream_t st) {
+    ce_kernel<<<(unsigned)M, 512, 0, st>>>((__nv_bfloat16*)logits, ld, V, tgt, w, lw, sums, write_grad, row_loss, row_correct, grad_of_numerator);
     SF_CUDA_CHECK_LAUNCH("dflash ce");
     sum4_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, row_loss, row_correct, M, sums);   // sums[2] = loss_num, sums[3] = correct
     SF_CUDA_CHECK_LAUNCH("dflash ce sums");

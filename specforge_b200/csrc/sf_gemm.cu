@@ -200,17 +200,16 @@ static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
     count_launch();
     return 0;
 }
-// Which tiling: the wide one moves 25 % fewer operand bytes per FLOP but has half as many tiles, so its last wave can be much
-// emptier (the K = T*M weight-gradient GEMMs have only 128-1008 tiles); take it unless it loses more than 3 % to wave quantisation.
+// Which tiling.  The wide one moves 25 % fewer operand bytes per FLOP but cannot hide its epilogue behind the next tile's main loop
+// (all 512 TMEM columns hold one tile), so it pays roughly one accumulator drain per tile.  Measured on B200 next to the 256 x 256
+// tiling and cuBLAS (profiles/r02_gemm_vs_cublas_b.txt): K = 4096 tiles are too short to amortise the drain (-6..-9 %), K = 8192 is
+// a tie, K >= 12288 wins (+3 % at 12 288, +7..9 % at 24 576-32 000, +17 % on the K = T*M weight-gradient GEMMs even where the
+// larger tiles leave the last wave 14 % empty).  gemm_wide: -1 never, 0 this rule, 2 always (tests / A-B).
 static bool use_wide(const GemmDesc& g) {
     const int o = opt(OPT_GEMM_WIDE);
     if (o < 0 || g.M < 512) return false;
     if (o == 2) return true;
-    if (o == 0) return false;       // default off until the round's B200 validation flips it (see bench.py / DESIGN.md)
-    const int clusters = num_sms() / 2;
-    auto eff = [&](int64_t tiles) { const int64_t waves = (tiles + clusters - 1) / clusters; return (double)tiles / (double)(waves * clusters); };
-    const int64_t nb = (g.N + 255) / 256;
-    return eff(((int64_t)g.M + 511) / 512 * nb) >= eff(((int64_t)g.M + 255) / 256 * nb) - 0.03;
+    return g.K > 8192;
 }
 
 int gemm(const GemmDesc& g, cudaStream_t stream) {

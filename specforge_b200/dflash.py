@@ -24,7 +24,8 @@ GLOBALS = ("fc.weight", "hidden_norm.weight", "norm.weight")
 class SfDflashConfig(Structure):
     _fields_ = [(n, c_int32) for n in ("batch", "seq_len", "num_blocks", "block_size", "hidden_size", "num_target_feats",
                                        "intermediate", "num_heads", "num_kv_heads", "head_dim", "num_layers", "vocab",
-                                       "mask_token_id", "rope_rows")] + [("rms_eps", c_float), ("loss_decay_gamma", c_float)]
+                                       "mask_token_id", "rope_rows")] + [("rms_eps", c_float), ("loss_decay_gamma", c_float),
+                                                                          ("grad_of_numerator", c_int32)]
 
 
 class SfDflashFrozen(Structure):
@@ -155,7 +156,7 @@ class DFlashEngine:
         d = self.dims
         return SfDflashConfig(B, S, N, d.block_size, d.hidden_size, d.num_target_feats, d.intermediate_size, d.num_heads,
                               d.num_kv_heads, d.head_dim, d.num_layers, d.vocab_size, d.mask_token_id, rope_rows, d.rms_norm_eps,
-                              float(d.loss_decay_gamma) if d.loss_decay_gamma else 0.0)
+                              float(d.loss_decay_gamma) if d.loss_decay_gamma else 0.0, int(getattr(self, "grad_of_numerator", 0)))
 
     def shape_of(self, name: str) -> Tuple[int, ...]:
         d = self.dims
@@ -365,18 +366,27 @@ class B200DFlashDraftModel(torch.nn.Module):
 
 # ------------------------------------------------------------------------------------------------ strategy seam
 class _DFlashStepFn(torch.autograd.Function):
-    """loss = f(flat params): forward / backward run in the CUDA library, the fp32 flat gradient stays in the engine."""
+    """(loss, loss_num) = f(flat params): forward / backward run in the CUDA library, the fp32 flat gradient stays in the engine.
+    Exactly one of the two outputs may be backpropagated, fixed by the strategy's normalisation mode: `loss` = loss_num / loss_den
+    when the engine differentiates the ratio ("local"), `loss_num` when it differentiates the numerator for the reference
+    controller's loss_terms path ("global", controller.py:334-398)."""
 
     @staticmethod
     def forward(ctx, flat_params, strategy, batch_tensors, anchors, keep, need_grad):
-        loss, _ = strategy.engine.forward(batch_tensors, anchors, keep, need_grad=need_grad)
+        loss, metrics = strategy.engine.forward(batch_tensors, anchors, keep, need_grad=need_grad)
         ctx.strategy = strategy
-        return loss.clone().reshape(())
+        return loss.clone().reshape(()), metrics[0].clone().reshape(())
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_loss, grad_num):
         st = ctx.strategy
-        st._last_grad_out = grad_out.detach()
+        want_num = st.normalization == "global"
+        g = grad_num if want_num else grad_loss
+        other = grad_loss if want_num else grad_num
+        if other is not None and bool((other != 0).any()):
+            raise RuntimeError(f"DFlash strategy in normalization={st.normalization!r} mode: backpropagate "
+                               f"{'loss_terms[0] (the numerator)' if want_num else 'StepOutput.loss'}, not the other output")
+        st._last_grad_out = g.detach()
         st.engine.backward(accumulate=st._micro_in_window > 0)
         st._micro_in_window += 1
         return None, None, None, None, None, None
@@ -396,10 +406,19 @@ class B200DFlashTrainStrategy:
     required_features = {"input_ids", "hidden_states", "loss_mask"}
 
     def __init__(self, draft_model: "B200DFlashDraftModel", *, target_embed_weight: torch.Tensor, target_head_weight: torch.Tensor,
-                 num_anchors: int = 512, generator: Optional[torch.Generator] = None, sync_free_anchors: bool = True):
+                 num_anchors: int = 512, generator: Optional[torch.Generator] = None, sync_free_anchors: bool = True,
+                 normalization: str = "local"):
+        """normalization: "local" — the step's loss is loss_num / loss_den of THIS micro-batch and `loss_terms` is not reported, so the
+        reference controller treats it like any scalar loss (mean over accumulation steps and ranks); "global" — the reference's
+        DFlash contract: `loss_terms = (loss_num with grad, loss_den)`, the engine differentiates the numerator and the controller
+        divides the synchronised gradients by the global denominator (training/strategies/base.py:415-452, controller.py:334-398)."""
         if draft_model.engine is None:
             raise RuntimeError("bind_engine() must be called on the draft model first")
+        if normalization not in ("local", "global"):
+            raise ValueError("normalization must be 'local' or 'global'")
+        self.normalization = normalization
         self.draft_model, self.engine = draft_model, draft_model.engine
+        self.engine.grad_of_numerator = int(normalization == "global")
         self.num_anchors, self.generator = num_anchors, generator
         self.sync_free_anchors = sync_free_anchors      # see sample_anchor_positions(fixed_width=...)
         self.engine.set_frozen(embed_tokens=target_embed_weight, lm_head=target_head_weight)
@@ -427,10 +446,13 @@ class B200DFlashTrainStrategy:
         need_grad = torch.is_grad_enabled()
         eng = self.engine
         flat = eng.params if not need_grad else eng.params.detach().requires_grad_(True)
-        loss = _DFlashStepFn.apply(flat, self, t, anchors, keep, need_grad)
+        loss, loss_num = _DFlashStepFn.apply(flat, self, t, anchors, keep, need_grad)
         m = eng.metrics.clone()            # loss_num, loss_den, correct, accuracy_den (device, no host sync)
-        return StepOutput(loss=loss, metrics={"accuracy": m[2] / m[3], "accuracy_denom": m[3]},
-                          ratio_metrics={"acc": (m[2], m[3])}, loss_terms=(m[0], m[1]))
+        if not self.sync_free_anchors and float(m[1]) <= 0:
+            raise ValueError("DFlash batch has no supervised draft position (need two consecutive loss-mask tokens)")
+        terms = (loss_num, m[1]) if self.normalization == "global" else None
+        return StepOutput(loss=loss, metrics={"accuracy": m[2] / m[3].clamp_min(1e-6), "accuracy_denom": m[3]},
+                          ratio_metrics={"acc": (m[2], m[3])}, loss_terms=terms)
 
     def checkpoint_state_filter(self, state_dict):
         return {k.replace("draft_model.", ""): v for k, v in state_dict.items() if "draft_model." in k}

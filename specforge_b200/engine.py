@@ -304,6 +304,13 @@ class Eagle3Engine:
         }
         am = batch.get("attention_mask")
         t["attention_mask"] = None if am is None else am.to(dev, torch.int64, non_blocking=True).contiguous()
+        pinned = [v for v in batch.values() if isinstance(v, torch.Tensor) and not v.is_cuda and v.is_pinned()]
+        if pinned:   # asynchronous copies out of reusable pinned buffers: tell their producer when they have executed
+            from .feed import mark_copied
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            for v in pinned:
+                mark_copied(v, ev)
         if t["input_ids"].dim() != 2:
             raise ValueError(f"input_ids must be [batch, seq], got {tuple(t['input_ids'].shape)}")
         # The engine is bound to a MAXIMUM (batch, seq_len): the reference collator pads each batch to its own longest

@@ -12,6 +12,20 @@ from typing import Iterable, Iterator, Optional
 import torch
 
 
+def mark_copied(host_tensor: torch.Tensor, event: "torch.cuda.Event") -> None:
+    """Called by whoever enqueues a non-blocking H2D copy FROM a reusable pinned host tensor: the producer that owns the buffer must
+    not overwrite it before `event` (recorded after the copy on the copying stream) has completed."""
+    host_tensor._sf_copy_event = event
+
+
+def wait_until_copied(host_tensor: torch.Tensor) -> None:
+    """Producer side: block (host) until the last asynchronous copy out of this pinned buffer has executed."""
+    ev = getattr(host_tensor, "_sf_copy_event", None)
+    if ev is not None:
+        ev.synchronize()
+        host_tensor._sf_copy_event = None
+
+
 class DevicePrefetcher:
     def __init__(self, batches: Iterable, device: Optional[torch.device] = None, depth: int = 2):
         self.batches = batches
@@ -21,16 +35,20 @@ class DevicePrefetcher:
 
     def _stage(self, batch):
         with torch.cuda.stream(self.stream):
-            tensors = {}
+            tensors, sources = {}, []
             for k, v in batch.tensors.items():
                 if isinstance(v, torch.Tensor) and not v.is_cuda:
                     if not v.is_pinned():
                         v = v.pin_memory()
+                    else:
+                        sources.append(v)
                     tensors[k] = v.to(self.device, non_blocking=True)
                 else:
                     tensors[k] = v
             ev = torch.cuda.Event()
             ev.record(self.stream)
+            for v in sources:                 # a loader that reuses its pinned buffers waits on this before rewriting them
+                mark_copied(v, ev)
         return dataclasses.replace(batch, tensors=tensors), ev
 
     def __iter__(self) -> Iterator:

@@ -20,6 +20,8 @@ from typing import Dict, Iterable, Iterator, List, Mapping, Optional, Sequence, 
 
 import torch
 
+from .feed import wait_until_copied
+
 from ._lib import check, lib
 from .contracts import TrainBatch
 
@@ -282,8 +284,14 @@ class Eagle3ShardLoader:
     def set_epoch(self, epoch: int) -> None:
         self.epoch = epoch
 
+    def _per_rank(self) -> int:
+        """Samples every rank iterates per epoch: ceil(N / world), the DistributedSampler rule the reference's partition follows
+        (launch.py:174-239: strided slices of a seeded permutation, wrap-padded) — identical on all ranks, so no rank can run an
+        extra optimizer step and block the others in the gradient all-reduce."""
+        return (len(self._where) + self.world - 1) // self.world
+
     def __len__(self) -> int:
-        n = len(self._where[self.rank::self.world])
+        n = self._per_rank()
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     def _order(self) -> List[int]:
@@ -291,7 +299,12 @@ class Eagle3ShardLoader:
         if self.shuffle:
             g = torch.Generator().manual_seed(self.seed + self.epoch)
             order = torch.randperm(len(order), generator=g).tolist()
-        return order[self.rank::self.world]          # independent samples: ranks take disjoint strided slices
+        total = self._per_rank() * self.world
+        if order and len(order) < total:             # wrap-padding: repeat from the start until every rank has the same count
+            order = (order * ((total + len(order) - 1) // len(order)))[:total]
+        mine = order[self.rank::self.world]          # independent samples: ranks take strided slices
+        assert len(mine) == self._per_rank()
+        return mine
 
     def batch(self, sample_indices: Sequence[int]) -> TrainBatch:
         by_reader: Dict[int, List[int]] = {}
@@ -304,6 +317,8 @@ class Eagle3ShardLoader:
             (ri, _), = by_reader.items()
             slot = self._ring[self._ring_pos]
             self._ring_pos = (self._ring_pos + 1) % len(self._ring)
+            for t in slot.values():                  # a consumer may still have an asynchronous H2D copy out of this slot in flight
+                wait_until_copied(t)
             raw = self.readers[ri].read_batch([self._where[gi][1] for gi in sample_indices], self.max_len, S, self.RAW_KEYS,
                                               self.pin, self.threads, out=slot)
             slot.update(raw)

@@ -116,7 +116,8 @@ def test_dflash_strategy_host_logic_with_a_fake_engine():
     out = st.forward_loss(batch)
     assert float(out.loss) == 2.0 and out.loss.requires_grad
     assert float(out.metrics["accuracy"]) == 0.5 and float(out.metrics["accuracy_denom"]) == 4.0
-    assert [float(v) for v in out.ratio_metrics["acc"]] == [2.0, 4.0] and [float(v) for v in out.loss_terms] == [6.0, 3.0]
+    assert [float(v) for v in out.ratio_metrics["acc"]] == [2.0, 4.0]
+    assert out.loss_terms is None                      # "local" normalisation: a plain scalar loss for the controller
     (out.loss / 2).backward()
     out2 = st.forward_loss(batch)
     (out2.loss / 2).backward()
@@ -126,6 +127,19 @@ def test_dflash_strategy_host_logic_with_a_fake_engine():
     with torch.no_grad():
         st.forward_loss(batch)
     assert eng.calls[-1] == ("fwd", (2, 5), False)
+    # "global": the reference's loss_terms contract — the numerator carries the gradient (dflash_family_model.py:459,
+    # controller.py:334-351), the engine is told to differentiate it, and backpropagating the ratio instead is refused
+    sg = B200DFlashTrainStrategy(FakeDraft(), target_embed_weight=torch.zeros(4, 4), target_head_weight=torch.zeros(4, 4), num_anchors=5,
+                                 generator=torch.Generator().manual_seed(0), normalization="global")
+    assert eng.grad_of_numerator == 1
+    og = sg.forward_loss(batch)
+    num, den = og.loss_terms
+    assert float(num) == 6.0 and float(den) == 3.0 and num.requires_grad and not den.requires_grad
+    n0 = len(eng.calls)
+    (num / 4).backward()
+    assert eng.calls[n0:] == [("bwd", False)] and float(sg._last_grad_out) == 0.25
+    with pytest.raises(RuntimeError, match="numerator"):
+        sg.forward_loss(batch).loss.backward()
     with pytest.raises(ValueError):
         st.forward_loss(TrainBatch(sample_ids=["0"], strategy="dflash", tensors={"input_ids": torch.zeros(1, 4)}, metadata={}))
 

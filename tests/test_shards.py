@@ -93,6 +93,15 @@ def test_multi_shard_shuffle_rank_split_and_empty_record(tmp_path):
                 assert torch.equal(g.view(torch.int16) if g.dtype == torch.bfloat16 else g,
                                    w.view(torch.int16) if w.dtype == torch.bfloat16 else w), k
     assert sorted(seen) == list(range(6))          # ranks cover the data set exactly once
+    # N not divisible by world: DistributedSampler semantics — every rank iterates ceil(N / world) samples (wrap-padded), so all
+    # ranks run the same number of steps (an extra step on one rank would block forever in the gradient all-reduce)
+    per_rank = []
+    for rank in range(4):
+        ld = Eagle3ShardLoader(shards, batch_size=1, max_len=28, shuffle=True, seed=3, rank=rank, world=4, drop_last=True)
+        ids = [int(b.sample_ids[0].split(":")[1]) for b in ld]
+        assert len(ids) == len(ld) == 2
+        per_rank.append(ids)
+    assert sorted(set(sum(per_rank, []))) == list(range(6))     # everything is still covered; two samples appear twice
     # writer-side validation
     with pytest.raises(ValueError):
         w = ShardWriter(str(tmp_path / "bad.sfpk"), [("x", torch.float32, 4)])

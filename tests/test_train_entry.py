@@ -212,3 +212,70 @@ def test_registry_and_patch_points():
     with T.b200_patches():
         assert ref_trainer.FSDPTrainingBackend is B200TrainingBackend and ref_opt.BF16Optimizer is B200BF16Optimizer
     assert ref_trainer.FSDPTrainingBackend is stock_backend and ref_opt.BF16Optimizer is stock_opt
+
+
+@needs_ref
+def test_dflash_loss_terms_through_the_reference_trainer_core():
+    """The reference TrainerCore (controller.py:328-398) on a strategy that reports loss_terms: it backpropagates the NUMERATOR
+    divided by the accumulation steps and, at the boundary, scales the gradients by world * accum / sum(denominators).  With the
+    B200 backend + DFlash strategy in normalization="global" the accumulated gradient must come out as sum_i d(num_i) / sum_i den_i."""
+    from specforge.training.controller import TrainerCore
+    from specforge_b200.backend import B200TrainingBackend
+    from specforge_b200.contracts import TrainBatch
+    from specforge_b200.dflash import B200DFlashTrainStrategy
+
+    class Eng(CpuFlatEngine):
+        """forward: loss_num = c * sum(params), den = d for scripted (c, d); backward adds d(loss_num) = c (numerator mode)."""
+        script = [(3.0, 2.0), (5.0, 6.0)]
+
+        def __init__(self):
+            super().__init__({"w": (8,)})
+            self.i, self.metrics, self.loss, self.grad_of_numerator = 0, torch.zeros(4), torch.zeros(1), 0
+            self.names = ["w"]
+
+        def set_frozen(self, **kw):
+            pass
+
+        def forward(self, batch, anchors, keep, need_grad=True):
+            c, d = self.script[self.i % 2]
+            self.cur = c
+            num = c * float(self.params.float().sum())
+            self.metrics = torch.tensor([num, d, 1.0, 2.0])
+            self.loss = torch.tensor([num / d])
+            self.i += 1
+            return self.loss, self.metrics
+
+        def backward(self, accumulate=False):
+            assert self.grad_of_numerator == 1
+            g = torch.full((8,), self.cur)
+            self.grads_f32 = self.grads_f32 + g if accumulate else g
+
+    class Draft(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.engine = Eng()
+
+    draft = Draft()
+    eng = draft.engine
+    backend = B200TrainingBackend(lr=1e-2, max_grad_norm=1e9, total_steps=10, warmup_ratio=0.0)
+    st = B200DFlashTrainStrategy(draft, target_embed_weight=torch.zeros(4, 4), target_head_weight=torch.zeros(4, 4), num_anchors=3,
+                                 generator=torch.Generator().manual_seed(0), normalization="global")
+    backend.attach(st)
+    backend.prepare_model(st.trainable_module())
+    core = TrainerCore(st, backend, accumulation_steps=2)
+    batch = TrainBatch(sample_ids=["0"], strategy="dflash", tensors={"input_ids": torch.zeros(1, 12, dtype=torch.long),
+                                                                     "hidden_states": torch.zeros(1, 12, 8), "loss_mask": torch.ones(1, 12)}, metadata={})
+    r1 = core.train_step(batch)
+    assert not r1.optimizer_stepped
+    seen = {}
+    orig = eng.optimizer_step
+
+    def spy(lr, **kw):
+        seen["g"] = eng.grads_bf16.float().clone()
+        return orig(lr, **kw)
+
+    eng.optimizer_step = spy
+    r2 = core.train_step(batch)
+    assert r2.optimizer_stepped
+    # (3 + 5) / (2 + 6) = 1.0 per element: sum of numerator gradients over the sum of denominators
+    torch.testing.assert_close(seen["g"], torch.full((8,), 1.0), rtol=1e-2, atol=1e-2)
