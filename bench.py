@@ -385,6 +385,20 @@ def run_ours(args):
     ms_prof, _ = timed(dev_batch, False, args.steps)
     gms, gfl = ctypes.c_double(), ctypes.c_double()
     n_gemm = int(L.sf_profile_gemm_collect(ctypes.byref(gms), ctypes.byref(gfl)))
+    # the same launches by shape: which GEMMs run at what rate inside the step (live, power-capped)
+    L.sf_profile_gemm_detail.restype = ctypes.c_longlong
+    cap = max(1, n_gemm)
+    mnkt, tms = (ctypes.c_longlong * (4 * cap))(), (ctypes.c_double * cap)()
+    nd = int(L.sf_profile_gemm_detail(mnkt, tms, cap))
+    by_shape = {}
+    for i in range(nd):
+        key = tuple(mnkt[4 * i + k] for k in range(4))
+        c = by_shape.setdefault(key, [0, 0.0])
+        c[0] += 1
+        c[1] += tms[i]
+    gemm_by_shape = [{"M": k[0], "N": k[1], "K": k[2], "tile_rows": k[3], "launches_per_step": v[0] / args.steps,
+                      "ms_per_step": round(v[1] / args.steps, 3), "tflops": round(2.0 * k[0] * k[1] * k[2] * v[0] / v[1] / 1e9, 1)}
+                     for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])]
     L.sf_profile_gemm(0)
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
@@ -500,7 +514,7 @@ def run_ours(args):
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained if sustained else None,
                      "peak_burst": burst, "frac_of_burst": achieved / burst if burst else None, "peak_source": peak_src,
                      "gemm_ms_per_step": gms.value / args.steps, "gemm_share_of_step": (gms.value / args.steps) / (ms_prof / args.steps),
-                     "ms_per_step_with_events": ms_prof / args.steps,
+                     "ms_per_step_with_events": ms_prof / args.steps, "gemm_by_shape": gemm_by_shape,
                      "step_tflops_algorithmic": flops_step / 1e12 / (ms_step / 1e3),
                      "step_frac_of_burst": flops_step / 1e12 / (ms_step / 1e3) / burst if burst else None,
                      # DRAM bytes of the largest per-TTT-step GEMM (lm_head forward, 16384x32000x4096) from the committed

@@ -44,6 +44,8 @@ void sf_launch_count_reset(void);
  * and algorithmic FLOPs (2*M*N*K) of the recorded launches. */
 void sf_profile_gemm(int enable);
 long long sf_profile_gemm_collect(double* total_ms, double* total_flops);
+/* per launch: mnkt[4 i ..] = {M, N, K, rows per CTA-pair tile (256 | 512)}, ms[i] = device time; returns the number written */
+long long sf_profile_gemm_detail(long long* mnkt, double* ms, long long max_n);
 
 /* ---- model / step description ---- */
 typedef struct sf_eagle3_config {

@@ -47,6 +47,7 @@ struct GemmProf {
     bool on = false;
     std::vector<cudaEvent_t> ev;   // pairs
     std::vector<double> flops;
+    std::vector<long long> shape;  // 4 per launch: M, N, K, tiling (256 or 512 rows per CTA pair)
     size_t used = 0;
 };
 static GemmProf g_prof;
@@ -90,7 +91,10 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     p.stages = opt(OPT_GEMM_STAGES) > 0 ? opt(OPT_GEMM_STAGES) : Cfg::kStages;
     if (p.stages < 2) p.stages = 2;
     if (p.stages > Cfg::kMaxStages) p.stages = Cfg::kMaxStages;
-    const int smem_bytes = Cfg::smem_bytes(p.stages);
+    // warp-staged (coalesced) bf16 epilogue transfers: needs 8 KB, i.e. one ring stage less than the deepest ring
+    p.staged = opt(OPT_GEMM_EPI_STAGED) == 1 ? 1 : 0;
+    if (p.staged && Cfg::smem_bytes(p.stages, 1) > 227 * 1024) --p.stages;
+    const int smem_bytes = Cfg::smem_bytes(p.stages, p.staged);
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int clusters = num_sms() / G;
     if (tiles < clusters) clusters = tiles;
@@ -98,7 +102,7 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     auto kern = gemm_kernel<G, AM, BM, BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(Cfg::kMaxStages));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(Cfg::kMaxStages, 0));
         if (e != cudaSuccess) return set_error(-22, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
@@ -125,6 +129,7 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
         e0 = g_prof.ev[g_prof.used]; e1 = g_prof.ev[g_prof.used + 1];
         g_prof.used += 2;
         g_prof.flops.push_back(2.0 * (double)g.M * (double)g.N * (double)g.K);
+        g_prof.shape.insert(g_prof.shape.end(), {(long long)g.M, (long long)g.N, (long long)g.K, (long long)Cfg::TILE_M});
         cudaEventRecord(e0, stream);
     }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
@@ -159,6 +164,7 @@ static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
     p.group_m = (g.K > 32768 ? (gmw > 0 ? gmw : 8) : g.K > 4608 ? (gmk > 0 ? gmk : 16) : (gm > 0 ? gm : 16)) / 2;
     if (p.group_m < 1) p.group_m = 1;
     p.stages = Cfg::kStages;
+    p.staged = opt(OPT_GEMM_EPI_STAGED) >= 0 ? 1 : 0;
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int clusters = num_sms() / 2;
     if (tiles < clusters) clusters = tiles;
@@ -192,6 +198,7 @@ static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
         e0 = g_prof.ev[g_prof.used]; e1 = g_prof.ev[g_prof.used + 1];
         g_prof.used += 2;
         g_prof.flops.push_back(2.0 * (double)g.M * (double)g.N * (double)g.K);
+        g_prof.shape.insert(g_prof.shape.end(), {(long long)g.M, (long long)g.N, (long long)g.K, (long long)Cfg::TILE_M});
         cudaEventRecord(e0, stream);
     }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
@@ -202,14 +209,17 @@ static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
 }
 // Which tiling.  The wide one moves 25 % fewer operand bytes per FLOP but cannot hide its epilogue behind the next tile's main loop
 // (all 512 TMEM columns hold one tile), so it pays roughly one accumulator drain per tile.  Measured on B200 next to the 256 x 256
-// tiling and cuBLAS (profiles/r02_gemm_vs_cublas_b.txt): K = 4096 tiles are too short to amortise the drain (-6..-9 %), K = 8192 is
-// a tie, K >= 12288 wins (+3 % at 12 288, +7..9 % at 24 576-32 000, +17 % on the K = T*M weight-gradient GEMMs even where the
-// larger tiles leave the last wave 14 % empty).  gemm_wide: -1 never, 0 this rule, 2 always (tests / A-B).
+// tiling and cuBLAS (profiles/r02_gemm_vs_cublas_c.txt, isolated kernels, random operands): with the warp-staged epilogue K = 4096
+// tiles lose 2 % (4.6 % under the teacher-statistics epilogue), K = 8192 gains 3 %, K >= 12288 gains 5-17 %; inside the step
+// (bench.py --ab gemm_wide=-1,0,2, settings alternated step by step on one box) always-wide is the fastest setting by 1-3 %: the
+// lower L2 -> SM traffic also buys clock under the 1 kW cap.  gemm_wide: -1 never, 0 (default) always for M >= 512,
+// 1 = as 0 but the 256 x 256 tiling for the row-statistics epilogues at K <= 4096, 3 = only K > 8192.
 static bool use_wide(const GemmDesc& g) {
     const int o = opt(OPT_GEMM_WIDE);
     if (o < 0 || g.M < 512) return false;
-    if (o == 2) return true;
-    return g.K > 8192;
+    if (o == 3) return g.K > 8192;
+    if (o == 1 && g.K <= 4096 && (g.epi == EPI_TEACHER || g.epi == EPI_BF16_STATS)) return false;
+    return true;
 }
 
 int gemm(const GemmDesc& g, cudaStream_t stream) {
@@ -258,6 +268,20 @@ extern "C" void sf_profile_gemm(int enable) {
     sf::g_prof.on = enable != 0;
     sf::g_prof.used = 0;
     sf::g_prof.flops.clear();
+    sf::g_prof.shape.clear();
+}
+// Per-launch detail of the recorded GEMMs (after a stream sync): mnkt[4 i ..] = M, N, K, rows per pair tile; ms[i] = device time.
+extern "C" long long sf_profile_gemm_detail(long long* mnkt, double* ms, long long max_n) {
+    std::lock_guard<std::mutex> lk(sf::g_prof_mu);
+    const size_t n = sf::g_prof.used / 2;
+    long long out = 0;
+    for (size_t i = 0; i < n && out < max_n; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sf::g_prof.ev[2 * i], sf::g_prof.ev[2 * i + 1]) != cudaSuccess) continue;
+        for (int k = 0; k < 4; ++k) mnkt[4 * out + k] = sf::g_prof.shape[4 * i + k];
+        ms[out++] = t;
+    }
+    return out;
 }
 // Sums the recorded launches (call after synchronising the stream).  Returns the number of launches.
 extern "C" long long sf_profile_gemm_collect(double* total_ms, double* total_flops) {

@@ -58,6 +58,7 @@ struct GemmParams {
     int n_half;           // EPI_SWIGLU / EPI_SWIGLU_BWD: I (columns of gate == columns of up)
     int group_m;          // M-blocks per raster group (L2 reuse window of the A operand)
     int stages;           // depth of the TMA -> MMA smem ring (6 or 7 x 32 KB)
+    int staged;           // 1: the epilogue warps own a 2 KB staging block each (after the barriers) for coalesced bf16 transfers
     // EPI_BF16_STATS / EPI_TEACHER
     float* stats;                  // [3 or 5][num_n_blocks][M]
     const uint32_t* t2d_bits;      // [ceil(N / 32)] bit e of word w: column 32 w + e is in the draft vocabulary
@@ -80,18 +81,63 @@ struct GemmCfg {
     static constexpr int kMaxStages = (224 * 1024) / STAGE_BYTES;   // deepest ring that fits the 227 KB of a CTA
     static constexpr int kAccStages = 2;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/; }
+    static constexpr int STAGING_BYTES = 4 * 2048;                  // optional: 2 KB per epilogue warp (GemmParams::staged)
+    static constexpr int smem_bytes(int stages, int staged = 0) { return stages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + (staged ? STAGING_BYTES : 0); }
     static constexpr int SMEM_BYTES = smem_bytes(kStages);
     static constexpr int kThreads = 256;
     static_assert(kBlockN * kAccStages <= 512, "TMEM overflow");
     static_assert(kBlockN % 64 == 0 && kBlockN <= 256, "bad BLOCK_N");
 };
 
+// ---- warp-staged row-block transfers --------------------------------------------------------------------------------------
+// In the epilogue a thread owns one accumulator ROW (TMEM lane), so writing its 32 bf16 columns straight to global memory makes
+// every 16-byte store instruction of the warp touch 32 different 128-byte lines.  Staged through a 2 KB per-warp shared-memory
+// block ([32 rows x 64 B], 16-byte units XOR-swizzled so the row-wise and the 8-rows-per-instruction accesses are both
+// bank-conflict-free) the same data leaves as 4 instructions that each write 8 rows x 64 contiguous bytes (whole sectors).
+__device__ __forceinline__ uint32_t stg_off(int r, int u) { return (uint32_t)(r * 64 + ((u ^ ((r >> 1) & 3)) << 4)); }
+// lane r holds row r's 32 bf16 (o[16]); dst -> (row 0 of the block, first column); rows >= rows_valid are not written
+__device__ __forceinline__ void warp_store_32x32(uint8_t* wbuf, int lane, const uint32_t (&o)[16], __nv_bfloat16* dst, int64_t ld,
+                                                 int rows_valid) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(wbuf + stg_off(lane, q)) = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+    __syncwarp();
+    const int u = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        const uint4 v = *reinterpret_cast<const uint4*>(wbuf + stg_off(r, u));
+        if (r < rows_valid) *reinterpret_cast<uint4*>(dst + (size_t)r * ld + u * 8) = v;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_load_32x32(uint8_t* wbuf, int lane, uint32_t (&o)[16], const __nv_bfloat16* src, int64_t ld,
+                                                int rows_valid) {
+    const int u = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * ld + u * 8));
+        *reinterpret_cast<uint4*>(wbuf + stg_off(r, u)) = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4*>(wbuf + stg_off(lane, q));
+        o[q * 4] = v.x; o[q * 4 + 1] = v.y; o[q * 4 + 2] = v.z; o[q * 4 + 3] = v.w;
+    }
+    __syncwarp();
+}
+
 // The epilogue of one thread: its row of the [128 x kBlockN] accumulator block at TMEM address t_row (lane = row), processed in
-// 32-column chunks; shared by the 256 x 256 (gemm_kernel) and 512 x 256 (gemm_wide_kernel) tilings.
+// 32-column chunks; shared by the 256 x 256 (gemm_kernel) and 512 x 256 (gemm_wide_kernel) tilings.  wbuf: this warp's 2 KB
+// staging block (bf16 outputs / inputs then move as described above) or nullptr (direct per-thread accesses).
 template <int kBlockN>
 __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const int row, const bool row_ok, const int n_blk,
-                                                   const int n0, const uint32_t t_row) {
+                                                   const int n0, const uint32_t t_row, uint8_t* wbuf, const int lane) {
+            const int row0 = row - lane;                                   // first row of this warp's 32-row block
+            const int rows_valid = min(32, max(0, p.M - row0));
             if (p.epi == EPI_SWIGLU) {
                 // columns [0,128) of the accumulator = gate(j0 + .), [128,256) = up(j0 + .)
                 const int j0 = n_blk * (kBlockN / 2);
@@ -104,7 +150,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                     tmem_ld_32x32b_x32(t_row + kBlockN / 2 + c * 32, u);
                     tmem_ld_wait();
                     const int col = j0 + c * 32;
-                    if (!row_ok || col >= p.n_half) continue;
+                    if (col >= p.n_half || (!wbuf && !row_ok)) continue;
                     uint32_t og[16], ou[16], oa[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -118,6 +164,13 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         oa[e] = pack_bf16x2(s0 * __bfloat162float(ub.x), s1 * __bfloat162float(ub.y));
                     }
                     // host guarantees n_half % 128 == 0: every 32-column chunk is whole
+                    if (wbuf) {
+                        __nv_bfloat16* gu0 = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row0 * p.ldd;
+                        warp_store_32x32(wbuf, lane, og, gu0 + col, p.ldd, rows_valid);
+                        warp_store_32x32(wbuf, lane, ou, gu0 + p.n_half + col, p.ldd, rows_valid);
+                        warp_store_32x32(wbuf, lane, oa, reinterpret_cast<__nv_bfloat16*>(p.D2) + (size_t)row0 * p.ldd2 + col, p.ldd2, rows_valid);
+                        continue;
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         reinterpret_cast<uint4*>(gu + col)[q] = make_uint4(og[q * 4], og[q * 4 + 1], og[q * 4 + 2], og[q * 4 + 3]);
@@ -134,14 +187,26 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
                     tmem_ld_wait();
                     const int col = n0 + c * 32;
-                    if (!row_ok || col >= p.n_half) continue;
+                    if (col >= p.n_half || (!wbuf && !row_ok)) continue;
                     // host guarantees n_half % 32 == 0
+                    uint32_t gsw[16], usw[16], dgw[16], duw[16];
+                    if (wbuf) {
+                        const __nv_bfloat16* gu0 = p.R + (size_t)row0 * p.ldr;
+                        warp_load_32x32(wbuf, lane, gsw, gu0 + col, p.ldr, rows_valid);
+                        warp_load_32x32(wbuf, lane, usw, gu0 + p.n_half + col, p.ldr, rows_valid);
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(gu + col) + q);
-                        const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(gu + p.n_half + col) + q);
-                        const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
-                        uint32_t odg[4], odu[4];
+                        uint32_t gw[4], uw[4];
+                        if (wbuf) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { gw[e] = gsw[q * 4 + e]; uw[e] = usw[q * 4 + e]; }
+                        } else {
+                            const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(gu + col) + q);
+                            const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(gu + p.n_half + col) + q);
+                            gw[0] = g4.x; gw[1] = g4.y; gw[2] = g4.z; gw[3] = g4.w;
+                            uw[0] = u4.x; uw[1] = u4.y; uw[2] = u4.z; uw[3] = u4.w;
+                        }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&gw[e]);
@@ -155,11 +220,18 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                                 dg[w] = da * uu * (sg * (1.f + gg * (1.f - sg)));
                                 du[w] = da * gg * sg;
                             }
-                            odg[e] = pack_bf16x2(dg[0], dg[1]);
-                            odu[e] = pack_bf16x2(du[0], du[1]);
+                            dgw[q * 4 + e] = pack_bf16x2(dg[0], dg[1]);
+                            duw[q * 4 + e] = pack_bf16x2(du[0], du[1]);
                         }
-                        reinterpret_cast<uint4*>(dgu + col)[q] = make_uint4(odg[0], odg[1], odg[2], odg[3]);
-                        reinterpret_cast<uint4*>(dgu + p.n_half + col)[q] = make_uint4(odu[0], odu[1], odu[2], odu[3]);
+                        if (!wbuf) {
+                            reinterpret_cast<uint4*>(dgu + col)[q] = make_uint4(dgw[q * 4], dgw[q * 4 + 1], dgw[q * 4 + 2], dgw[q * 4 + 3]);
+                            reinterpret_cast<uint4*>(dgu + p.n_half + col)[q] = make_uint4(duw[q * 4], duw[q * 4 + 1], duw[q * 4 + 2], duw[q * 4 + 3]);
+                        }
+                    }
+                    if (wbuf) {
+                        __nv_bfloat16* dgu0 = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row0 * p.ldd;
+                        warp_store_32x32(wbuf, lane, dgw, dgu0 + col, p.ldd, rows_valid);
+                        warp_store_32x32(wbuf, lane, duw, dgu0 + p.n_half + col, p.ldd, rows_valid);
                     }
                 }
             } else if (p.epi == EPI_BF16_STATS || p.epi == EPI_TEACHER) {
@@ -174,8 +246,10 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
                     tmem_ld_wait();
                     const int col = n0 + c * 32;
-                    if (!row_ok || col >= p.N) continue;
+                    if (col >= p.N) continue;
                     const bool full = (col + 32 <= p.N);
+                    const bool staged = wbuf && full && !gather;
+                    if (!row_ok && !staged) continue;
                     float x[32];
                     uint32_t o[16];
 #pragma unroll
@@ -190,7 +264,10 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         for (int e = 0; e < 32; ++e)
                             if (col + e >= p.N) x[e] = -INFINITY;
                     }
-                    if (!gather) {
+                    if (staged) {
+                        warp_store_32x32(wbuf, lane, o, reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row0 * p.ldd + col, p.ldd, rows_valid);
+                        if (!row_ok) continue;
+                    } else if (!gather) {
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col;
                         if (full) {
                             uint4* dp = reinterpret_cast<uint4*>(dst);
@@ -242,8 +319,29 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                 tmem_ld_32x32b_x32(t_row + c * 32, v);
                 tmem_ld_wait();
                 const int col = n0 + c * 32;
-                if (!row_ok || col >= p.N) continue;
+                if (col >= p.N) continue;
                 const bool full = (col + 32 <= p.N);
+                if (wbuf && full && (p.epi == EPI_BF16 || p.epi == EPI_BF16_RESID)) {   // warp-staged: every lane takes part
+                    uint32_t o[16];
+                    if (p.epi == EPI_BF16_RESID) {
+                        uint32_t rw[16];
+                        warp_load_32x32(wbuf, lane, rw, p.R + (size_t)row0 * p.ldr + col, p.ldr, rows_valid);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+                            // match the reference's two roundings: linear output -> bf16, then add
+                            const float a0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[2 * e])));
+                            const float a1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[2 * e + 1])));
+                            o[e] = pack_bf16x2(a0 + __bfloat162float(rb.x), a1 + __bfloat162float(rb.y));
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    }
+                    warp_store_32x32(wbuf, lane, o, reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row0 * p.ldd + col, p.ldd, rows_valid);
+                    continue;
+                }
+                if (!row_ok) continue;
                 if (p.epi == EPI_BF16 || p.epi == EPI_BF16_RESID) {
                     __nv_bfloat16* dst =
                         reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col;
@@ -470,7 +568,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + astage * Cfg::BLOCK_N;
             const bool row_ok = row < p.M;
-            gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row_ok, n_blk, n0, t_row);
+            uint8_t* wbuf = p.staged ? smem_raw + (bar_base + 512u - smem_u32(smem_raw)) + (warp - 4) * 2048 : nullptr;
+            gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row_ok, n_blk, n0, t_row, wbuf, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

@@ -30,7 +30,8 @@ struct GemmWideCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KB
     static constexpr int kStages = 4;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr int STAGING_BYTES = 8 * 2048;          // 2 KB per epilogue warp (coalesced bf16 transfers, sf_gemm.cuh)
+    static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + STAGING_BYTES;
     static constexpr int kThreads = 384;
 };
 
@@ -175,7 +176,8 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(tfull_bar(h), tphase, 4);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + h * Cfg::BLOCK_N;
-            gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row < p.M, n_blk, n0, t_row);
+            uint8_t* wbuf = p.staged ? smem_raw + (bar_base + 512u - smem_u32(smem_raw)) + (warp - 4) * 2048 : nullptr;
+            gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row < p.M, n_blk, n0, t_row, wbuf, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(h), 0);

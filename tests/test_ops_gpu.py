@@ -109,6 +109,39 @@ def test_gemm_wide_fused_epilogues():
         assert torch.equal(t2, t1)
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(1000, 776, 1096, 0), (1000, 776, 1096, 1), (300, 264, 64, 1)])
+def test_gemm_staged_epilogue_narrow(M, N, K, epi):
+    """The warp-staged (coalesced) bf16 epilogue of the 256 x 256 tiling (gemm_epi_staged = 1) == the direct per-thread stores,
+    ragged M / N included; plus the fused SwiGLU epilogues under staging."""
+    from specforge_b200 import ops
+    torch.manual_seed(2)
+    dev = _dev()
+    a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+    R = torch.randn(M, N, device=dev).bfloat16() if epi == 1 else None
+    x = (torch.randn(1000, 512, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(2 * 1280, 512, device=dev) * 0.05).bfloat16()
+    dy = (torch.randn(1000, 512, device=dev) * 0.1).bfloat16()
+    wd = (torch.randn(512, 1280, device=dev) * 0.03).bfloat16()
+    outs = {}
+    try:
+        for st in (-1, 1):
+            _set_opt(b"gemm_wide", -1)
+            _set_opt(b"gemm_epi_staged", st)
+            outs[st] = ops.gemm(a, b, residual=R, epi=epi)
+            if M == 1000 and epi == 0:
+                gu, act = ops.gemm_swiglu(x, w)
+                outs[(st, "sw")] = (gu, act, ops.gemm_swiglu_bwd(dy, wd, gu))
+            torch.cuda.synchronize()
+    finally:
+        _set_opt(b"gemm_wide", 0)
+        _set_opt(b"gemm_epi_staged", 0)
+    assert torch.equal(outs[1], outs[-1])
+    if (1, "sw") in outs:
+        for t2, t1 in zip(outs[(1, "sw")], outs[(-1, "sw")]):
+            assert torch.equal(t2, t1)
+
+
 def test_gemm_step_shapes():
     """The shapes the headline step runs that the small cases above do not reach: the K = T*M = 114 688 weight-gradient
     contraction (MN-major x MN-major, fp32 accumulate in TMEM, EPI_F32_ACCUM) and an N = 151 936 target-head row block."""
