@@ -32,6 +32,29 @@ CPU_SAMPLE_TOKENS = 128
 CPU_MAX_THREADS = 32
 
 
+def gemm_traffic():
+    """`roofline.traffic`: DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the CURRENT
+    kernel sources (profiles/gemm_traffic.json, written by tools/ncu_traffic.py together with a hash of csrc/sf_gemm*).  A capture
+    taken from other sources is reported as stale (traffic: null) instead of being quoted."""
+    import hashlib
+    out = {"traffic": None, "traffic_algorithmic": None, "traffic_kernel": None}
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
+            t = json.load(f)
+        h = hashlib.sha1()
+        for name in ("sf_gemm.cuh", "sf_gemm_wide.cuh", "sf_gemm.cu"):
+            with open(os.path.join(ROOT, "specforge_b200", "csrc", name), "rb") as f:
+                h.update(f.read())
+        if t.get("src_sha1") == h.hexdigest():
+            out.update(traffic=t["dram_read_bytes"] + t["dram_write_bytes"], traffic_algorithmic=t["algorithmic_bytes"],
+                       traffic_kernel=t["kernel"], traffic_source=t.get("source"))
+        else:
+            out["traffic_note"] = "profiles/gemm_traffic.json was captured from other kernel sources (stale): not quoted"
+    except (OSError, KeyError, ValueError):
+        out["traffic_note"] = "no ncu capture committed for this build"
+    return out
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -517,11 +540,16 @@ def run_ours(args):
                      "ms_per_step_with_events": ms_prof / args.steps, "gemm_by_shape": gemm_by_shape,
                      "step_tflops_algorithmic": flops_step / 1e12 / (ms_step / 1e3),
                      "step_frac_of_burst": flops_step / 1e12 / (ms_step / 1e3) / burst if burst else None,
-                     # DRAM bytes of the largest per-TTT-step GEMM (lm_head forward, 16384x32000x4096) from the committed
-                     # `ncu --set full` capture profiles/r01_gemm_ncu_full_e.csv: 1.69 GB read + 1.05 GB written per launch
-                     # vs 1.44 GB algorithmic (weights re-streamed once per 16-M-block group); tensor pipe 87.7 % active
-                     "traffic": 2.738e9, "traffic_algorithmic": 1.445e9, "traffic_kernel": "lm_head forward GEMM"},
+                     **gemm_traffic()},
     }
+    if world > 1:
+        # driver-visible DP correctness: after K optimizer steps on different data every replica must hold the same weights
+        # (one all-reduced gradient, identical fused updates) and have seen the same global gradient norm
+        chk = torch.stack([eng.params.float().sum(), eng.params.float().square().sum(), eng.grad_norm.reshape(()).float()]).double()
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        line["replicas_identical"] = bool(all(torch.equal(allc[0], c) for c in allc))
+        line["replica_checksums"] = [[float(v) for v in c.tolist()] for c in allc] if not line["replicas_identical"] else [float(v) for v in allc[0].tolist()]
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             val, ms, cores, kind, sample = cpu_arm(1, 0)

@@ -33,8 +33,9 @@ extern "C" {
 const char* sf_version(void);
 const char* sf_last_error(void);
 /* Tuning / A-B switch by name ("no_pdl", "loss_side", "no_overlap", "no_swiglu_fusion", "gemm_group_m",
- * "gemm_group_m_midk", "gemm_group_m_wgrad", "dflash_attn_tc" (-1: CUDA-core DFlash attention instead of tcgen05)); each defaults to
- * its SF_<NAME> environment variable.  Diagnostic only. */
+ * "gemm_group_m_midk", "gemm_group_m_wgrad", "dflash_attn_tc" (-1: CUDA-core DFlash attention instead of tcgen05), "gemm_stages",
+ * "gemm_wide" (-1: 256x256 tiling only, 0: 512x256 for M >= 512), "gemm_epi_staged", "no_teacher_fusion", "no_loss_stats_fusion",
+ * "no_rope_fusion"); each defaults to its SF_<NAME> environment variable.  Diagnostic only. */
 int sf_debug_option(const char* name, int value);
 long long sf_launch_count(void);      /* kernels launched by this library since the last reset */
 void sf_launch_count_reset(void);
@@ -46,6 +47,9 @@ void sf_profile_gemm(int enable);
 long long sf_profile_gemm_collect(double* total_ms, double* total_flops);
 /* per launch: mnkt[4 i ..] = {M, N, K, rows per CTA-pair tile (256 | 512)}, ms[i] = device time; returns the number written */
 long long sf_profile_gemm_detail(long long* mnkt, double* ms, long long max_n);
+/* Diagnostic: device buffer of >= 512 uint64 that cluster 0 of the 512 x 256 GEMM tiling fills with clock64() stamps of its
+ * MMA-issuer / epilogue hand-offs (16 per tile; tools/gemm_trace.py); NULL switches it off. */
+void sf_debug_gemm_trace(unsigned long long* dev_buf);
 
 /* ---- model / step description ---- */
 typedef struct sf_eagle3_config {
@@ -154,6 +158,11 @@ int sf_gemm_bf16_ex(const void* A, int64_t lda, int a_major, const void* B, int6
                     void* stream);
 /* out[i, :] = table[ids[i], :] (bf16 [V, H] table, int64 ids; embed_input_ids, llama3_eagle.py:1759-1760) */
 int sf_embedding_gather(const void* table, int64_t V, int H, const int64_t* ids, int64_t n, void* out, void* stream);
+/* D(bf16) [M, N] = RoPE(A W^T): the fused [q;k;v] projection with the rotary embedding applied in the GEMM epilogue to the columns
+ * < rope_cols (heads of head_dim 64 | 128) at position (row % S) + pos_offset; cos / sin: bf16 [rows, head_dim] tables
+ * (llama3_eagle.py:133-142,673-675,730-734).  Identical to sf_gemm_bf16 followed by sf_rope. */
+int sf_gemm_bf16_rope(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
+                      const void* cos_t, const void* sin_t, int S, int pos_offset, int head_dim, int rope_cols, void* stream);
 int sf_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* out, int64_t ldo, int64_t M, int H, float eps,
                    void* stream);
 /* dw (+)= column sums via per-block partials in `scratch` (sf_rmsnorm_bwd_scratch_bytes(H) bytes): deterministic. */

@@ -102,8 +102,8 @@ static Plan make_plan(const sf_eagle3_config& c) {
     // forward temporaries
     p.tgt_shift = take(M * x.Ht * 2);
     p.tlogits = take(M * (int64_t)x.V * 2);
-    p.tpart = take(5 * (int64_t)((x.V + 255) / 256) * M * 4);      // EPI_TEACHER partials [5][n-blocks][M]
-    p.lstats = take(3 * (int64_t)((x.DV + 255) / 256) * M * 4);    // EPI_BF16_STATS partials of one step's lm_head GEMM
+    p.tpart = take(5 * 2 * (int64_t)((x.V + 255) / 256) * M * 4);      // EPI_TEACHER partials [5][<= 2 per n-block][M]
+    p.lstats = take(3 * 2 * (int64_t)((x.DV + 255) / 256) * M * 4);    // EPI_BF16_STATS partials of one step's lm_head GEMM
     p.t2d_bits = take((int64_t)((x.V + 31) / 32) * 4);
     p.t2d_prefix = take((int64_t)((x.V + 31) / 32) * 4);
     const int64_t fwd_end = o;
@@ -234,7 +234,7 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         g.stats = c.at<float>(p.tpart); g.t2d_bits = c.at<uint32_t>(p.t2d_bits); g.t2d_prefix = c.at<int>(p.t2d_prefix);
         g.xg = c.bf(p.xg); g.S = x.S; g.T = T; g.DV = x.DV;
         SF_TRY(gemm(g, st));
-        SF_TRY(teacher_merge(c.at<float>(p.tpart), (x.V + 255) / 256, M, fz.t2d, c.at<int>(p.loss_mask32), c.at<float>(p.tstats),
+        SF_TRY(teacher_merge(c.at<float>(p.tpart), gemm_stats_blocks(g), M, fz.t2d, c.at<int>(p.loss_mask32), c.at<float>(p.tstats),
                              c.at<int64_t>(p.ids), c.at<int>(p.pos_mask), c.bf(p.xg), x.B, x.S, T, x.DV, st));
         side = nullptr;   // nothing left to overlap: the side stream is only used by the unfused path below
         ls = st;
@@ -283,8 +283,16 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         SF_TRY(rmsnorm_fwd(fz.embed_tokens, x.H, bt.input_ids, x.S, 1 + j, c.W[SF_P_INPUT_NORM], xcat, 2 * x.H, M, x.H, cfg.rms_eps, nullptr, st));
         SF_TRY(rmsnorm_fwd(h_in, x.H, nullptr, x.S, 0, c.W[SF_P_HIDDEN_NORM], xcat + x.H, 2 * x.H, M, x.H, cfg.rms_eps, nullptr, st));
         // fused q/k/v projection, RoPE at position s + j   (llama3_eagle.py:673-675,730-734)
-        SF_TRY(mm(c, xcat, 2 * x.H, MAJOR_K, c.W[SF_P_Q], 2 * x.H, MAJOR_K, qkv, x.QKV, nullptr, 0, M, x.QKV, 2 * x.H, EPI_BF16));
-        SF_TRY(rope(qkv, nullptr, x.QKV, 0, x.nh + x.nkv, x.d, fz.rope_cos, fz.rope_sin, x.S, j, M, 0, st));
+        if (opt(OPT_NO_ROPE_FUSION) != 1) {   // RoPE of the q and k heads inside the projection's epilogue (v columns pass through)
+            GemmDesc g;
+            g.A = xcat; g.lda = 2 * x.H; g.a_major = MAJOR_K; g.B = c.W[SF_P_Q]; g.ldb = 2 * x.H; g.b_major = MAJOR_K;
+            g.D = qkv; g.ldd = x.QKV; g.R = nullptr; g.ldr = 0; g.M = (int)M; g.N = (int)x.QKV; g.K = 2 * x.H; g.epi = EPI_BF16_ROPE; g.cta_group = 0;
+            g.rope_cos = fz.rope_cos; g.rope_sin = fz.rope_sin; g.S = x.S; g.rope_pos0 = j; g.head_dim = x.d; g.rope_cols = (int)(x.A + x.KV);
+            SF_TRY(gemm(g, st));
+        } else {
+            SF_TRY(mm(c, xcat, 2 * x.H, MAJOR_K, c.W[SF_P_Q], 2 * x.H, MAJOR_K, qkv, x.QKV, nullptr, 0, M, x.QKV, 2 * x.H, EPI_BF16));
+            SF_TRY(rope(qkv, nullptr, x.QKV, 0, x.nh + x.nkv, x.d, fz.rope_cos, fz.rope_sin, x.S, j, M, 0, st));
+        }
         // TTT attention   (llama3_eagle.py:739-785)
         AttnDesc a{};
         a.q = qkv; a.ldq = x.QKV; a.ldkv = x.QKV; a.out = attn; a.ldo = x.A; a.lse = lse; a.sd_ws = c.at<float>(p.sd_ws);
@@ -310,11 +318,13 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         if (cfg.norm_output)
             SF_TRY(rmsnorm_fwd(h_out, x.H, nullptr, x.S, 0, c.W[SF_P_NORM], hf, x.H, M, x.H, cfg.rms_eps, nullptr, st));
         const bool fuse_stats = opt(OPT_NO_LOSS_STATS_FUSION) != 1 && !(side && loss_on_side());   // one partials buffer: the loss must run in stream order
+        int stats_nb = 0;
         if (fuse_stats) {   // logits + per-tile (max, sum-exp, argmax) partials: the loss kernel's first pass over the row disappears
             GemmDesc g;
             g.A = hf; g.lda = x.H; g.a_major = MAJOR_K; g.B = c.W[SF_P_LM_HEAD]; g.ldb = x.H; g.b_major = MAJOR_K;
             g.D = logits; g.ldd = x.DV; g.R = nullptr; g.ldr = 0; g.M = (int)M; g.N = x.DV; g.K = x.H; g.epi = EPI_BF16_STATS; g.cta_group = 0;
             g.stats = c.at<float>(p.lstats);
+            stats_nb = gemm_stats_blocks(g);
             SF_TRY(gemm(g, st));
         } else {
             SF_TRY(mm(c, hf, x.H, MAJOR_K, c.W[SF_P_LM_HEAD], x.H, MAJOR_K, logits, x.DV, nullptr, 0, M, x.DV, x.H, EPI_BF16));
@@ -337,7 +347,7 @@ static int forward(Ctx& c, const sf_eagle3_frozen& fz, const sf_eagle3_batch& bt
         SF_TRY(loss_step(logits, x.DV, c.bf(p.xg), c.at<float>(p.tstats), c.at<int64_t>(p.ids), c.at<int>(p.pos_mask),
                          c.at<int>(p.loss_mask32), fz.d2t, x.B, x.S, T, x.DV, j, step_weight, need_grad, cfg.lk_loss_type,
                          cfg.kl_scale, cfg.kl_decay, c.at<float>(p.row_ws), c.at<float>(p.metrics),
-                         fuse_stats ? c.at<float>(p.lstats) : nullptr, (x.DV + 255) / 256, on_side ? ls : st));
+                         fuse_stats ? c.at<float>(p.lstats) : nullptr, stats_nb, on_side ? ls : st));
     }
     total_loss_kernel<<<1, 64, 0, st>>>(c.at<float>(p.metrics), T, cfg.ploss_decay, loss_out ? loss_out : c.at<float>(p.misc), metrics_out);
     SF_CUDA_CHECK_LAUNCH("total_loss");
@@ -566,6 +576,14 @@ extern "C" int sf_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* o
 extern "C" int sf_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const void* dy, int64_t lddy, const void* add, void* dx,
                               float* dw, float* scratch, int64_t M, int H, float eps, void* stream) {
     return rmsnorm_bwd(x, ldx, nullptr, 1, 0, w, dy, lddy, add, nullptr, dx, dw, scratch, M, H, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int sf_gemm_bf16_rope(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
+                                 const void* cos_t, const void* sin_t, int S, int pos_offset, int head_dim, int rope_cols, void* stream) {
+    GemmDesc g;
+    g.A = A; g.lda = lda; g.a_major = MAJOR_K; g.B = B; g.ldb = ldb; g.b_major = MAJOR_K; g.D = D; g.ldd = ldd; g.R = nullptr; g.ldr = 0;
+    g.M = M; g.N = N; g.K = K; g.epi = EPI_BF16_ROPE; g.cta_group = 0;
+    g.rope_cos = cos_t; g.rope_sin = sin_t; g.S = S; g.rope_pos0 = pos_offset; g.head_dim = head_dim; g.rope_cols = rope_cols;
+    return gemm(g, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int sf_embedding_gather(const void* table, int64_t V, int H, const int64_t* ids, int64_t n, void* out, void* stream) {
     if (!table || !ids || !out) return set_error(-22, "null argument");

@@ -51,6 +51,7 @@ struct GemmProf {
     size_t used = 0;
 };
 static GemmProf g_prof;
+static unsigned long long* g_trace = nullptr;   // sf_debug_gemm_trace
 static std::mutex g_prof_mu;
 
 static int num_sms() {
@@ -81,6 +82,9 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     p.D2 = g.D2; p.ldd2 = (int)g.ldd2; p.n_half = g.n_half;
     p.stats = g.stats; p.t2d_bits = g.t2d_bits; p.t2d_prefix = g.t2d_prefix; p.xg = reinterpret_cast<__nv_bfloat16*>(g.xg);
     p.S = g.S; p.T = g.T; p.DV = g.DV;
+    p.rope_cos = reinterpret_cast<const __nv_bfloat16*>(g.rope_cos); p.rope_sin = reinterpret_cast<const __nv_bfloat16*>(g.rope_sin);
+    p.rope_cols = g.rope_cols; p.rope_pos0 = g.rope_pos0; p.head_dim = g.head_dim;
+    p.trace = g_trace;
     p.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
     p.num_n_blocks = (g.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
     // Raster: tiles walk N inside groups of `group_m` M-blocks, so a group's A rows stay L2-resident while B streams.
@@ -157,6 +161,9 @@ static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
     p.D2 = g.D2; p.ldd2 = (int)g.ldd2; p.n_half = g.n_half;
     p.stats = g.stats; p.t2d_bits = g.t2d_bits; p.t2d_prefix = g.t2d_prefix; p.xg = reinterpret_cast<__nv_bfloat16*>(g.xg);
     p.S = g.S; p.T = g.T; p.DV = g.DV;
+    p.rope_cos = reinterpret_cast<const __nv_bfloat16*>(g.rope_cos); p.rope_sin = reinterpret_cast<const __nv_bfloat16*>(g.rope_sin);
+    p.rope_cols = g.rope_cols; p.rope_pos0 = g.rope_pos0; p.head_dim = g.head_dim;
+    p.trace = g_trace;
     p.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
     p.num_n_blocks = (g.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
     const int gm = opt(OPT_GEMM_GROUP_M), gmk = opt(OPT_GEMM_GROUP_M_MIDK), gmw = opt(OPT_GEMM_GROUP_M_WGRAD);
@@ -208,23 +215,42 @@ static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
     return 0;
 }
 // Which tiling.  The wide one moves 25 % fewer operand bytes per FLOP but cannot hide its epilogue behind the next tile's main loop
-// (all 512 TMEM columns hold one tile), so it pays roughly one accumulator drain per tile.  Measured on B200 next to the 256 x 256
-// tiling and cuBLAS (profiles/r02_gemm_vs_cublas_c.txt, isolated kernels, random operands): with the warp-staged epilogue K = 4096
-// tiles lose 2 % (4.6 % under the teacher-statistics epilogue), K = 8192 gains 3 %, K >= 12288 gains 5-17 %; inside the step
-// (bench.py --ab gemm_wide=-1,0,2, settings alternated step by step on one box) always-wide is the fastest setting by 1-3 %: the
-// lower L2 -> SM traffic also buys clock under the 1 kW cap.  gemm_wide: -1 never, 0 (default) always for M >= 512,
-// 1 = as 0 but the 256 x 256 tiling for the row-statistics epilogues at K <= 4096, 3 = only K > 8192.
+// (all 512 TMEM columns hold one tile), so the accumulator drain is paid once per tile — and TMEM reads run at 64 B/clk per SM
+// (tools/gemm_trace.py: ~5 k cycles per 128 x 256 half next to the other half's MMAs, ~11 k exposed per tile of 65 k at K = 4096).
+// Measured on B200 next to the 256 x 256 tiling and cuBLAS (profiles/r02_gemm_vs_cublas_d.txt, isolated kernels, random operands):
+// K = 4096 tiles lose 3 %, K = 8192 gains 4 %, K = 12 288 gains 9 %, K >= 24 576 gains 13-20 % (0.95-0.97 of cuBLAS).  Inside the step
+// (bench.py --ab gemm_wide=0,2,-1, alternated step by step on one box, profiles/r02_ab_gemm_tiling.jsonl): wide for K > 4096 only
+// 230.2 ms, wide everywhere but the statistics epilogues 243.3 ms, never 240.4 ms.
+// In-step rates by shape (bench.py roofline.gemm_by_shape) show why: with its drain exposed the wide tiling runs the SwiGLU
+// epilogues at 780-1065 TFLOP/s at K = 4096 (1350 in the 256 x 256 tiling, where the epilogue hides behind the next tile).
+// gemm_wide: -1 never; 0 (default) M >= 512 and K > 4096, K > 8192 for the heavy epilogues (SwiGLU fwd/bwd, RoPE, row statistics);
+// 1 every GEMM except the row-statistics epilogues at K <= 4096; 2 always; 3 only K > 8192.
 static bool use_wide(const GemmDesc& g) {
     const int o = opt(OPT_GEMM_WIDE);
     if (o < 0 || g.M < 512) return false;
+    if (o == 2) return true;
     if (o == 3) return g.K > 8192;
-    if (o == 1 && g.K <= 4096 && (g.epi == EPI_TEACHER || g.epi == EPI_BF16_STATS)) return false;
-    return true;
+    const bool stats = g.epi == EPI_TEACHER || g.epi == EPI_BF16_STATS;
+    if (o == 1) return g.K > 4096 || !stats;
+    const bool heavy = stats || g.epi == EPI_SWIGLU || g.epi == EPI_SWIGLU_BWD || g.epi == EPI_BF16_ROPE;
+    return g.K > (heavy ? 8192 : 4096);
+}
+
+// Number of per-row partial blocks the row-statistics epilogues (EPI_BF16_STATS / EPI_TEACHER) of this GEMM will write: one per
+// 256-column n-block in the 256 x 256 tiling, two (column halves, one per epilogue warpgroup) in the 512 x 256 tiling.
+int gemm_stats_blocks(const GemmDesc& g) {
+    const int nb = (g.N + 255) / 256;
+    int G = g.cta_group;
+    if (G == 0) G = (g.M > 128) ? 2 : 1;
+    return (G == 2 && g.cta_group == 0 && use_wide(g)) ? 2 * nb : nb;
 }
 
 int gemm(const GemmDesc& g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(-22, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
-    if (g.epi < 0 || g.epi > 7) return set_error(-22, "gemm: bad epilogue %d", g.epi);
+    if (g.epi < 0 || g.epi > 8) return set_error(-22, "gemm: bad epilogue %d", g.epi);
+    if (g.epi == EPI_BF16_ROPE && (!g.rope_cos || !g.rope_sin || g.S <= 0 || (g.head_dim != 64 && g.head_dim != 128) || g.rope_cols % g.head_dim ||
+                                   g.N % g.head_dim || g.rope_cols > g.N))
+        return set_error(-22, "gemm: RoPE epilogue needs cos/sin tables, S, head_dim 64|128, rope_cols and N multiples of head_dim");
     if ((g.epi == EPI_BF16_STATS || g.epi == EPI_TEACHER) && !g.stats) return set_error(-22, "gemm: statistics epilogue without a stats buffer");
     if (g.epi == EPI_TEACHER && (!g.t2d_bits || !g.t2d_prefix || !g.xg || g.S <= 0 || g.DV <= 0)) return set_error(-22, "gemm: teacher epilogue needs t2d_bits, t2d_prefix, xg, S, DV");
     if (g.epi == EPI_SWIGLU) {
@@ -316,3 +342,7 @@ extern "C" int sf_gemm_bf16_ex(const void* A, int64_t lda, int a_major, const vo
     g.D2 = D2; g.ldd2 = ldd2; g.n_half = n_half;
     return sf::gemm(g, reinterpret_cast<cudaStream_t>(stream));
 }
+
+// Diagnostic: device buffer (>= 32 tiles x 16 stamps of clock64()) that cluster 0 / CTA 0 of the 512 x 256 GEMM kernel fills with the
+// times of its MMA-issuer and epilogue hand-offs; nullptr switches the tracing off.  See tools/gemm_trace.py.
+extern "C" void sf_debug_gemm_trace(unsigned long long* dev_buf) { sf::g_trace = dev_buf; }

@@ -45,6 +45,11 @@ enum : int {
     //                   (eagle3/model.py:487-501; this is also core/compact_teacher.py:57-150's streaming logsumexp/argmax).
     EPI_BF16_STATS = 6,
     EPI_TEACHER = 7,
+    // D(bf16) = RoPE(bf16(acc)) on the columns < rope_cols (the q and k heads of a fused [q;k;v] projection), plain bf16 beyond:
+    // x' = x cos + rotate_half(x) sin at position (row % S) + rope_pos0, cos / sin the reference's bf16 tables [rows, head_dim]
+    // (llama3_eagle.py:133-142; fp32 math on the bf16-rounded linear output, one rounding — what the standalone rope kernel
+    // computes).  Needs head_dim in {64, 128} and rope_cols % head_dim == 0; a head never straddles a 128-column part.
+    EPI_BF16_ROPE = 8,
 };
 
 struct GemmParams {
@@ -64,6 +69,9 @@ struct GemmParams {
     const uint32_t* t2d_bits;      // [ceil(N / 32)] bit e of word w: column 32 w + e is in the draft vocabulary
     const int* t2d_prefix;         // [ceil(N / 32)] draft-vocab columns before column 32 w
     __nv_bfloat16* xg; int S, T, DV;
+    // EPI_BF16_ROPE (S as above = sequence length)
+    const __nv_bfloat16* rope_cos; const __nv_bfloat16* rope_sin; int rope_cols, rope_pos0, head_dim;
+    unsigned long long* trace;     // diagnostic (sf_debug_gemm_trace): cluster 0 / CTA 0 writes clock64() stamps, 16 per tile
 };
 
 template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN>
@@ -135,7 +143,10 @@ __device__ __forceinline__ void warp_load_32x32(uint8_t* wbuf, int lane, uint32_
 // staging block (bf16 outputs / inputs then move as described above) or nullptr (direct per-thread accesses).
 template <int kBlockN>
 __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const int row, const bool row_ok, const int n_blk,
-                                                   const int n0, const uint32_t t_row, uint8_t* wbuf, const int lane) {
+                                                   const int n0, const uint32_t t_row, uint8_t* wbuf, const int lane,
+                                                   const int part = 0, const int nparts = 1) {
+            // part / nparts: this call covers the part-th of nparts equal column ranges of the tile (the 512 x 256 tiling drains
+            // each accumulator half with two warpgroups side by side); the row-statistics partials are then per (n-block, part)
             const int row0 = row - lane;                                   // first row of this warp's 32-row block
             const int rows_valid = min(32, max(0, p.M - row0));
             if (p.epi == EPI_SWIGLU) {
@@ -144,7 +155,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                 __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
                 __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.D2) + (size_t)row * p.ldd2;
 #pragma unroll 1
-                for (int c = 0; c < kBlockN / 64; ++c) {
+                for (int c = part * (kBlockN / 64 / nparts); c < (part + 1) * (kBlockN / 64 / nparts); ++c) {
                     uint32_t g[32], u[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, g);
                     tmem_ld_32x32b_x32(t_row + kBlockN / 2 + c * 32, u);
@@ -182,7 +193,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                 const __nv_bfloat16* gu = p.R + (size_t)row * p.ldr;
                 __nv_bfloat16* dgu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
 #pragma unroll 1
-                for (int c = 0; c < kBlockN / 32; ++c) {
+                for (int c = part * (kBlockN / 32 / nparts); c < (part + 1) * (kBlockN / 32 / nparts); ++c) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
                     tmem_ld_wait();
@@ -241,7 +252,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                 __nv_bfloat16* xo = nullptr;
                 if (gather && row_ok) xo = p.xg + ((size_t)row + (size_t)(row / p.S) * p.T) * p.DV;
 #pragma unroll 1
-                for (int c = 0; c < kBlockN / 32; ++c) {
+                for (int c = part * (kBlockN / 32 / nparts); c < (part + 1) * (kBlockN / 32 / nparts); ++c) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
                     tmem_ld_wait();
@@ -306,15 +317,80 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         }
                     }
                 }
-                if (row_ok && n0 < p.N) {
-                    const size_t plane = (size_t)p.num_n_blocks * p.M;
-                    float* sp = p.stats + (size_t)n_blk * p.M + row;
+                if (row_ok) {   // a part with no valid column writes the neutral state (max -inf, sum 0), which the merges skip
+                    const size_t plane = (size_t)p.num_n_blocks * nparts * p.M;
+                    float* sp = p.stats + ((size_t)n_blk * nparts + part) * p.M + row;
                     sp[0] = m; sp[plane] = d; sp[2 * plane] = __int_as_float(idx);
                     if (gather) { sp[3 * plane] = md; sp[4 * plane] = dd; }
                 }
+            } else if (p.epi == EPI_BF16_ROPE) {
+                // chunk pairs (c, c + half/32) of one head: x1 = columns [hc, hc+32), x2 = columns [hc + half, hc + half + 32)
+                const int hchunks = p.head_dim / 32, pairs = hchunks / 2;              // 4 / 2 (d = 128) or 2 / 1 (d = 64)
+                const int pos = (row_ok ? row % p.S : 0) + p.rope_pos0;
+                const __nv_bfloat16* cosr = p.rope_cos + (size_t)pos * p.head_dim;
+                const __nv_bfloat16* sinr = p.rope_sin + (size_t)pos * p.head_dim;
+                __nv_bfloat16* drow0 = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row0 * p.ldd;
+                __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
+                const int c_begin = part * (kBlockN / 32 / nparts), c_end = (part + 1) * (kBlockN / 32 / nparts);
+#pragma unroll 1
+                for (int cb = c_begin; cb < c_end; cb += hchunks) {                      // one head per iteration
+#pragma unroll 1
+                    for (int cc = 0; cc < pairs; ++cc) {
+                        const int c1 = cb + cc, c2 = c1 + pairs;
+                        uint32_t v1[32], v2[32];
+                        tmem_ld_32x32b_x32(t_row + c1 * 32, v1);
+                        tmem_ld_32x32b_x32(t_row + c2 * 32, v2);
+                        tmem_ld_wait();
+                        const int col1 = n0 + c1 * 32, col2 = n0 + c2 * 32;
+                        if (col1 >= p.N) continue;                                       // host: N % head_dim == 0 -> whole pairs
+                        uint32_t o1[16], o2[16];
+                        if (col1 < p.rope_cols) {
+                            const int hc = (col1 % p.head_dim);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(cosr + hc) + q);
+                                const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(sinr + hc) + q);
+                                const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w}, sw[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const __nv_bfloat162 cb2 = *reinterpret_cast<const __nv_bfloat162*>(&cw[e]);
+                                    const __nv_bfloat162 sb2 = *reinterpret_cast<const __nv_bfloat162*>(&sw[e]);
+                                    const int i = q * 8 + e * 2;
+                                    float a[2], b[2];
+#pragma unroll
+                                    for (int w = 0; w < 2; ++w) {
+                                        const float x1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v1[i + w])));
+                                        const float x2 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v2[i + w])));
+                                        const float cf = __bfloat162float(w ? cb2.y : cb2.x), sf_ = __bfloat162float(w ? sb2.y : sb2.x);
+                                        a[w] = x1 * cf - x2 * sf_;
+                                        b[w] = x2 * cf + x1 * sf_;
+                                    }
+                                    o1[q * 4 + e] = pack_bf16x2(a[0], a[1]);
+                                    o2[q * 4 + e] = pack_bf16x2(b[0], b[1]);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                o1[e] = pack_bf16x2(__uint_as_float(v1[2 * e]), __uint_as_float(v1[2 * e + 1]));
+                                o2[e] = pack_bf16x2(__uint_as_float(v2[2 * e]), __uint_as_float(v2[2 * e + 1]));
+                            }
+                        }
+                        if (wbuf) {
+                            warp_store_32x32(wbuf, lane, o1, drow0 + col1, p.ldd, rows_valid);
+                            warp_store_32x32(wbuf, lane, o2, drow0 + col2, p.ldd, rows_valid);
+                        } else if (row_ok) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                reinterpret_cast<uint4*>(drow + col1)[q] = make_uint4(o1[q * 4], o1[q * 4 + 1], o1[q * 4 + 2], o1[q * 4 + 3]);
+                                reinterpret_cast<uint4*>(drow + col2)[q] = make_uint4(o2[q * 4], o2[q * 4 + 1], o2[q * 4 + 2], o2[q * 4 + 3]);
+                            }
+                        }
+                    }
+                }
             } else
 #pragma unroll 1
-            for (int c = 0; c < kBlockN / 32; ++c) {
+            for (int c = part * (kBlockN / 32 / nparts); c < (part + 1) * (kBlockN / 32 / nparts); ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + c * 32, v);
                 tmem_ld_wait();

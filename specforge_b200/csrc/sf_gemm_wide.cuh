@@ -69,7 +69,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int h = 0; h < 2; ++h) {
             mbar_init(tfull_bar(h), 1);
-            mbar_init(tempty_bar(h), 4 * 2);   // the four warps of half h's epilogue warpgroup in each CTA of the pair
+            mbar_init(tempty_bar(h), 8 * 2);   // all eight epilogue warps of each CTA of the pair drain every half together
         }
         fence_mbar_init();
     }
@@ -138,49 +138,80 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         constexpr uint32_t b_kstep = (kBMajor == MAJOR_K) ? 32u : 2048u;
         int stage = 0;
         uint32_t phase = 0, tphase = 0;
+        // Half 0 runs ONE k-block ahead of half 1 ( h0(0) | h0(1) h1(0) | h0(2) h1(1) | ... | h1(n-1) ): half 0's accumulator is
+        // complete two half-steps before half 1's, its drain starts earlier, and at the start of the next tile the tensor pipe has
+        // two half-steps of half-0 work to do while half 1 is still being drained.
+        auto issue_half = [&](int h, int st, bool first) {
+            const uint32_t sa = smem_base + st * Cfg::STAGE_BYTES;
+            const uint64_t adesc = make_smem_desc_sw128(sa + h * Cfg::A_HALF_BYTES, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::A_BYTES, b_lbo, 1024);
+            const uint32_t d_tmem = tmem_base + h * Cfg::BLOCK_N;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / Cfg::UMMA_K; ++k)
+                umma_bf16<2>(d_tmem, adesc + ((k * a_kstep) >> 4), bdesc + ((k * b_kstep) >> 4), idesc, (first && k == 0) ? 0u : 1u);
+        };
+        int tcount = 0;
+        unsigned long long* tr = (p.trace && cluster_id == 0) ? p.trace : nullptr;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            if (tr && tcount < 32) tr[tcount * 16 + 0] = clock64();
+            mbar_wait(full_bar(stage), phase, 3);
+            if (tr && tcount < 32) tr[tcount * 16 + 1] = clock64();
+            mbar_wait(tempty_bar(0), tphase ^ 1u, 2);     // half 0's accumulator drained by the epilogue warps
+            if (tr && tcount < 32) tr[tcount * 16 + 2] = clock64();
+            tc_fence_after();
+            issue_half(0, stage, true);
+            if (num_k_blocks == 1) umma_commit_pair(tfull_bar(0), 0b11);
             for (int kb = 0; kb < num_k_blocks; ++kb) {
-                mbar_wait(full_bar(stage), phase, 3);
-                tc_fence_after();
-                const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                const uint32_t sb = sa + Cfg::A_BYTES;
-                const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (kb == 0) {   // this half's accumulator must have been drained by its epilogue warpgroup
-                        mbar_wait(tempty_bar(h), tphase ^ 1u, 2);
-                        tc_fence_after();
-                    }
-                    const uint64_t adesc = make_smem_desc_sw128(sa + h * Cfg::A_HALF_BYTES, a_lbo, 1024);
-                    const uint32_t d_tmem = tmem_base + h * Cfg::BLOCK_N;
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / Cfg::UMMA_K; ++k)
-                        umma_bf16<2>(d_tmem, adesc + ((k * a_kstep) >> 4), bdesc + ((k * b_kstep) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
-                    if (kb == num_k_blocks - 1) umma_commit_pair(tfull_bar(h), 0b11);
+                int nstage = stage + 1;
+                uint32_t nphase = phase;
+                if (nstage == kStages) { nstage = 0; nphase ^= 1u; }
+                if (kb + 1 < num_k_blocks) {
+                    mbar_wait(full_bar(nstage), nphase, 3);
+                    tc_fence_after();
+                    issue_half(0, nstage, false);
+                    if (kb + 2 == num_k_blocks) umma_commit_pair(tfull_bar(0), 0b11);
                 }
+                if (kb == 0) {
+                    mbar_wait(tempty_bar(1), tphase ^ 1u, 2);
+                    if (tr && tcount < 32) tr[tcount * 16 + 3] = clock64();
+                    tc_fence_after();
+                }
+                issue_half(1, stage, kb == 0);
                 umma_commit_pair(empty_bar(stage), 0b11);
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                if (kb + 1 == num_k_blocks) umma_commit_pair(tfull_bar(1), 0b11);
+                stage = nstage; phase = nphase;
+                if (tr && tcount < 32 && kb == num_k_blocks / 2) tr[tcount * 16 + 4] = clock64();
             }
+            if (tr && tcount < 32) tr[tcount * 16 + 5] = clock64();
+            ++tcount;
             tphase ^= 1u;
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: one warpgroup per accumulator half =====================
-        const int h = (warp - 4) >> 2;
+        // ===================== epilogue: both warpgroups drain half 0, then half 1 (128 columns each) =====================
+        const int part = (warp - 4) >> 2;
         const int wq = warp & 3;  // TMEM lane quadrant this warp may read
         uint32_t tphase = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        uint8_t* wbuf = p.staged ? smem_raw + (bar_base + 512u - smem_u32(smem_raw)) + (warp - 4) * 2048 : nullptr;
+        int tcount = 0;
+        unsigned long long* tr = (p.trace && cluster_id == 0 && is_leader && warp == 4 && lane == 0) ? p.trace : nullptr;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
             int m_blk, n_blk;
             tile_coords(tile, m_blk, n_blk);
-            const int row = m_blk * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M + h * 128 + wq * 32 + lane;
             const int n0 = n_blk * Cfg::BLOCK_N;
-            mbar_wait(tfull_bar(h), tphase, 4);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + h * Cfg::BLOCK_N;
-            uint8_t* wbuf = p.staged ? smem_raw + (bar_base + 512u - smem_u32(smem_raw)) + (warp - 4) * 2048 : nullptr;
-            gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row < p.M, n_blk, n0, t_row, wbuf, lane);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_bar(h), 0);
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int row = m_blk * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M + h * 128 + wq * 32 + lane;
+                if (tr && tcount < 32) tr[tcount * 16 + 8 + h * 3] = clock64();
+                mbar_wait(tfull_bar(h), tphase, 4);
+                if (tr && tcount < 32) tr[tcount * 16 + 9 + h * 3] = clock64();
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + h * Cfg::BLOCK_N;
+                gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row < p.M, n_blk, n0, t_row, wbuf, lane, part, 2);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_bar(h), 0);
+                if (tr && tcount < 32) tr[tcount * 16 + 10 + h * 3] = clock64();
+            }
             tphase ^= 1u;
         }
     }

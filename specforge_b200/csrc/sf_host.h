@@ -12,7 +12,7 @@ void count_launch(int n = 1);
 
 // Tuning / A-B switches.  Each starts from its environment variable (SF_<NAME>, upper case) and can be changed at run time
 // through sf_debug_option() so that two settings can be alternated inside ONE process (boxes of the pool differ by +-8 %).
-enum Opt { OPT_NO_PDL, OPT_LOSS_SIDE, OPT_NO_OVERLAP, OPT_NO_SWIGLU_FUSION, OPT_GEMM_GROUP_M, OPT_GEMM_GROUP_M_MIDK, OPT_GEMM_GROUP_M_WGRAD, OPT_DFLASH_ATTN_TC, OPT_GEMM_STAGES, OPT_NO_TEACHER_FUSION, OPT_NO_LOSS_STATS_FUSION, OPT_GEMM_WIDE, OPT_GEMM_EPI_STAGED, OPT_COUNT };
+enum Opt { OPT_NO_PDL, OPT_LOSS_SIDE, OPT_NO_OVERLAP, OPT_NO_SWIGLU_FUSION, OPT_GEMM_GROUP_M, OPT_GEMM_GROUP_M_MIDK, OPT_GEMM_GROUP_M_WGRAD, OPT_DFLASH_ATTN_TC, OPT_GEMM_STAGES, OPT_NO_TEACHER_FUSION, OPT_NO_LOSS_STATS_FUSION, OPT_GEMM_WIDE, OPT_GEMM_EPI_STAGED, OPT_NO_ROPE_FUSION, OPT_COUNT };
 int opt(Opt o);
 
 struct GemmDesc {
@@ -28,10 +28,13 @@ struct GemmDesc {
     // EPI_BF16_STATS / EPI_TEACHER (see sf_gemm.cuh): partial row statistics [3 or 5][ceil(N/256)][M], draft-vocab gather
     float* stats = nullptr; const uint32_t* t2d_bits = nullptr; const int* t2d_prefix = nullptr;
     void* xg = nullptr; int S = 0, T = 0, DV = 0;
+    // EPI_BF16_ROPE: RoPE of the columns < rope_cols at position (row % S) + rope_pos0 (cos / sin: bf16 [rows, head_dim] tables)
+    const void* rope_cos = nullptr; const void* rope_sin = nullptr; int rope_cols = 0, rope_pos0 = 0, head_dim = 0;
     int overlap_prev = 0;                      // 1: independent of the previous kernel in the stream — programmatic
                                                // dependent launch lets its CTAs start on the SMs the previous GEMM's tail frees
 };
 int gemm(const GemmDesc& g, cudaStream_t stream);
+int gemm_stats_blocks(const GemmDesc& g);   // partial blocks per row the statistics epilogues of g write (tiling-dependent)
 
 // TTT attention at step j = J (J diagonal blocks).  k[i]/v[i]: [B*S, nkv*D] views of block i (row stride ldkv).
 struct AttnDesc {

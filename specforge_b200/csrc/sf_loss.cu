@@ -200,7 +200,7 @@ teacher_merge_kernel(const float* __restrict__ stats, int nb, int64_t M, const u
         const float* sp = stats + (size_t)b * M + r;
         const float pm = sp[0], pd = sp[plane], pmd = sp[3 * plane], pdd = sp[4 * plane];
         if (pm > m) { d = d * __expf(m - pm) + pd; m = pm; idx = __float_as_int(sp[2 * plane]); }
-        else d += pd * __expf(pm - m);
+        else if (pm > -INFINITY) d += pd * __expf(pm - m);
         if (pmd > md) { dd = dd * __expf(md - pmd) + pdd; md = pmd; }
         else if (pmd > -INFINITY) dd += pdd * __expf(pmd - md);
     }
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
                 const float* sp = p.stats + (size_t)nb * p.M + r;
                 const float pm = __ldg(sp), pd = __ldg(sp + plane);
                 if (pm > mi.v) { d = d * __expf(mi.v - pm) + pd; mi.v = pm; mi.i = __float_as_int(__ldg(sp + 2 * plane)); }
-                else d += pd * __expf(pm - mi.v);
+                else if (pm > -INFINITY) d += pd * __expf(pm - mi.v);
             }
             const float my_m = mi.v;
             mi = warp_argmax(mi);                                     // equal maxima: the smaller index wins

@@ -34,6 +34,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major=MAJOR_K, b_major=MAJOR_K, 
     return out
 
 
+def gemm_rope(x: torch.Tensor, w: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, S: int, pos_offset: int, head_dim: int,
+              rope_cols: int) -> torch.Tensor:
+    """qkv = RoPE(x @ w.T): projection with the rotary embedding fused into the GEMM epilogue (columns < rope_cols rotated)."""
+    import ctypes
+    l = lib()
+    l.sf_gemm_bf16_rope.restype = ctypes.c_int
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    check(l.sf_gemm_bf16_rope(P(x), ctypes.c_int64(x.stride(0)), P(w), ctypes.c_int64(w.stride(0)), P(out), ctypes.c_int64(N), M, N, K,
+                              P(cos), P(sin), S, pos_offset, head_dim, rope_cols, ctypes.c_void_p(_stream())), "sf_gemm_bf16_rope")
+    return out
+
+
 def gemm_swiglu(x: torch.Tensor, w_gate_up: torch.Tensor):
     """(gu, act) = fused gate/up projection + SwiGLU (EPI_SWIGLU): x [M, K], w_gate_up [2I, K] -> gu [M, 2I], act [M, I]."""
     import ctypes

@@ -142,6 +142,37 @@ def test_gemm_staged_epilogue_narrow(M, N, K, epi):
             assert torch.equal(t2, t1)
 
 
+@pytest.mark.parametrize("hd,nh,nkv,M,S", [(128, 4, 2, 640, 160), (64, 6, 2, 600, 100), (128, 2, 1, 96, 96)])
+def test_gemm_rope_epilogue(hd, nh, nkv, M, S):
+    """RoPE fused into the [q;k;v] projection's epilogue (EPI_BF16_ROPE) == the plain GEMM followed by the rope kernel, bit for bit,
+    in both tilings (M >= 512: 512 x 256 warp-staged; M = 96: the 1-CTA kernel), positions wrapping at sequence boundaries."""
+    from oracle import eagle3_oracle as O
+    from specforge_b200 import ops
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(4)
+    cfg = O.Eagle3Config(hidden_size=256, intermediate_size=512, num_heads=nh, num_kv_heads=nkv, head_dim=hd, vocab_size=1024,
+                         draft_vocab_size=256, rope_theta=1e4, max_position_embeddings=512)
+    cos, sin = O.rope_tables(cfg, torch.bfloat16)
+    cos, sin = cos.to(dev).contiguous(), sin.to(dev).contiguous()
+    K, N = 320, (nh + 2 * nkv) * hd
+    x = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    for wide in (-1, 0):
+        _set_opt(b"gemm_wide", wide)
+        try:
+            fused = ops.gemm_rope(x, w, cos, sin, S, 3, hd, (nh + nkv) * hd)
+            ref = ops.gemm(x, w)
+        finally:
+            _set_opt(b"gemm_wide", 0)
+        ops.rope_(ref, nh + nkv, hd, cos, sin, S, 3, inverse=False)
+        torch.cuda.synchronize()
+        # same arithmetic (fp32 on the bf16-rounded projection, one rounding); the two kernels may contract x1*c - x2*s into FMAs
+        # differently, so allow a last-bit difference on a vanishing fraction of the elements
+        assert (fused != ref).float().mean().item() < 1e-3, wide
+        assert (fused.float() - ref.float()).abs().max().item() <= 2 ** -7 * ref.float().abs().max().item(), wide
+        assert torch.equal(fused[:, (nh + nkv) * hd:], ref[:, (nh + nkv) * hd:])       # v columns pass through untouched
+
+
 def test_gemm_step_shapes():
     """The shapes the headline step runs that the small cases above do not reach: the K = T*M = 114 688 weight-gradient
     contraction (MN-major x MN-major, fp32 accumulate in TMEM, EPI_F32_ACCUM) and an N = 151 936 target-head row block."""
