@@ -36,7 +36,7 @@ enum : int {
     EPI_SWIGLU_BWD = 5,
     // Row statistics fused into the epilogue (the reductions of _compute_target_p / LogSoftmaxLoss pass A move into the GEMM
     // that produces the row).  Per (row, n-block) the epilogue emits partial online-softmax state over the bf16-ROUNDED outputs
-    // x = bf16(acc):  stats[k][n_blk][row], k = 0 max, 1 sum exp(x - max), 2 first index of the max (int bits); a small merge
+    // x = bf16(acc):  stats[k][row][n_blk], k = 0 max, 1 sum exp(x - max), 2 first index of the max (int bits); a small merge
     // kernel combines the n-blocks in ascending order (first index wins ties = torch.argmax).
     //   EPI_BF16_STATS: D(bf16) = acc as EPI_BF16, plus the three partials          (draft lm_head -> loss pass A)
     //   EPI_TEACHER:    no D at all.  Columns flagged in t2d_bits are appended, in vocabulary order, to xg[orow, :] (the gathered
@@ -65,7 +65,7 @@ struct GemmParams {
     int stages;           // depth of the TMA -> MMA smem ring (6 or 7 x 32 KB)
     int staged;           // 1: the epilogue warps own a 2 KB staging block each (after the barriers) for coalesced bf16 transfers
     // EPI_BF16_STATS / EPI_TEACHER
-    float* stats;                  // [3 or 5][num_n_blocks][M]
+    float* stats;                  // [3 or 5][M][partial blocks per row]  (a row's partials are contiguous for the merge)
     const uint32_t* t2d_bits;      // [ceil(N / 32)] bit e of word w: column 32 w + e is in the draft vocabulary
     const int* t2d_prefix;         // [ceil(N / 32)] draft-vocab columns before column 32 w
     __nv_bfloat16* xg; int S, T, DV;
@@ -138,6 +138,56 @@ __device__ __forceinline__ void warp_load_32x32(uint8_t* wbuf, int lane, uint32_
     __syncwarp();
 }
 
+// The same load split in two so that the global reads of chunk c+1 can be in flight while chunk c is processed (the epilogue of a
+// tile is a chain of dependent HBM/L2 round trips otherwise: 8 chunks x ~1.5 k cycles, enough to make a K = 4096 GEMM
+// epilogue-paced — the SwiGLU-backward dgrad ran at 800 TFLOP/s inside the step before this).
+__device__ __forceinline__ void warp_load_issue(int lane, uint4 (&t)[4], const __nv_bfloat16* src, int64_t ld, int rows_valid) {
+    const int u = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        t[i] = make_uint4(0, 0, 0, 0);
+        if (r < rows_valid) t[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * ld + u * 8));
+    }
+}
+__device__ __forceinline__ void warp_load_commit(uint8_t* wbuf, int lane, const uint4 (&t)[4], uint32_t (&o)[16]) {
+    const int u = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(wbuf + stg_off(i * 8 + (lane >> 2), u)) = t[i];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4*>(wbuf + stg_off(lane, q));
+        o[q * 4] = v.x; o[q * 4 + 1] = v.y; o[q * 4 + 2] = v.z; o[q * 4 + 3] = v.w;
+    }
+    __syncwarp();
+}
+// direct (per-thread row) variant: this thread's 32 bf16 of one row as 4 x 16 bytes
+__device__ __forceinline__ void row_load_issue(uint4 (&t)[4], const __nv_bfloat16* src, bool ok) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t[q] = ok ? __ldg(reinterpret_cast<const uint4*>(src) + q) : make_uint4(0, 0, 0, 0);
+}
+
+// L2 prefetch of the epilogue INPUTS of this thread's row in the NEXT tile of its CTA (residual row, or the saved gate / up rows of
+// the SwiGLU backward): issued at the start of the current tile's epilogue, a whole main loop before they are read, so that the
+// register prefetch above finds them in L2 instead of paying an HBM round trip per 32-column chunk.
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+template <int kBlockN>
+__device__ __forceinline__ void gemm_epilogue_prefetch(const GemmParams& p, const int row, const int n0) {
+    if (row >= p.M) return;
+    if (p.epi == EPI_BF16_RESID) {
+        const __nv_bfloat16* r = p.R + (size_t)row * p.ldr + n0;
+#pragma unroll
+        for (int i = 0; i < kBlockN / 64; ++i)
+            if (n0 + i * 64 < p.N) prefetch_l2(r + i * 64);
+    } else if (p.epi == EPI_SWIGLU_BWD) {
+        const __nv_bfloat16* g = p.R + (size_t)row * p.ldr + n0;
+#pragma unroll
+        for (int i = 0; i < kBlockN / 64; ++i)
+            if (n0 + i * 64 < p.n_half) { prefetch_l2(g + i * 64); prefetch_l2(g + p.n_half + i * 64); }
+    }
+}
+
 // The epilogue of one thread: its row of the [128 x kBlockN] accumulator block at TMEM address t_row (lane = row), processed in
 // 32-column chunks; shared by the 256 x 256 (gemm_kernel) and 512 x 256 (gemm_wide_kernel) tilings.  wbuf: this warp's 2 KB
 // staging block (bf16 outputs / inputs then move as described above) or nullptr (direct per-thread accesses).
@@ -191,20 +241,33 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                 }
             } else if (p.epi == EPI_SWIGLU_BWD) {
                 const __nv_bfloat16* gu = p.R + (size_t)row * p.ldr;
+                const __nv_bfloat16* gu0 = p.R + (size_t)row0 * p.ldr;
                 __nv_bfloat16* dgu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
+                const int c_begin = part * (kBlockN / 32 / nparts), c_end = (part + 1) * (kBlockN / 32 / nparts);
+                uint4 gn[4], un[4];                                  // the NEXT chunk's gate / up inputs, already in flight
+                auto issue = [&](int c) {
+                    const int col = n0 + c * 32;
+                    if (c >= c_end || col >= p.n_half) return;
+                    if (wbuf) { warp_load_issue(lane, gn, gu0 + col, p.ldr, rows_valid); warp_load_issue(lane, un, gu0 + p.n_half + col, p.ldr, rows_valid); }
+                    else { row_load_issue(gn, gu + col, row_ok); row_load_issue(un, gu + p.n_half + col, row_ok); }
+                };
+                issue(c_begin);
 #pragma unroll 1
-                for (int c = part * (kBlockN / 32 / nparts); c < (part + 1) * (kBlockN / 32 / nparts); ++c) {
+                for (int c = c_begin; c < c_end; ++c) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
+                    uint4 gc[4], uc[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { gc[q] = gn[q]; uc[q] = un[q]; }
+                    issue(c + 1);
                     tmem_ld_wait();
                     const int col = n0 + c * 32;
                     if (col >= p.n_half || (!wbuf && !row_ok)) continue;
                     // host guarantees n_half % 32 == 0
                     uint32_t gsw[16], usw[16], dgw[16], duw[16];
                     if (wbuf) {
-                        const __nv_bfloat16* gu0 = p.R + (size_t)row0 * p.ldr;
-                        warp_load_32x32(wbuf, lane, gsw, gu0 + col, p.ldr, rows_valid);
-                        warp_load_32x32(wbuf, lane, usw, gu0 + p.n_half + col, p.ldr, rows_valid);
+                        warp_load_commit(wbuf, lane, gc, gsw);
+                        warp_load_commit(wbuf, lane, uc, usw);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -213,8 +276,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
 #pragma unroll
                             for (int e = 0; e < 4; ++e) { gw[e] = gsw[q * 4 + e]; uw[e] = usw[q * 4 + e]; }
                         } else {
-                            const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(gu + col) + q);
-                            const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(gu + p.n_half + col) + q);
+                            const uint4 g4 = gc[q], u4 = uc[q];
                             gw[0] = g4.x; gw[1] = g4.y; gw[2] = g4.z; gw[3] = g4.w;
                             uw[0] = u4.x; uw[1] = u4.y; uw[2] = u4.z; uw[3] = u4.w;
                         }
@@ -318,8 +380,9 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                     }
                 }
                 if (row_ok) {   // a part with no valid column writes the neutral state (max -inf, sum 0), which the merges skip
-                    const size_t plane = (size_t)p.num_n_blocks * nparts * p.M;
-                    float* sp = p.stats + ((size_t)n_blk * nparts + part) * p.M + row;
+                    const size_t nbt = (size_t)p.num_n_blocks * nparts;       // partial blocks per row; layout [k][row][block]
+                    const size_t plane = nbt * p.M;
+                    float* sp = p.stats + (size_t)row * nbt + ((size_t)n_blk * nparts + part);
                     sp[0] = m; sp[plane] = d; sp[2 * plane] = __int_as_float(idx);
                     if (gather) { sp[3 * plane] = md; sp[4 * plane] = dd; }
                 }
@@ -388,11 +451,25 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         }
                     }
                 }
-            } else
+            } else {
+            const int c_begin = part * (kBlockN / 32 / nparts), c_end = (part + 1) * (kBlockN / 32 / nparts);
+            const bool resid = p.epi == EPI_BF16_RESID;
+            uint4 rn[4];                                             // the NEXT chunk's residual, already in flight
+            auto issue_resid = [&](int c) {
+                const int col = n0 + c * 32;
+                if (!resid || c >= c_end || col + 32 > p.N) return;   // ragged last chunk: loaded element-wise below
+                if (wbuf) warp_load_issue(lane, rn, p.R + (size_t)row0 * p.ldr + col, p.ldr, rows_valid);
+                else row_load_issue(rn, p.R + (size_t)row * p.ldr + col, row_ok);
+            };
+            issue_resid(c_begin);
 #pragma unroll 1
-            for (int c = part * (kBlockN / 32 / nparts); c < (part + 1) * (kBlockN / 32 / nparts); ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + c * 32, v);
+                uint4 rc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rc[q] = rn[q];
+                issue_resid(c + 1);
                 tmem_ld_wait();
                 const int col = n0 + c * 32;
                 if (col >= p.N) continue;
@@ -401,7 +478,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                     uint32_t o[16];
                     if (p.epi == EPI_BF16_RESID) {
                         uint32_t rw[16];
-                        warp_load_32x32(wbuf, lane, rw, p.R + (size_t)row0 * p.ldr + col, p.ldr, rows_valid);
+                        warp_load_commit(wbuf, lane, rc, rw);
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
@@ -424,11 +501,9 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                     if (full) {
                         uint32_t o[16];
                         if (p.epi == EPI_BF16_RESID) {
-                            const uint4* rp =
-                                reinterpret_cast<const uint4*>(p.R + (size_t)row * p.ldr + col);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                uint4 r4 = __ldg(rp + q);
+                                const uint4 r4 = rc[q];
                                 const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
@@ -480,6 +555,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         }
                     }
                 }
+            }
             }
 }
 
@@ -645,6 +721,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + astage * Cfg::BLOCK_N;
             const bool row_ok = row < p.M;
             uint8_t* wbuf = p.staged ? smem_raw + (bar_base + 512u - smem_u32(smem_raw)) + (warp - 4) * 2048 : nullptr;
+            if (tile + num_clusters < num_tiles && (p.epi == EPI_BF16_RESID || p.epi == EPI_SWIGLU_BWD)) {
+                int nm, nn;
+                tile_coords(tile + num_clusters, nm, nn);
+                gemm_epilogue_prefetch<Cfg::BLOCK_N>(p, nm * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M + wq * 32 + lane, nn * Cfg::BLOCK_N);
+            }
             gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row_ok, n_blk, n0, t_row, wbuf, lane);
             tc_fence_before();
             __syncwarp();

@@ -198,6 +198,12 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int m_blk, n_blk;
             tile_coords(tile, m_blk, n_blk);
             const int n0 = n_blk * Cfg::BLOCK_N;
+            if (tile + num_clusters < num_tiles && part == 0 && (p.epi == EPI_BF16_RESID || p.epi == EPI_SWIGLU_BWD)) {
+                int nm, nn;
+                tile_coords(tile + num_clusters, nm, nn);
+                for (int h = 0; h < 2; ++h)
+                    gemm_epilogue_prefetch<Cfg::BLOCK_N>(p, nm * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M + h * 128 + wq * 32 + lane, nn * Cfg::BLOCK_N);
+            }
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 const int row = m_blk * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M + h * 128 + wq * 32 + lane;

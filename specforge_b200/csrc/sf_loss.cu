@@ -197,7 +197,7 @@ teacher_merge_kernel(const float* __restrict__ stats, int nb, int64_t M, const u
     float m = -INFINITY, d = 0.f, md = -INFINITY, dd = 0.f;
     int idx = 0x7fffffff;
     for (int b = 0; b < nb; ++b) {
-        const float* sp = stats + (size_t)b * M + r;
+        const float* sp = stats + (size_t)r * nb + b;
         const float pm = sp[0], pd = sp[plane], pmd = sp[3 * plane], pdd = sp[4 * plane];
         if (pm > m) { d = d * __expf(m - pm) + pd; m = pm; idx = __float_as_int(sp[2 * plane]); }
         else if (pm > -INFINITY) d += pd * __expf(pm - m);
@@ -231,7 +231,7 @@ struct LossParams {
     float grad_coef;      // ploss_decay^step * upstream / M
     int write_grad;
     float* row_loss; float* row_accept; float* row_correct;  // [M]
-    const float* stats; int stats_nb;   // optional pass-A partials from the lm_head GEMM epilogue (EPI_BF16_STATS): [3][nb][M]
+    const float* stats; int stats_nb;   // optional pass-A partials from the lm_head GEMM epilogue (EPI_BF16_STATS): [3][M][nb]
 };
 
 __global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
     if (p.stats) {
         if (warp == 0) {
             const size_t plane = (size_t)p.stats_nb * p.M;
-            for (int nb = lane; nb < p.stats_nb; nb += 32) {          // ascending n-blocks per lane
-                const float* sp = p.stats + (size_t)nb * p.M + r;
+            for (int nb = lane; nb < p.stats_nb; nb += 32) {          // ascending n-blocks per lane; a row's partials are contiguous
+                const float* sp = p.stats + (size_t)r * p.stats_nb + nb;
                 const float pm = __ldg(sp), pd = __ldg(sp + plane);
                 if (pm > mi.v) { d = d * __expf(mi.v - pm) + pd; mi.v = pm; mi.i = __float_as_int(__ldg(sp + 2 * plane)); }
                 else if (pm > -INFINITY) d += pd * __expf(pm - mi.v);
