@@ -28,6 +28,17 @@ QWEN3_8B = dict(hidden_size=4096, intermediate_size=12288, num_heads=32, num_kv_
                 draft_vocab_size=32000, rms_norm_eps=1e-6, rope_theta=1000000.0, max_position_embeddings=40960)
 B, S, T = 8, 2048, 7
 METRIC = "EAGLE3 draft-step samples/sec (Qwen3-8B, TTT=7, seq 2048)"
+WORKLOAD = "BASELINE config 2 per GPU: Qwen3-8B EAGLE3 offline draft step"
+# the other EAGLE3 configurations of BASELINE.json (opt-in with --config; parity-test cases, not the headline):
+OTHER_CONFIGS = {
+    3: (dict(hidden_size=4096, intermediate_size=14336, num_heads=32, num_kv_heads=8, head_dim=128, vocab_size=128256, draft_vocab_size=32000,
+             rms_norm_eps=1e-5, rope_theta=10000.0, max_position_embeddings=2048), 8, 2048,
+        "EAGLE3 draft-step samples/sec (Llama3-8B, TTT=7, seq 2048)", "BASELINE config 3 per GPU: Llama3-8B EAGLE3 offline draft step"),
+    5: (dict(hidden_size=2048, intermediate_size=12288, num_heads=32, num_kv_heads=4, head_dim=128, vocab_size=151936, draft_vocab_size=32000,
+             rms_norm_eps=1e-6, rope_theta=1000000.0, max_position_embeddings=8192, fc_norm=True), 4, 4096,
+        "EAGLE3.1 draft-step samples/sec (Qwen3-30B-A3B, TTT=7, seq 4096)",
+        "BASELINE config 5 per GPU: Qwen3-30B-A3B EAGLE3.1 (fc_norm) offline draft step, max_position_embeddings raised to 8192"),
+}
 CPU_SAMPLE_TOKENS = 128
 CPU_MAX_THREADS = 32
 
@@ -524,8 +535,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "BASELINE config 2 per GPU: Qwen3-8B EAGLE3 offline draft step (teacher + TTT fwd + loss + bwd + "
-                               "grad all-reduce + clip/AdamW)", "batch_per_gpu": B, "global_batch": world * B, "seq_len": S,
+        "config": {"workload": WORKLOAD + " (teacher + TTT fwd + loss + bwd + grad all-reduce + clip/AdamW)", "batch_per_gpu": B, "global_batch": world * B, "seq_len": S,
                    "ttt_length": T, "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (per-step working set ~45 GB)",
                    "weights": "random-init, reference shapes; draft-vocab rows of the frozen head x2 so ~95 % of positions are live"},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -690,7 +700,12 @@ def main():
     ap.add_argument("--workload", default="eagle3", choices=["eagle3", "dflash"],
                     help="eagle3 = the headline metric (BASELINE config 2); dflash = BASELINE config 4 (next row, opt-in)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5], help="EAGLE3 BASELINE configuration (2 = the headline metric)")
     args = ap.parse_args()
+    if args.config != 2:
+        global QWEN3_8B, B, S, METRIC, WORKLOAD
+        QWEN3_8B, B, S, METRIC, WORKLOAD = OTHER_CONFIGS[args.config]
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "dflash":

@@ -119,7 +119,9 @@ int sf_eagle3_forward(const sf_eagle3_config* cfg, const void* params_flat, cons
 int sf_eagle3_workspace_view(const sf_eagle3_config* cfg, const char* name, int64_t* offset_bytes, int64_t* size_bytes);
 
 /* Full backward of the step just run by sf_eagle3_forward(need_grad=1) on the same workspace.
- * grads_flat_f32 (+)= loss_scale * dLoss/dParams  (accumulate != 0 adds into the buffer). */
+ * grads_flat_f32 (+)= loss_scale * dLoss/dParams  (accumulate != 0 adds into the buffer).  loss_scale != 1 is applied as one pass
+ * over the finished buffer and is therefore refused (-EINVAL) together with `accumulate` or the gradient-ready callback: scale an
+ * accumulation window once, through sf_grads_to_bf16's scale_dev or sf_optimizer_step's grad_scale. */
 int sf_eagle3_backward(const sf_eagle3_config* cfg, const void* params_flat, const sf_eagle3_frozen* frozen,
                        const sf_eagle3_batch* batch, void* workspace, size_t workspace_bytes, float loss_scale,
                        float* grads_flat_f32, int accumulate, void* stream);
@@ -224,6 +226,9 @@ typedef struct sf_dflash_config {
     int32_t grad_of_numerator;        /* 0: backward yields d(loss_num / loss_den) (a self-contained step); 1: d(loss_num) —    */
                                       /* the reference controller's loss_terms contract, which backprops the numerator and then  */
                                       /* divides the synchronised gradients by the GLOBAL denominator (controller.py:334-398)     */
+    int32_t loss_type;                /* 0 "dflash"; D-PACE (dflash_family_model.py:245-279,360-369): 1 "dpace",                   */
+                                      /* 2 "dpace-cumulative-confidence-only", 3 "dpace-continuation-value-only"; loss_den = batch */
+    float dpace_alpha;                /* smoothing of the draft's confidence on the target token (default 0.5)                    */
 } sf_dflash_config;
 /* parameter order inside the flat buffer: for each layer the SF_DF_* slices below (q, k, v contiguous = one fused GEMM
  * operand, likewise gate, up), then fc [H, F*H], hidden_norm [H], norm [H].  Names/shapes: dflash.py:336-375. */

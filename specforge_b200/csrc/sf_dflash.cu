@@ -43,6 +43,8 @@ static int validate(const sf_dflash_config& c) {
     if (c.num_heads % c.num_kv_heads) return set_error(-22, "dflash config: num_heads %% num_kv_heads != 0");
     if (c.rope_rows < c.seq_len + c.block_size) return set_error(-22, "dflash config: rope tables have %d rows, need >= S+block=%d", c.rope_rows, c.seq_len + c.block_size);
     if (c.mask_token_id < 0 || c.mask_token_id >= c.vocab) return set_error(-22, "dflash config: mask_token_id outside the vocabulary");
+    if (c.loss_type < 0 || c.loss_type > 3) return set_error(-22, "dflash config: loss_type=%d (0 dflash, 1 dpace, 2 cumulative-confidence-only, 3 continuation-value-only)", c.loss_type);
+    if (c.loss_type != 0 && (c.dpace_alpha < 0.f || c.dpace_alpha > 1.f)) return set_error(-22, "dflash config: dpace_alpha must be in [0, 1]");
     return 0;
 }
 
@@ -63,7 +65,7 @@ static void layout(const sf_dflash_config& c, int64_t* off, int64_t* sz, int64_t
 }
 
 struct Plan {
-    int64_t pos, tgt, nid, w, lw, sums, row_loss, row_correct;
+    int64_t pos, tgt, nid, w, lw, sums, row_loss, row_correct, row_state;
     int64_t ctx_raw, ctx, x, hn, qkv, kvc, qr, krn, krc, attn, lse, x1, hn2, gu, act, hf, logits;
     // backward
     int64_t dxa, dxb, dtmp, dgu, dact, dattn, dqr, dkrn, dkrc, dqkv, dkvc, delta, dctx32, dctx, norm_ws, head_ws;
@@ -76,7 +78,7 @@ static Plan make_plan(const sf_dflash_config& c) {
     auto take = [&](int64_t bytes) { int64_t r = o; o = align_up(o + bytes, 1024); return r; };
     const int64_t Mq = x.Mq, Mc = x.Mc, L = x.L;
     p.pos = take(Mq * 4); p.tgt = take(Mq * 4); p.nid = take(Mq * 4); p.w = take(Mq * 4); p.lw = take(Mq * 4);
-    p.sums = take(64); p.row_loss = take(Mq * 4); p.row_correct = take(Mq * 4);
+    p.sums = take(64); p.row_loss = take(Mq * 4); p.row_correct = take(Mq * 4); p.row_state = take(Mq * 8);
     p.ctx_raw = take(Mc * x.H * 2); p.ctx = take(Mc * x.H * 2);
     p.x = take((L + 1) * Mq * x.H * 2);
     p.hn = take(L * Mq * x.H * 2);
@@ -199,7 +201,8 @@ static int forward(Ctx& c, const sf_dflash_frozen& fz, const sf_dflash_batch& bt
     SF_TRY(rmsnorm_fwd(c.bf(p.x, (int64_t)x.L * Mq * x.H), x.H, nullptr, x.S, 0, c.Wg(2), c.bf(p.hf), x.H, Mq, x.H, cfg.rms_eps, nullptr, st));
     SF_TRY(mm(c, c.bf(p.hf), x.H, MAJOR_K, fz.lm_head, x.H, MAJOR_K, c.bf(p.logits), x.V, nullptr, 0, Mq, x.V, x.H, EPI_BF16));
     SF_TRY(ce(c.bf(p.logits), x.V, x.V, c.at<int32_t>(p.tgt), c.at<float>(p.w), c.at<float>(p.lw), c.at<float>(p.sums), need_grad,
-              c.at<float>(p.row_loss), c.at<float>(p.row_correct), Mq, cfg.grad_of_numerator, st));
+              c.at<float>(p.row_loss), c.at<float>(p.row_correct), Mq, cfg.grad_of_numerator, cfg.loss_type, cfg.dpace_alpha, x.bs, x.B,
+              c.at<float>(p.row_state), st));
     // metrics = {loss_num, loss_den, correct, acc_den}; loss = loss_num / loss_den
     return finalize_loss(c.at<float>(p.sums), metrics_out, loss_out, st);
 }

@@ -45,8 +45,9 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t st);
 bool attn_tc_bwd_supported(const AttnArgs& a);      // sf_dflash_attn_tc_bwd.cu (default where the shape is covered)
 int attn_bwd_tc(const AttnArgs& a, cudaStream_t st);
 int attn_bwd(const AttnArgs& a, cudaStream_t st);
-int ce(void* logits, int64_t ld, int V, const int32_t* tgt, const float* w, const float* lw, float* sums, int write_grad,
-       float* row_loss, float* row_correct, int64_t M, int grad_of_numerator, cudaStream_t st);
+int ce(void* logits, int64_t ld, int V, const int32_t* tgt, const float* w, float* lw, float* sums, int write_grad,
+       float* row_loss, float* row_correct, int64_t M, int grad_of_numerator, int loss_type, float dpace_alpha, int bs, int batch,
+       float* row_state, cudaStream_t st);
 int finalize_loss(const float* sums, float* metrics, float* loss, cudaStream_t st);
 
 }  // namespace dflash

@@ -437,13 +437,31 @@ __global__ void __launch_bounds__(256) attn_bwd_ctx_kernel(AttnArgs a) {
 __global__ void __launch_bounds__(512) ce_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld, int V, const int32_t* __restrict__ tgt,
                                                  const float* __restrict__ w, const float* __restrict__ lw,
                                                  const float* __restrict__ sums /* [0] = loss_den */, int write_grad,
-                                                 float* __restrict__ row_loss, float* __restrict__ row_correct, int grad_of_numerator) {
+                                                 float* __restrict__ row_loss, float* __restrict__ row_correct, int grad_of_numerator,
+                                                 int mode, float* __restrict__ row_state /* [M][2] = {max, 1/sum-exp} */) {
+    // mode 0: statistics + loss + gradient in one launch (loss_type "dflash": the row's weight lw is known up front).
+    // mode 1: statistics only — row_loss = the raw -log q(target), row_state = {max, 1/sum-exp}: the D-PACE objectives need every
+    //         slot's q before any weight exists (dflash_family_model.py:245-279,360-369).   mode 2: gradient only, from row_state.
     __shared__ float redv[16], redd[16];
     __shared__ int redi[16];
     const int64_t r = blockIdx.x;
-    const float lwr = lw[r], wr = w[r];
+    const float lwr = (mode == 1) ? 1.f : lw[r], wr = w[r];
     __nv_bfloat16* row = logits + r * ld;
-    if (lwr == 0.f && wr == 0.f) {
+    if (mode == 2) {
+        const float coef = grad_of_numerator ? lwr : lwr / sums[0];
+        if (coef == 0.f) {
+            for (int c = threadIdx.x; c < V; c += 512) row[c] = __float2bfloat16_rn(0.f);
+            return;
+        }
+        const float m2 = row_state[2 * r], inv2 = row_state[2 * r + 1];
+        const int tg2 = tgt[r];
+        for (int c = threadIdx.x; c < V; c += 512) {
+            const float pr = __expf(bf(row[c]) - m2) * inv2;
+            row[c] = __float2bfloat16_rn(coef * (pr - (c == tg2 ? 1.f : 0.f)));
+        }
+        return;
+    }
+    if (mode == 0 && lwr == 0.f && wr == 0.f) {
         if (write_grad)
             for (int c = threadIdx.x; c < V; c += 512) row[c] = __float2bfloat16_rn(0.f);
         if (threadIdx.x == 0) { row_loss[r] = 0.f; row_correct[r] = 0.f; }
@@ -486,8 +504,9 @@ __global__ void __launch_bounds__(512) ce_kernel(__nv_bfloat16* __restrict__ log
     if (threadIdx.x == 0) {
         row_loss[r] = (lse - bf(row[tg])) * lwr;
         row_correct[r] = (am == tg && wr > 0.5f) ? 1.f : 0.f;
+        if (mode == 1) { row_state[2 * r] = m; row_state[2 * r + 1] = 1.f / dsum; }
     }
-    if (write_grad) {
+    if (write_grad && mode == 0) {
         const float coef = grad_of_numerator ? lwr : lwr / sums[0];
         const float inv = 1.f / dsum;
         __syncthreads();   // row[tg] was read above by thread 0
@@ -497,6 +516,38 @@ __global__ void __launch_bounds__(512) ce_kernel(__nv_bfloat16* __restrict__ log
         }
     }
 }
+
+// D-PACE position weights (dflash_family_model.py:245-279): one thread per anchor block of bs slots.  nll[] holds -log q(target);
+// smooth_k = (1-alpha) q_k + alpha on supervised slots (w > 0), 1 elsewhere; prefix_k = prod_{i<=k} smooth_i;
+// type 2 (cumulative-confidence-only): weight = prefix;  type 1 (dpace): weight_k = sum_{i>=k} prefix_i w_i;
+// type 3 (continuation-value-only): that suffix sum / max(prefix_k, tiny).  Writes lw = w * weight (detached) and
+// row_loss = nll * lw in place.
+__global__ void __launch_bounds__(256) dpace_weights_kernel(float* __restrict__ nll_loss, const float* __restrict__ w, float* __restrict__ lw,
+                                                            int64_t blocks, int bs, int type, float alpha) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= blocks) return;
+    float* nl = nll_loss + b * bs;
+    const float* wb = w + b * bs;
+    float* lwb = lw + b * bs;
+    float prefix = 1.f;
+    for (int k = 0; k < bs; ++k) {                       // forward: prefix products, parked in lw
+        const float wk = wb[k];
+        const float smooth = wk > 0.f ? (1.f - alpha) * __expf(-nl[k]) + alpha : 1.f;
+        prefix *= smooth;
+        lwb[k] = prefix;
+    }
+    float suffix = 0.f;
+    for (int k = bs - 1; k >= 0; --k) {                  // backward: suffix sums of prefix * w
+        const float pk = lwb[k], wk = wb[k];
+        suffix += pk * wk;
+        float dw = pk;
+        if (type == 1) dw = suffix;
+        else if (type == 3) dw = suffix / fmaxf(pk, 1.17549435e-38f);
+        lwb[k] = wk * dw;
+        nl[k] = nl[k] * wk * dw;
+    }
+}
+__global__ void set_den_kernel(float* sums, float v) { sums[0] = v; }
 
 // metrics = {loss_num, loss_den, correct, acc_den}; loss = loss_num / loss_den   (sums: see sf_dflash.h)
 __global__ void finalize_kernel(const float* __restrict__ sums, float* __restrict__ metrics, float* __restrict__ loss) {
@@ -587,10 +638,29 @@ int attn_bwd_cc(const AttnArgs& a, cudaStream_t st) {
     SF_CUDA_CHECK_LAUNCH("dflash attn_bwd_ctx");
     return 0;
 }
-int ce(void* logits, int64_t ld, int V, const int32_t* tgt, const float* w, const float* lw, float* sums, int write_grad,
-       float* row_loss, float* row_correct, int64_t M, int grad_of_numerator, cudaStream_t st) {
-    ce_kernel<<<(unsigned)M, 512, 0, st>>>((__nv_bfloat16*)logits, ld, V, tgt, w, lw, sums, write_grad, row_loss, row_correct, grad_of_numerator);
-    SF_CUDA_CHECK_LAUNCH("dflash ce");
+int ce(void* logits, int64_t ld, int V, const int32_t* tgt, const float* w, float* lw, float* sums, int write_grad,
+       float* row_loss, float* row_correct, int64_t M, int grad_of_numerator, int loss_type, float dpace_alpha, int bs, int batch,
+       float* row_state, cudaStream_t st) {
+    if (loss_type == 0) {
+        ce_kernel<<<(unsigned)M, 512, 0, st>>>((__nv_bfloat16*)logits, ld, V, tgt, w, lw, sums, write_grad, row_loss, row_correct,
+                                              grad_of_numerator, 0, nullptr);
+        SF_CUDA_CHECK_LAUNCH("dflash ce");
+    } else {
+        // D-PACE: statistics (raw -log q per slot) -> per-block weights -> gradient; loss = sum(nll w weight) / batch size
+        ce_kernel<<<(unsigned)M, 512, 0, st>>>((__nv_bfloat16*)logits, ld, V, tgt, w, lw, sums, 0, row_loss, row_correct, grad_of_numerator,
+                                              1, row_state);
+        SF_CUDA_CHECK_LAUNCH("dflash ce stats");
+        const int64_t blocks = M / bs;
+        dpace_weights_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, st>>>(row_loss, w, lw, blocks, bs, loss_type, dpace_alpha);
+        SF_CUDA_CHECK_LAUNCH("dflash dpace weights");
+        set_den_kernel<<<1, 1, 0, st>>>(sums, (float)batch);
+        SF_CUDA_CHECK_LAUNCH("dflash dpace den");
+        if (write_grad) {
+            ce_kernel<<<(unsigned)M, 512, 0, st>>>((__nv_bfloat16*)logits, ld, V, tgt, w, lw, sums, 1, row_loss, row_correct,
+                                                  grad_of_numerator, 2, row_state);
+            SF_CUDA_CHECK_LAUNCH("dflash ce grad");
+        }
+    }
     sum4_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, row_loss, row_correct, M, sums);   // sums[2] = loss_num, sums[3] = correct
     SF_CUDA_CHECK_LAUNCH("dflash ce sums");
     return 0;

@@ -64,7 +64,13 @@ static int num_sms() {
     return n;
 }
 
-template <int G, int AM, int BM, int BN>
+// the epilogues whose per-element work is long enough to pace a K <= 8192 GEMM with four epilogue warps (sf_gemm.cuh)
+static bool heavy_epilogue(int epi) {
+    return epi == EPI_TEACHER || epi == EPI_BF16_STATS || epi == EPI_SWIGLU || epi == EPI_SWIGLU_BWD || epi == EPI_BF16_ROPE;
+}
+static bool use_epi8(const GemmDesc& g) { return opt(OPT_GEMM_EPI8) >= 0 && (opt(OPT_GEMM_EPI8) == 1 || heavy_epilogue(g.epi)); }
+
+template <int G, int AM, int BM, int BN, int EW = 4>
 static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     using Cfg = GemmCfg<G, AM, BM, BN>;
     CUtensorMap ta, tb;
@@ -96,14 +102,16 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     if (p.stages < 2) p.stages = 2;
     if (p.stages > Cfg::kMaxStages) p.stages = Cfg::kMaxStages;
     // warp-staged (coalesced) bf16 epilogue transfers: needs 8 KB, i.e. one ring stage less than the deepest ring
-    p.staged = opt(OPT_GEMM_EPI_STAGED) == 1 ? 1 : 0;
-    if (p.staged && Cfg::smem_bytes(p.stages, 1) > 227 * 1024) --p.stages;
+    // gemm_epi_staged: 1 = every 256 x 256 launch, 2 = only the SwiGLU-backward epilogue (2 x 64 B read + 2 x 64 B written per chunk)
+    const int so = opt(OPT_GEMM_EPI_STAGED);
+    p.staged = (so == 1 || (so == 2 && g.epi == EPI_SWIGLU_BWD)) ? 1 : 0;
+    while (p.staged && Cfg::smem_bytes(p.stages, 1) > 227 * 1024) --p.stages;
     const int smem_bytes = Cfg::smem_bytes(p.stages, p.staged);
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int clusters = num_sms() / G;
     if (tiles < clusters) clusters = tiles;
 
-    auto kern = gemm_kernel<G, AM, BM, BN>;
+    auto kern = gemm_kernel<G, AM, BM, BN, EW>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(Cfg::kMaxStages, 0));
@@ -112,7 +120,7 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * G);
-    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.blockDim = dim3(128 + 32 * EW);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -232,7 +240,7 @@ static bool use_wide(const GemmDesc& g) {
     if (o == 3) return g.K > 8192;
     const bool stats = g.epi == EPI_TEACHER || g.epi == EPI_BF16_STATS;
     if (o == 1) return g.K > 4096 || !stats;
-    const bool heavy = stats || g.epi == EPI_SWIGLU || g.epi == EPI_SWIGLU_BWD || g.epi == EPI_BF16_ROPE;
+    const bool heavy = heavy_epilogue(g.epi);
     return g.K > (heavy ? 8192 : 4096);
 }
 
@@ -242,7 +250,8 @@ int gemm_stats_blocks(const GemmDesc& g) {
     const int nb = (g.N + 255) / 256;
     int G = g.cta_group;
     if (G == 0) G = (g.M > 128) ? 2 : 1;
-    return (G == 2 && g.cta_group == 0 && use_wide(g)) ? 2 * nb : nb;
+    if (G == 2 && g.cta_group == 0 && use_wide(g)) return 2 * nb;
+    return (G == 2 && use_epi8(g) && (g.a_major == MAJOR_K)) ? 2 * nb : nb;    // two epilogue warps per lane quadrant: two column halves
 }
 
 int gemm(const GemmDesc& g, cudaStream_t stream) {
@@ -280,8 +289,8 @@ int gemm(const GemmDesc& g, cudaStream_t stream) {
         case 0: return launch_cfg<1, MAJOR_K, MAJOR_K, 256>(g, stream);
         case 1: return launch_cfg<1, MAJOR_K, MAJOR_MN, 256>(g, stream);
         case 3: return launch_cfg<1, MAJOR_MN, MAJOR_MN, 256>(g, stream);
-        case 4: return launch_cfg<2, MAJOR_K, MAJOR_K, 256>(g, stream);
-        case 5: return launch_cfg<2, MAJOR_K, MAJOR_MN, 256>(g, stream);
+        case 4: return use_epi8(g) ? launch_cfg<2, MAJOR_K, MAJOR_K, 256, 8>(g, stream) : launch_cfg<2, MAJOR_K, MAJOR_K, 256>(g, stream);
+        case 5: return use_epi8(g) ? launch_cfg<2, MAJOR_K, MAJOR_MN, 256, 8>(g, stream) : launch_cfg<2, MAJOR_K, MAJOR_MN, 256>(g, stream);
         case 7: return launch_cfg<2, MAJOR_MN, MAJOR_MN, 256>(g, stream);
         default: return set_error(-22, "gemm: unsupported operand majors a=%d b=%d", g.a_major, g.b_major);
     }

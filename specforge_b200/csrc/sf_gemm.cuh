@@ -89,7 +89,7 @@ struct GemmCfg {
     static constexpr int kMaxStages = (224 * 1024) / STAGE_BYTES;   // deepest ring that fits the 227 KB of a CTA
     static constexpr int kAccStages = 2;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int STAGING_BYTES = 4 * 2048;                  // optional: 2 KB per epilogue warp (GemmParams::staged)
+    static constexpr int STAGING_BYTES = 8 * 2048;                  // optional: 2 KB per epilogue warp, up to 8 (GemmParams::staged)
     static constexpr int smem_bytes(int stages, int staged = 0) { return stages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + (staged ? STAGING_BYTES : 0); }
     static constexpr int SMEM_BYTES = smem_bytes(kStages);
     static constexpr int kThreads = 256;
@@ -559,8 +559,12 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
             }
 }
 
-template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN>
-__global__ void __launch_bounds__(256, 1)
+// kEpiWarps: 4 (one per TMEM lane quadrant) or 8 — two per quadrant, each taking half of the tile's columns.  With four, every
+// SM sub-partition hosts ONE epilogue warp, so nothing hides the latency of its dependent ALU / MUFU chain: the exp-heavy epilogues
+// (SwiGLU backward ~35 instructions per element) then take as long as the K = 4096 main loop and pace the GEMM (1.02 PFLOP/s in the
+// step).  Eight warps double the epilogue's issue rate at the price of a 168-register cap.
+template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN, int kEpiWarps = 4>
+__global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmParams p) {
     using Cfg = GemmCfg<kCtaGroup, kAMajor, kBMajor, kBlockN>;
@@ -596,7 +600,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4 * kCtaGroup);  // one arrive per epilogue warp per CTA
+            mbar_init(tempty_bar(s), kEpiWarps * kCtaGroup);  // one arrive per epilogue warp per CTA
         }
         fence_mbar_init();
     }
@@ -721,12 +725,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + astage * Cfg::BLOCK_N;
             const bool row_ok = row < p.M;
             uint8_t* wbuf = p.staged ? smem_raw + (bar_base + 512u - smem_u32(smem_raw)) + (warp - 4) * 2048 : nullptr;
-            if (tile + num_clusters < num_tiles && (p.epi == EPI_BF16_RESID || p.epi == EPI_SWIGLU_BWD)) {
+            if (tile + num_clusters < num_tiles && warp < 8 && (p.epi == EPI_BF16_RESID || p.epi == EPI_SWIGLU_BWD)) {
                 int nm, nn;
                 tile_coords(tile + num_clusters, nm, nn);
                 gemm_epilogue_prefetch<Cfg::BLOCK_N>(p, nm * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M + wq * 32 + lane, nn * Cfg::BLOCK_N);
             }
-            gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row_ok, n_blk, n0, t_row, wbuf, lane);
+            gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row_ok, n_blk, n0, t_row, wbuf, lane, (warp - 4) >> 2, kEpiWarps / 4);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

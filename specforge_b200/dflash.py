@@ -25,7 +25,8 @@ class SfDflashConfig(Structure):
     _fields_ = [(n, c_int32) for n in ("batch", "seq_len", "num_blocks", "block_size", "hidden_size", "num_target_feats",
                                        "intermediate", "num_heads", "num_kv_heads", "head_dim", "num_layers", "vocab",
                                        "mask_token_id", "rope_rows")] + [("rms_eps", c_float), ("loss_decay_gamma", c_float),
-                                                                          ("grad_of_numerator", c_int32)]
+                                                                          ("grad_of_numerator", c_int32), ("loss_type", c_int32),
+                                                                          ("dpace_alpha", c_float)]
 
 
 class SfDflashFrozen(Structure):
@@ -53,6 +54,11 @@ class DFlashDims:
     rope_theta: float = 1000000.0
     max_position_embeddings: int = 40960
     loss_decay_gamma: Optional[float] = None
+    loss_type: str = "dflash"         # "dflash" | "dpace" | "dpace-cumulative-confidence-only" | "dpace-continuation-value-only"
+    dpace_alpha: float = 0.5          # (dflash_family_model.py:29-31,245-279)
+
+
+LOSS_TYPES = {"dflash": 0, "dpace": 1, "dpace-cumulative-confidence-only": 2, "dpace-continuation-value-only": 3}
 
 
 def sample_anchor_positions(loss_mask: torch.Tensor, num_anchors: int, generator: Optional[torch.Generator] = None,
@@ -156,7 +162,8 @@ class DFlashEngine:
         d = self.dims
         return SfDflashConfig(B, S, N, d.block_size, d.hidden_size, d.num_target_feats, d.intermediate_size, d.num_heads,
                               d.num_kv_heads, d.head_dim, d.num_layers, d.vocab_size, d.mask_token_id, rope_rows, d.rms_norm_eps,
-                              float(d.loss_decay_gamma) if d.loss_decay_gamma else 0.0, int(getattr(self, "grad_of_numerator", 0)))
+                              float(d.loss_decay_gamma) if d.loss_decay_gamma else 0.0, int(getattr(self, "grad_of_numerator", 0)),
+                              LOSS_TYPES[d.loss_type], float(d.dpace_alpha))
 
     def shape_of(self, name: str) -> Tuple[int, ...]:
         d = self.dims

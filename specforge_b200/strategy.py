@@ -15,7 +15,11 @@ from .draft import B200Eagle3DraftModel
 
 
 class _Eagle3StepFn(torch.autograd.Function):
-    """loss = f(params) with the forward/backward done by the C-ABI library.  The flat bf16 parameter buffer is the
+    """loss = f(params) with the forward/backward done by the C-ABI library.
+    Accumulation contract: the engine accumulates UNSCALED micro-batch gradients in fp32 and the upstream factor (`grad_out`, i.e. the
+    controller's 1 / accumulation_steps, controller.py:345) is applied ONCE, when the window's sum is converted to bf16 — so every
+    micro-step of a window must arrive with the same `grad_out` (true for the reference controller; a caller that weights
+    micro-batches differently must scale its losses' gradients itself).  The flat bf16 parameter buffer is the
     single differentiable input; backward leaves dLoss/dparams in the engine's fp32 accumulator (the backend reads
     it) and, for stock optimizers/DDP, also returns it to autograd as a bf16 tensor."""
 
