@@ -29,7 +29,12 @@ def dims_from_config(config: Any) -> DraftDims:
     theta = rope_params["rope_theta"] if rope_params else get("rope_theta", 10000.0)
     scaling = get("rope_scaling") or (rope_params if rope_params and rope_params.get("rope_type") not in (None, "default") else None)
     if scaling and scaling.get("rope_type", scaling.get("type")) == "mrope":
-        raise NotImplementedError("mrope (three-axis multimodal positions) is not implemented on the CUDA path")
+        # Three-axis multimodal RoPE (llama3_eagle.py:145-183,389-424).  For TEXT positions the three axes carry the same index and
+        # the sectioned cos / sin equal the plain ones ("the text embedding rotary position embedding has no difference with modern
+        # LLMs", :153-155), so the default tables serve; the strategy refuses batches whose position_ids axes differ (vision tokens).
+        if float(scaling.get("factor", 1.0) or 1.0) != 1.0:
+            raise NotImplementedError("mrope with a scaling factor != 1 is not implemented on the CUDA path")
+        scaling = None
     return DraftDims(hidden_size=H, intermediate_size=get("intermediate_size"), num_heads=nh,
                      num_kv_heads=get("num_key_value_heads", nh), head_dim=head_dim, vocab_size=get("vocab_size"),
                      draft_vocab_size=get("draft_vocab_size"), target_hidden_size=get("target_hidden_size", H),

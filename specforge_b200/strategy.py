@@ -109,6 +109,7 @@ class B200Eagle3TrainStrategy:
                 raise ValueError("compact teacher is offline-only and requires target_repr='hidden_state'")
             raise ValueError(f"target_repr={target_repr!r}: the CUDA path implements the offline hidden-state teacher only "
                              "(online 'logits' / 'pruned_logits' capture is outside the replaced hot path)")
+        self._check_position_ids(batch.tensors.get("position_ids"), batch.tensors["input_ids"])
         need_grad = torch.is_grad_enabled()
         eng = self.engine
         flat = eng.params if not need_grad else eng.params.detach().requires_grad_(True)
@@ -125,6 +126,20 @@ class B200Eagle3TrainStrategy:
             "metric_loss_denoms": [m[j, 6] for j in range(T)],
         }
         return StepOutput(loss=loss, metrics=metrics)
+
+    @staticmethod
+    def _check_position_ids(position_ids, input_ids) -> None:
+        """The kernels rotate row s of every sequence at position s + j (the reference's default when a batch carries no
+        `position_ids`, eagle3/model.py:335-345).  Explicit positions are accepted only if they say the same thing: [B, S] or, for
+        mrope, [3, B, S] with all three axes equal to arange(S) — text tokens; anything else (packed sequences, vision tokens) is
+        refused rather than silently mis-rotated."""
+        if position_ids is None:
+            return
+        S = input_ids.shape[-1]
+        p = position_ids.reshape(-1, S)
+        if not bool((p == torch.arange(S, device=p.device, dtype=p.dtype)).all()):
+            raise NotImplementedError("position_ids other than arange(seq_len) on every axis (packed / multimodal positions) are not "
+                                      "implemented on the CUDA path")
 
     def checkpoint_state_filter(self, state_dict: Dict[str, Any]) -> Dict[str, Any]:
         """Same rule as the reference (strategies/base.py:306-319): draft weights without the `draft_model.` prefix,
