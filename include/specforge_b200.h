@@ -34,7 +34,10 @@ const char* sf_version(void);
 const char* sf_last_error(void);
 /* Tuning / A-B switch by name ("no_pdl", "loss_side", "no_overlap", "no_swiglu_fusion", "gemm_group_m",
  * "gemm_group_m_midk", "gemm_group_m_wgrad", "dflash_attn_tc" (-1: CUDA-core DFlash attention instead of tcgen05), "gemm_stages",
- * "gemm_wide" (-1: 256x256 tiling only, 0: 512x256 for M >= 512), "gemm_epi_staged", "no_teacher_fusion", "no_loss_stats_fusion",
+ * "gemm_wide" (-1: 256x256 tiling only, 0: 512x256 for M >= 512 by the K / epilogue rule in sf_gemm.cu), "gemm_epi_staged" (warp-staged
+ * coalesced epilogue transfers; 0: 512x256 tiling + the SwiGLU-backward epilogue, 1: everywhere, 3: 512x256 only, -1: nowhere),
+ * "gemm_epi8" (-1: four instead of eight epilogue warps for the fused epilogues), "dflash_attn_window" (window the op-level
+ * sf_dflash_attention_fwd / _bwd calls apply; the step takes it from sf_dflash_config), "no_teacher_fusion", "no_loss_stats_fusion",
  * "no_rope_fusion"); each defaults to its SF_<NAME> environment variable.  Diagnostic only. */
 int sf_debug_option(const char* name, int value);
 long long sf_launch_count(void);      /* kernels launched by this library since the last reset */
@@ -229,6 +232,10 @@ typedef struct sf_dflash_config {
     int32_t loss_type;                /* 0 "dflash"; D-PACE (dflash_family_model.py:245-279,360-369): 1 "dpace",                   */
                                       /* 2 "dpace-cumulative-confidence-only", 3 "dpace-continuation-value-only"; loss_den = batch */
     float dpace_alpha;                /* smoothing of the draft's confidence on the target token (default 0.5)                    */
+    int32_t sliding_window;           /* window W of the "sliding_attention" layers (config.sliding_window; dflash.py:38-68):      */
+                                      /* slot o of a block anchored at a sees context keys [a + o - (W - 1), a) and own slots <= o */
+                                      /* (dflash_family_model.py:73-84); 0 when no layer slides                                    */
+    uint32_t sliding_layers;          /* bit l set: layer l is "sliding_attention" (config.layer_types)                            */
 } sf_dflash_config;
 /* parameter order inside the flat buffer: for each layer the SF_DF_* slices below (q, k, v contiguous = one fused GEMM
  * operand, likewise gate, up), then fc [H, F*H], hidden_norm [H], norm [H].  Names/shapes: dflash.py:336-375. */

@@ -48,6 +48,17 @@ CASES = {
     "dflashtc_d128_drop_bf16": (dict(hidden_size=512, intermediate_size=512, num_heads=8, num_kv_heads=2, head_dim=128, num_layers=1,
                                      num_target_feats=2, vocab_size=512, mask_token_id=511, block_size=16, num_anchors=7), 2, 130,
                                 torch.bfloat16, "short_row", 6),
+    # sliding-window layers (dflash.py:24-68, dflash_family_model.py:73-84; configs/qwen3.6-27b-dflash.json mixes 4 sliding + 1 full)
+    "dflash_sliding_f32": (dict(num_layers=3, layer_types=("sliding_attention", "full_attention", "sliding_attention"), sliding_window=6,
+                                block_size=4, num_anchors=7), 2, 40, torch.float32, "prefix5", 10),
+    "dflashtc_sliding_bf16": (dict(hidden_size=256, intermediate_size=512, num_heads=4, num_kv_heads=1, head_dim=64, num_layers=2,
+                                   layer_types=("sliding_attention", "full_attention"), sliding_window=48,
+                                   num_target_feats=2, vocab_size=512, mask_token_id=511, block_size=16, num_anchors=6), 2, 200,
+                              torch.bfloat16, "prefix5", 11),
+    "dflashtc_sliding_d128_bf16": (dict(hidden_size=512, intermediate_size=512, num_heads=8, num_kv_heads=2, head_dim=128, num_layers=2,
+                                        layer_types=("sliding_attention", "sliding_attention"), sliding_window=100,
+                                        num_target_feats=2, vocab_size=512, mask_token_id=511, block_size=16, num_anchors=7), 2, 230,
+                                   torch.bfloat16, "short_row", 12),
 }
 
 
@@ -67,12 +78,17 @@ def loss_mask_for(kind, B, S, g):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, (over, B, S, dtype, lmk, seed) in CASES.items():
+        if only and name not in only:
+            continue
         c = D.DFlashConfig(**over)
         qc = Qwen3Config(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size, num_attention_heads=c.num_heads,
                          num_key_value_heads=c.num_kv_heads, head_dim=c.head_dim, num_hidden_layers=c.num_layers,
                          vocab_size=c.vocab_size, rms_norm_eps=c.rms_norm_eps, rope_theta=c.rope_theta,
-                         max_position_embeddings=1024, attention_bias=False, layer_types=["full_attention"] * c.num_layers)
+                         max_position_embeddings=1024, attention_bias=False,
+                         layer_types=list(c.layer_types) if c.layer_types else ["full_attention"] * c.num_layers,
+                         sliding_window=c.sliding_window, use_sliding_window=c.sliding_window is not None)
         qc.block_size = c.block_size
         qc.num_target_layers = 8
         qc.dflash_config = {"mask_token_id": c.mask_token_id, "target_layer_ids": list(range(c.num_target_feats))}

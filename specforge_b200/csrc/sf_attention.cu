@@ -134,10 +134,24 @@ __global__ void __launch_bounds__(256) attn_bwd_diag_kernel(AttnParams p) {
             lse[hh] = p.lse[((int64_t)b * p.nh + h) * p.S + t];
             dl[hh] = p.delta[((int64_t)b * p.nh + h) * p.S + t];
         }
+        // k_{i+1} / v_{i+1} and the fp32 accumulators this iteration updates are requested before iteration i's arithmetic and
+        // shuffles, so every warp keeps ~100 B per lane in flight instead of one dependent round trip at a time
+        uint4 kn = make_uint4(0, 0, 0, 0), vn = kn;
+        if (p.J > 0) {
+            kn = __ldg(reinterpret_cast<const uint4*>(p.kdiag[0] + r * p.ldkv + kvh * D + l * 8));
+            vn = __ldg(reinterpret_cast<const uint4*>(p.vdiag[0] + r * p.ldkv + kvh * D + l * 8));
+        }
         for (int i = 0; i < p.J; ++i) {
             float kf[8], vf[8], dk[8], dv[8];
-            unpack8f(*reinterpret_cast<const uint4*>(p.kdiag[i] + r * p.ldkv + kvh * D + l * 8), kf);
-            unpack8f(*reinterpret_cast<const uint4*>(p.vdiag[i] + r * p.ldkv + kvh * D + l * 8), vf);
+            unpack8f(kn, kf);
+            unpack8f(vn, vf);
+            float* acc_dst = (sub == 0 ? p.dkdiag[i] : p.dvdiag[i]) + r * p.ldacc + kvh * D + l * 8;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            if (sub < 2) { a0 = reinterpret_cast<const float4*>(acc_dst)[0]; a1 = reinterpret_cast<const float4*>(acc_dst)[1]; }
+            if (i + 1 < p.J) {
+                kn = __ldg(reinterpret_cast<const uint4*>(p.kdiag[i + 1] + r * p.ldkv + kvh * D + l * 8));
+                vn = __ldg(reinterpret_cast<const uint4*>(p.vdiag[i + 1] + r * p.ldkv + kvh * D + l * 8));
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) { dk[e] = 0.f; dv[e] = 0.f; }
 #pragma unroll
@@ -163,8 +177,7 @@ __global__ void __launch_bounds__(256) attn_bwd_diag_kernel(AttnParams p) {
                 }
             }
             if (sub < 2) {
-                float* dst = (sub == 0 ? p.dkdiag[i] : p.dvdiag[i]) + r * p.ldacc + kvh * D + l * 8;
-                float4 a0 = reinterpret_cast<float4*>(dst)[0], a1 = reinterpret_cast<float4*>(dst)[1];
+                float* dst = acc_dst;
                 const float* src = sub == 0 ? dk : dv;
                 a0.x += src[0]; a0.y += src[1]; a0.z += src[2]; a0.w += src[3];
                 a1.x += src[4]; a1.y += src[5]; a1.z += src[6]; a1.w += src[7];

@@ -22,7 +22,7 @@ int set_error(int code, const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static const char* const kOptNames[OPT_COUNT] = {"no_pdl", "loss_side", "no_overlap", "no_swiglu_fusion", "gemm_group_m", "gemm_group_m_midk",
-                                                 "gemm_group_m_wgrad", "dflash_attn_tc", "gemm_stages", "no_teacher_fusion", "no_loss_stats_fusion", "gemm_wide", "gemm_epi_staged", "no_rope_fusion", "gemm_epi8"};
+                                                 "gemm_group_m_wgrad", "dflash_attn_tc", "gemm_stages", "no_teacher_fusion", "no_loss_stats_fusion", "gemm_wide", "gemm_epi_staged", "no_rope_fusion", "gemm_epi8", "dflash_attn_window"};
 static std::atomic<int> g_opt[OPT_COUNT];
 static std::atomic<bool> g_opt_init{false};
 static void opt_init() {

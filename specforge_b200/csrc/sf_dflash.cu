@@ -45,6 +45,9 @@ static int validate(const sf_dflash_config& c) {
     if (c.mask_token_id < 0 || c.mask_token_id >= c.vocab) return set_error(-22, "dflash config: mask_token_id outside the vocabulary");
     if (c.loss_type < 0 || c.loss_type > 3) return set_error(-22, "dflash config: loss_type=%d (0 dflash, 1 dpace, 2 cumulative-confidence-only, 3 continuation-value-only)", c.loss_type);
     if (c.loss_type != 0 && (c.dpace_alpha < 0.f || c.dpace_alpha > 1.f)) return set_error(-22, "dflash config: dpace_alpha must be in [0, 1]");
+    if (c.sliding_layers >> c.num_layers) return set_error(-22, "dflash config: sliding_layers names a layer >= num_layers=%d", c.num_layers);
+    if (c.sliding_layers && c.sliding_window <= 0)      // dflash.py:62-67
+        return set_error(-22, "dflash config: sliding_attention layers require a positive sliding_window");
     return 0;
 }
 
@@ -151,6 +154,7 @@ static AttnArgs attn_args(const Ctx& c, const sf_dflash_batch& bt, int l) {
     a.anchors = bt.anchors; a.keep = bt.keep;
     a.B = x.B; a.S = x.S; a.N = x.N; a.bs = x.bs; a.nh = x.nh; a.nkv = x.nkv; a.d = x.d;
     a.scale = 1.0f / sqrtf((float)x.d);
+    a.window = ((c.cfg->sliding_layers >> l) & 1u) ? c.cfg->sliding_window : 0;
     return a;
 }
 
@@ -330,6 +334,7 @@ static AttnArgs op_args(const void* q, const void* kn, const void* vn, const voi
     a.kc = (const __nv_bfloat16*)kc; a.ldkc = KV; a.vc = (const __nv_bfloat16*)vc; a.ldvc = KV;
     a.out = (__nv_bfloat16*)out; a.ldo = A; a.lse = lse; a.anchors = anchors; a.keep = keep;
     a.B = B; a.S = S; a.N = N; a.bs = bs; a.nh = nh; a.nkv = nkv; a.d = d; a.scale = 1.0f / sqrtf((float)d);
+    a.window = opt(OPT_DFLASH_ATTN_WINDOW) > 0 ? opt(OPT_DFLASH_ATTN_WINDOW) : 0;      // diagnostic: the op-level calls have no config
     return a;
 }
 extern "C" int sf_dflash_attention_fwd(const void* q, const void* kn, const void* vn, const void* kc, const void* vc, void* out, float* lse,

@@ -17,6 +17,8 @@ struct AttnArgs {
     float* lse;                                   // [Mq, nh]  natural-log LSE of the scaled scores
     const int32_t* anchors; const uint8_t* keep;  // [B, N]
     int B, S, N, bs, nh, nkv, d;
+    int window;                                   // sliding-window layers (dflash_family_model.py:73-84): slot o of a block anchored at a sees the
+                                                  // context keys [a + o - (window - 1), a) and its block's slots <= o; 0 = full attention
     float scale;
     // backward
     const __nv_bfloat16* dout; int64_t lddo;

@@ -35,6 +35,7 @@ struct TcParams {
     float* lse;                    // [Mq, nh], natural log of sum exp(scaled score)
     const int32_t* anchors; const uint8_t* keep;
     int B, S, N, bs, nh, nkv, g;
+    int window;                    // sliding-window layer (0 = full attention)
     float scale_log2;              // d^-0.5 * log2(e)
 };
 
@@ -83,12 +84,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int BPC = 2 * BPU;                  // blocks per CTA
     const int n0 = blockIdx.x * BPC;
     constexpr int nx = 2;
-    int amax = 0;                             // largest anchor of a kept block of this CTA (uniform)
+    int amax = 0, amin = 0x7fffffff;          // largest / smallest anchor of a kept block of this CTA (uniform)
     for (int i = 0; i < BPC; ++i) {
         const int n = n0 + i;
-        if (n < p.N && p.keep[b * p.N + n]) amax = max(amax, p.anchors[b * p.N + n]);
+        if (n < p.N && p.keep[b * p.N + n]) { amax = max(amax, p.anchors[b * p.N + n]); amin = min(amin, p.anchors[b * p.N + n]); }
     }
-    const int n_ctx = (amax + C::BKV - 1) / C::BKV;
+    // sliding-window layer (window > 0): slot o of a block anchored at a sees context keys [a + o - (W - 1), a) and own slots <= o
+    // (dflash_family_model.py:73-84); context tiles that end below every kept block's window are not visited at all
+    const int t_lo = (p.window > 0 && amax > 0) ? max(0, amin - (p.window - 1)) / C::BKV : 0;
+    const int n_ctx = (amax + C::BKV - 1) / C::BKV - t_lo;
     const int n_kv = n_ctx + 1;               // + the own-keys tile
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kc); tma_prefetch_desc(&tm_vc); tma_prefetch_desc(&tm_kn); tma_prefetch_desc(&tm_vn); }
@@ -124,7 +128,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 mbar_expect_tx(b_kfull(s), C::KV_BYTES);
                 for (int kb = 0; kb < C::NB; ++kb) {
                     const uint32_t dst = sbase + C::OFF_K + s * C::KV_BYTES + kb * (C::BKV * 128);
-                    if (t < n_ctx) tma_load_3d(dst, &tm_kc, b_kfull(s), kvh * D + kb * 64, t * C::BKV, b);
+                    if (t < n_ctx) tma_load_3d(dst, &tm_kc, b_kfull(s), kvh * D + kb * 64, (t_lo + t) * C::BKV, b);
                     else           tma_load_3d(dst, &tm_kn, b_kfull(s), kvh * D + kb * 64, n0 * p.bs, b);
                 }
             }
@@ -136,7 +140,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 mbar_expect_tx(b_vfull(s), C::KV_BYTES);
                 for (int kb = 0; kb < C::NB; ++kb) {
                     const uint32_t dst = sbase + C::OFF_V + s * C::KV_BYTES + kb * (C::BKV * 128);
-                    if (t < n_ctx) tma_load_3d(dst, &tm_vc, b_vfull(s), kvh * D + kb * 64, t * C::BKV, b);
+                    if (t < n_ctx) tma_load_3d(dst, &tm_vc, b_vfull(s), kvh * D + kb * 64, (t_lo + t) * C::BKV, b);
                     else           tma_load_3d(dst, &tm_vn, b_vfull(s), kvh * D + kb * 64, n0 * p.bs, b);
                 }
             }
@@ -195,14 +199,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int hg = (r % R) / p.bs, o = r % p.bs;
         const bool valid = n < p.N;
         const bool kept = valid && p.keep[b * p.N + n] != 0;
-        const int a_r = kept ? p.anchors[b * p.N + n] : 0;       // context keys [0, a_r)
+        const int a_r = kept ? p.anchors[b * p.N + n] : 0;       // context keys [lo_r, a_r)
+        const int W = p.window, lo_r = (W > 0 && kept) ? a_r + o - (W - 1) : 0;
         const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
         const uint32_t t_o = t_lane + C::TM_O + x * D;
         float m_ref = -INFINITY, l = 0.f;
         const float c = p.scale_log2;
         for (int t = 0; t < n_kv; ++t) {
             const int u = t & 1;
-            const int kv0 = t * C::BKV;
+            const int kv0 = (t_lo + t) * C::BKV;
             const bool own = t == n_ctx;
             mbar_wait(b_sfull(x, u), (t >> 1) & 1, 22 + x);
             tc_fence_after();
@@ -213,11 +218,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             if (own) {                          // block-diagonal: key column cc belongs to CTA block cc / bs
 #pragma unroll
                 for (int cc = 0; cc < C::BKV; ++cc)
-                    if (!kept || cc / p.bs != blk) sv[cc] = 0xff800000u;
-            } else if (!kept || kv0 + C::BKV > a_r) {
+                    if (!kept || cc / p.bs != blk || (W > 0 && cc % p.bs > o)) sv[cc] = 0xff800000u;
+            } else if (!kept || kv0 + C::BKV > a_r || kv0 < lo_r) {
 #pragma unroll
                 for (int cc = 0; cc < C::BKV; ++cc)
-                    if (!kept || kv0 + cc >= a_r) sv[cc] = 0xff800000u;
+                    if (!kept || kv0 + cc >= a_r || kv0 + cc < lo_r) sv[cc] = 0xff800000u;
             }
             float mx = -INFINITY;
 #pragma unroll
@@ -311,7 +316,7 @@ static int fwd_tc_t(const AttnArgs& a, cudaStream_t st) {
     SF_TRY_RC(make_tmap_3d_bf16(&tvn, a.vn, KVc, Q, a.B, a.ldvn, C::BKV));
     TcParams p{};
     p.out = a.out; p.ldo = a.ldo; p.lse = a.lse; p.anchors = a.anchors; p.keep = a.keep;
-    p.B = a.B; p.S = a.S; p.N = a.N; p.bs = a.bs; p.nh = a.nh; p.nkv = a.nkv; p.g = g;
+    p.B = a.B; p.S = a.S; p.N = a.N; p.bs = a.bs; p.nh = a.nh; p.nkv = a.nkv; p.g = g; p.window = a.window;
     p.scale_log2 = a.scale * 1.4426950408889634f;
     static bool set = false;
     if (!set) {

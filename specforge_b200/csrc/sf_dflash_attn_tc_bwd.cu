@@ -33,6 +33,7 @@ struct TcBwdParams {
     __nv_bfloat16* dkc; int64_t lddkc;             // [Mc, nkv*D]
     __nv_bfloat16* dvc; int64_t lddvc;
     int B, S, N, bs, nh, nkv, g;
+    int window;                                    // sliding-window layer (0 = full attention), see sf_dflash_attn_tc.cu
     float scale_log2;
 };
 
@@ -77,12 +78,13 @@ df_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int kvh = blockIdx.y, b = blockIdx.z;
     const int R = p.g * p.bs, BPU = C::BQ / R;
     const int n0 = blockIdx.x * BPU;              // first anchor block of this unit
-    int amax = 0;
+    int amax = 0, amin = 0x7fffffff;
     for (int i = 0; i < BPU; ++i) {
         const int n = n0 + i;
-        if (n < p.N && p.keep[b * p.N + n]) amax = max(amax, p.anchors[b * p.N + n]);
+        if (n < p.N && p.keep[b * p.N + n]) { amax = max(amax, p.anchors[b * p.N + n]); amin = min(amin, p.anchors[b * p.N + n]); }
     }
-    const int n_ctx = (amax + C::BKV - 1) / C::BKV;
+    const int t_lo = (p.window > 0 && amax > 0) ? max(0, amin - (p.window - 1)) / C::BKV : 0;   // first context tile inside a window
+    const int n_ctx = (amax + C::BKV - 1) / C::BKV - t_lo;
     const int n_kv = n_ctx + 1;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_kc); tma_prefetch_desc(&tm_vc); tma_prefetch_desc(&tm_kn); tma_prefetch_desc(&tm_vn); }
@@ -118,7 +120,7 @@ df_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 mbar_expect_tx(b_kfull(sk), C::KT_BYTES);
                 for (int kbk = 0; kbk < C::NB; ++kbk) {
                     const uint32_t dst = sbase + C::OFF_K + sk * C::KT_BYTES + kbk * (C::BKV * 128);
-                    if (t < n_ctx) tma_load_3d(dst, &tm_kc, b_kfull(sk), kvh * D + kbk * 64, t * C::BKV, b);
+                    if (t < n_ctx) tma_load_3d(dst, &tm_kc, b_kfull(sk), kvh * D + kbk * 64, (t_lo + t) * C::BKV, b);
                     else           tma_load_3d(dst, &tm_kn, b_kfull(sk), kvh * D + kbk * 64, n0 * p.bs, b);
                 }
             }
@@ -129,7 +131,7 @@ df_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 mbar_expect_tx(b_vfull(sv), C::KT_BYTES);
                 for (int kbk = 0; kbk < C::NB; ++kbk) {
                     const uint32_t dst = sbase + C::OFF_V + sv * C::KT_BYTES + kbk * (C::BKV * 128);
-                    if (t < n_ctx) tma_load_3d(dst, &tm_vc, b_vfull(sv), kvh * D + kbk * 64, t * C::BKV, b);
+                    if (t < n_ctx) tma_load_3d(dst, &tm_vc, b_vfull(sv), kvh * D + kbk * 64, (t_lo + t) * C::BKV, b);
                     else           tma_load_3d(dst, &tm_vn, b_vfull(sv), kvh * D + kbk * 64, n0 * p.bs, b);
                 }
             }
@@ -191,6 +193,7 @@ df_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const bool valid = n < p.N;
         const bool kept = valid && p.keep[b * p.N + n] != 0;
         const int a_r = kept ? p.anchors[b * p.N + n] : 0;
+        const int W = p.window, lo_r = (W > 0 && kept) ? a_r + o - (W - 1) : 0;
         const int head = kvh * p.g + hg;
         const int64_t orow = ((int64_t)b * p.N + min(n, p.N - 1)) * p.bs + o;
         const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
@@ -200,7 +203,7 @@ df_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const float Dl = kept ? p.delta[orow * p.nh + head] : 0.f;
         for (int t = 0; t < n_kv; ++t) {
             const int u = t & 1;
-            const int kv0 = t * C::BKV;
+            const int kv0 = (t_lo + t) * C::BKV;
             const bool own = t == n_ctx;
             mbar_wait(b_sdpfull(u), (t >> 1) & 1, 47);
             tc_fence_after();
@@ -214,11 +217,11 @@ df_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             if (own) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e)
-                    if (!kept || (x * 32 + e) / p.bs != blk) sv[e] = 0xff800000u;
-            } else if (!kept || kv0 + C::BKV > a_r) {
+                    if (!kept || (x * 32 + e) / p.bs != blk || (W > 0 && (x * 32 + e) % p.bs > o)) sv[e] = 0xff800000u;
+            } else if (!kept || kv0 + C::BKV > a_r || kv0 < lo_r) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e)
-                    if (!kept || kv0 + x * 32 + e >= a_r) sv[e] = 0xff800000u;
+                    if (!kept || kv0 + x * 32 + e >= a_r || kv0 + x * 32 + e < lo_r) sv[e] = 0xff800000u;
             }
             uint32_t dsk[16];
 #pragma unroll
@@ -305,11 +308,14 @@ df_bwd_ctx_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int k0 = kb * C::BK;
     // kept blocks come first and their anchors are sorted (sample_anchor_positions): the blocks that see key k0 are
     // the contiguous range [n_lo, n_hi)
+    // (sliding-window layer: additionally only the blocks whose lowest window bound a - (W - 1) does not lie above the tile)
     int n_hi = 0, n_lo = 0;
     for (int n = 0; n < p.N; ++n) {
         if (!p.keep[b * p.N + n]) break;
+        const int an = p.anchors[b * p.N + n];
+        if (p.window > 0 && an - (p.window - 1) > k0 + C::BK - 1) break;
         n_hi = n + 1;
-        if (p.anchors[b * p.N + n] <= k0) n_lo = n + 1;
+        if (an <= k0) n_lo = n + 1;
     }
     const int n_it = n_hi - n_lo;
     if (n_it <= 0) {      // nobody attends to this tile: its gradients are zero (uniform early exit, before any barrier)
@@ -442,7 +448,9 @@ df_bwd_ctx_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         for (int it = 0; it < n_it; ++it) {
             const int u = it & 1;
             const int a_n = p.anchors[b * p.N + n_lo + it];          // every query column of this iteration shares the limit
-            const bool key_ok = key < a_n;                           // (a_n <= S - 2, so key < S as well)
+            // sliding-window layer: query slot o sees this key iff key >= a_n + o - (W - 1), i.e. o <= slack
+            const int slack = p.window > 0 ? key - (a_n - (p.window - 1)) : 0x3fffffff;
+            const bool key_ok = key < a_n && slack >= 0;             // (a_n <= S - 2, so key < S as well)
             mbar_wait(b_sdpfull(u), (it >> 1) & 1, 36);
             mbar_wait(b_ldfull(u), (it >> 1) & 1, 35);
             tc_fence_after();
@@ -467,7 +475,8 @@ df_bwd_ctx_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     float pv[4], dsv[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float pr = ex2_approx(fmaf(__uint_as_float(sv[j * 4 + e]), c, -Lv[e]));
+                        float pr = ex2_approx(fmaf(__uint_as_float(sv[j * 4 + e]), c, -Lv[e]));
+                        if ((x * 32 + j * 4 + e) % p.bs > slack) pr = 0.f;       // query column = hg * bs + o (never true for full layers)
                         pv[e] = pr;
                         dsv[e] = pr * (__uint_as_float(dv[j * 4 + e]) - Dv[e]) * scale;
                     }
@@ -576,7 +585,8 @@ __global__ void __launch_bounds__(256) df_bwd_own_kernel(AttnArgs a) {
         const int head = kvh * g + rr / bs;
         float s = 0.f, dp = 0.f;
         for (int c = 0; c < d; ++c) { s += Qs[rr * ds + c] * Ks[k * ds + c]; dp += Gs[rr * ds + c] * Vs[k * ds + c]; }
-        const float pr = __expf(s * a.scale - a.lse[orow * a.nh + head]);
+        const bool allowed = a.window == 0 || k <= rr % bs;          // sliding-window layer: own slots <= the query's slot
+        const float pr = allowed ? __expf(s * a.scale - a.lse[orow * a.nh + head]) : 0.f;
         Ps[rr * ts + k] = pr;
         Ds[rr * ts + k] = pr * (dp - a.delta[orow * a.nh + head]) * a.scale;
     }
@@ -591,6 +601,7 @@ __global__ void __launch_bounds__(256) df_bwd_own_kernel(AttnArgs a) {
 }
 
 // ============================================================================================ host
+static int g_own_smem_set = 0;
 template <int D>
 static int bwd_tc_t(const AttnArgs& a, cudaStream_t st) {
     const int g = a.nh / a.nkv, R = g * a.bs;
@@ -608,7 +619,7 @@ static int bwd_tc_t(const AttnArgs& a, cudaStream_t st) {
     TcBwdParams p{};
     p.lse = a.lse; p.delta = a.delta; p.anchors = a.anchors; p.keep = a.keep;
     p.dq = a.dq; p.lddq = a.lddq; p.dkc = a.dkc; p.lddkc = a.lddkc; p.dvc = a.dvc; p.lddvc = a.lddvc;
-    p.B = a.B; p.S = a.S; p.N = a.N; p.bs = a.bs; p.nh = a.nh; p.nkv = a.nkv; p.g = g;
+    p.B = a.B; p.S = a.S; p.N = a.N; p.bs = a.bs; p.nh = a.nh; p.nkv = a.nkv; p.g = g; p.window = a.window;
     p.scale_log2 = a.scale * kLog2e;
     df_delta_kernel<<<(unsigned)((Mq * a.nh * 32 + 255) / 256), 256, 0, st>>>(a.out, a.ldo, a.dout, a.lddo, a.nh, D, Mq, a.delta);
     SF_CUDA_CHECK_LAUNCH("dflash delta");
@@ -626,8 +637,13 @@ static int bwd_tc_t(const AttnArgs& a, cudaStream_t st) {
     }
     {
         const int smem = (int)((2 * R * (D + 1) + 2 * a.bs * (D + 1) + 2 * R * (a.bs + 1)) * 4);
-        static int set = 0;
-        if (smem > set) { cudaFuncSetAttribute(df_bwd_own_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = smem; }
+        // one high-water mark for both head dims: the kernel is not a template, so a per-instantiation mark let the d = 64 call
+        // lower the limit a d = 128 call had raised ("invalid argument" on the next d = 128 launch)
+        if (smem > g_own_smem_set) {
+            cudaError_t e = cudaFuncSetAttribute(df_bwd_own_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return set_error(-22, "dflash bwd_own smem attr: %s", cudaGetErrorString(e));
+            g_own_smem_set = smem;
+        }
         df_bwd_own_kernel<<<dim3(a.N, a.nkv, a.B), 256, smem, st>>>(a);
         SF_CUDA_CHECK_LAUNCH("dflash bwd_own");
     }

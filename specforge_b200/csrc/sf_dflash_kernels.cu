@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
     for (int i = 0; i < kMaxCols; ++i) acc[i] = 0.f;
     const int n_ctx_tiles = (anchor + kTK - 1) / kTK;
-    for (int tile = 0; tile <= n_ctx_tiles; ++tile) {
+    // sliding-window layer: row o sees context keys >= lo_r and own slots <= o; tiles below the block's window are skipped
+    const int W = a.window, lo_r = W > 0 ? anchor + o - (W - 1) : 0;
+    const int tile0 = W > 0 ? min(n_ctx_tiles, max(0, anchor - (W - 1)) / kTK) : 0;
+    for (int tile = tile0; tile <= n_ctx_tiles; ++tile) {
         const bool own = tile == n_ctx_tiles;
         const int k0 = own ? 0 : tile * kTK;
         const int nk = own ? bs : min(kTK, anchor - k0);
@@ -229,7 +232,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
         for (int k = p; k < nk; k += TPR) {
             float s = 0.f;
             for (int c = 0; c < d; ++c) s += Qs[r * ds + c] * Ks[k * ds + c];
-            Ss[r * (kTK + 1) + k] = s * a.scale;
+            const bool allowed = W == 0 || (own ? k <= o : k0 + k >= lo_r);
+            Ss[r * (kTK + 1) + k] = allowed ? s * a.scale : -FLT_MAX;      // -FLT_MAX marks a masked key (exp -> 0 below)
         }
         __syncthreads();
         if (p == 0) {
@@ -237,7 +241,11 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
             for (int k = 0; k < nk; ++k) mx = fmaxf(mx, Ss[r * (kTK + 1) + k]);
             const float sc = __expf(m_s[r] - mx);
             float l = l_s[r] * sc;
-            for (int k = 0; k < nk; ++k) { const float e = __expf(Ss[r * (kTK + 1) + k] - mx); Ss[r * (kTK + 1) + k] = e; l += e; }
+            for (int k = 0; k < nk; ++k) {
+                const float sv = Ss[r * (kTK + 1) + k];
+                const float e = sv == -FLT_MAX ? 0.f : __expf(sv - mx);
+                Ss[r * (kTK + 1) + k] = e; l += e;
+            }
             m_s[r] = mx; l_s[r] = l; sc_s[r] = sc;
         }
         __syncthreads();
@@ -309,7 +317,9 @@ __global__ void __launch_bounds__(256) attn_bwd_q_kernel(AttnArgs a) {
 #pragma unroll
     for (int i = 0; i < kMaxCols; ++i) acc[i] = 0.f;
     const int n_ctx_tiles = (anchor + kTK - 1) / kTK;
-    for (int tile = 0; tile <= n_ctx_tiles; ++tile) {
+    const int W = a.window, lo_r = W > 0 ? anchor + o - (W - 1) : 0;          // sliding-window layer, as in the forward
+    const int tile0 = W > 0 ? min(n_ctx_tiles, max(0, anchor - (W - 1)) / kTK) : 0;
+    for (int tile = tile0; tile <= n_ctx_tiles; ++tile) {
         const bool own = tile == n_ctx_tiles;
         const int k0 = own ? 0 : tile * kTK;
         const int nk = own ? bs : min(kTK, anchor - k0);
@@ -325,7 +335,8 @@ __global__ void __launch_bounds__(256) attn_bwd_q_kernel(AttnArgs a) {
         for (int k = p; k < nk; k += TPR) {
             float s = 0.f, dp = 0.f;
             for (int c = 0; c < d; ++c) { s += Qs[r * ds + c] * Ks[k * ds + c]; dp += Gs[r * ds + c] * Vs[k * ds + c]; }
-            const float pr = __expf(s * a.scale - lse_s[r]);
+            const bool allowed = W == 0 || (own ? k <= o : k0 + k >= lo_r);
+            const float pr = allowed ? __expf(s * a.scale - lse_s[r]) : 0.f;
             Ps[r * ts + k] = pr;
             Ds[r * ts + k] = pr * (dp - del_s[r]) * a.scale;
         }
@@ -381,6 +392,7 @@ __global__ void __launch_bounds__(256) attn_bwd_ctx_kernel(AttnArgs a) {
     for (int n = 0; n < a.N; ++n) {
         const int anchor = a.anchors[b * a.N + n];
         if (!a.keep[b * a.N + n] || anchor <= k0) continue;      // uniform across the CTA
+        if (a.window > 0 && k0 + nk_tile - 1 < anchor - (a.window - 1)) continue;   // the whole tile lies below the block's window
         const int nk = min(nk_tile, anchor - k0);
         const int64_t qrow0 = ((int64_t)b * a.N + n) * bs;
         __syncthreads();
@@ -398,7 +410,7 @@ __global__ void __launch_bounds__(256) attn_bwd_ctx_kernel(AttnArgs a) {
             const float lse = a.lse[orow * a.nh + head], del = a.delta[orow * a.nh + head];
             for (int k = p; k < kTK; k += TPR) {
                 float pr = 0.f, dsv = 0.f;
-                if (k < nk) {
+                if (k < nk && (a.window == 0 || k0 + k >= anchor + r % bs - (a.window - 1))) {
                     float s = 0.f, dp = 0.f;
                     for (int c = 0; c < d; ++c) { s += Qs[r * ds + c] * Ks[k * ds + c]; dp += Gs[r * ds + c] * Vs[k * ds + c]; }
                     pr = __expf(s * a.scale - lse);

@@ -93,7 +93,7 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
 // One block per row (looping), kChunks 16-byte chunks per thread, ONE block reduction per row
 // (sum x^2 and sum g*x together), so several blocks stay resident per SM and hide the HBM latency.
 template <int kChunks, int kThreads>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kChunks == 1 ? 1024 / kThreads : 1)   // 64 registers: two 512-thread blocks per SM
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64_t* __restrict__ ids, int S, int shift,
                    const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ dy, int64_t lddy,
                    const __nv_bfloat16* __restrict__ add1, const __nv_bfloat16* __restrict__ add2,
@@ -113,7 +113,12 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
         }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t r = blockIdx.x; r < M; r += gridDim.x) {
+    // Software pipeline over the rows of this block: the 16-byte loads of row r + gridDim.x (x and dy) and row r's own residual-
+    // gradient addends are issued before row r's block reduction, so a block always has a row of loads in flight — with one row at
+    // a time the two dependent round trips per row (x/dy, then the addends) left the kernel at ~0.45 of HBM bandwidth.
+    uint4 xn[kChunks], dn[kChunks];
+    const bool has_add1 = dx && add1, has_add2 = dx && add2;
+    auto issue = [&](int64_t r) {
         const __nv_bfloat16* xr;
         if (ids) {
             const int64_t b = r / S, s = r % S;
@@ -122,20 +127,35 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
         } else {
             xr = x + r * ldx;
         }
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            const int ch = threadIdx.x + c * kThreads;
+            if (ch < nchunks) {
+                xn[c] = __ldg(reinterpret_cast<const uint4*>(xr) + ch);
+                dn[c] = __ldg(reinterpret_cast<const uint4*>(dy + r * lddy) + ch);
+            }
+        }
+    };
+    if ((int64_t)blockIdx.x < M) issue(blockIdx.x);
+    for (int64_t r = blockIdx.x; r < M; r += gridDim.x) {
         float xv[kChunks][8], gv[kChunks][8];
+        uint4 a1c[kChunks], a2c[kChunks];
         float ss = 0.f, gx = 0.f;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
             const int ch = threadIdx.x + c * kThreads;
             if (ch < nchunks) {
-                bf16x8 t; t.u = __ldg(reinterpret_cast<const uint4*>(xr) + ch);
+                if (has_add1) a1c[c] = __ldg(reinterpret_cast<const uint4*>(add1 + r * (int64_t)H) + ch);   // consumed after the reduction
+                if (has_add2) a2c[c] = __ldg(reinterpret_cast<const uint4*>(add2 + r * (int64_t)H) + ch);
+                bf16x8 t; t.u = xn[c];
                 t.unpack(xv[c]);
-                bf16x8 d; d.u = __ldg(reinterpret_cast<const uint4*>(dy + r * lddy) + ch);
+                bf16x8 d; d.u = dn[c];
                 d.unpack(gv[c]);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { ss += xv[c][i] * xv[c][i]; gx += gv[c][i] * wf[c][i] * xv[c][i]; }
             }
         }
+        if (r + gridDim.x < M) issue(r + gridDim.x);
         ss = warp_sum(ss); gx = warp_sum(gx);
         __syncthreads();
         if (lane == 0) red[warp] = make_float2(ss, gx);
@@ -158,14 +178,14 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
                     o[i] = rstd * (gv[c][i] * wf[c][i] - xh * mean);
                 }
                 if (dx) {
-                    if (add1) {
-                        bf16x8 a; a.u = __ldg(reinterpret_cast<const uint4*>(add1 + r * (int64_t)H) + ch);
+                    if (has_add1) {
+                        bf16x8 a; a.u = a1c[c];
                         float af[8]; a.unpack(af);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o[i] += af[i];
                     }
-                    if (add2) {
-                        bf16x8 a; a.u = __ldg(reinterpret_cast<const uint4*>(add2 + r * (int64_t)H) + ch);
+                    if (has_add2) {
+                        bf16x8 a; a.u = a2c[c];
                         float af[8]; a.unpack(af);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o[i] += af[i];

@@ -68,7 +68,7 @@ static int num_sms() {
 static bool heavy_epilogue(int epi) {
     return epi == EPI_TEACHER || epi == EPI_BF16_STATS || epi == EPI_SWIGLU || epi == EPI_SWIGLU_BWD || epi == EPI_BF16_ROPE;
 }
-static bool use_epi8(const GemmDesc& g) { return opt(OPT_GEMM_EPI8) >= 0 && (opt(OPT_GEMM_EPI8) == 1 || heavy_epilogue(g.epi)); }
+static bool use_epi8(const GemmDesc& g) { return opt(OPT_GEMM_EPI8) >= 0 && heavy_epilogue(g.epi); }   // the 8-warp instance holds the fused epilogues only
 
 template <int G, int AM, int BM, int BN, int EW = 4>
 static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
@@ -102,9 +102,10 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     if (p.stages < 2) p.stages = 2;
     if (p.stages > Cfg::kMaxStages) p.stages = Cfg::kMaxStages;
     // warp-staged (coalesced) bf16 epilogue transfers: needs 8 KB, i.e. one ring stage less than the deepest ring
-    // gemm_epi_staged: 1 = every 256 x 256 launch, 2 = only the SwiGLU-backward epilogue (2 x 64 B read + 2 x 64 B written per chunk)
+    // gemm_epi_staged: 0 (default) / 2 = only the SwiGLU-backward epilogue (2 x 64 B read + 2 x 64 B written per chunk) — in the step
+    // 238.9 vs 242.7 ms (none, value 3) vs 240.3 (every launch, value 1), profiles/r02_ab_gemm_tiling.jsonl; -1 = no staging in either tiling
     const int so = opt(OPT_GEMM_EPI_STAGED);
-    p.staged = (so == 1 || (so == 2 && g.epi == EPI_SWIGLU_BWD)) ? 1 : 0;
+    p.staged = (so == 1 || ((so == 0 || so == 2) && g.epi == EPI_SWIGLU_BWD)) ? 1 : 0;
     while (p.staged && Cfg::smem_bytes(p.stages, 1) > 227 * 1024) --p.stages;
     const int smem_bytes = Cfg::smem_bytes(p.stages, p.staged);
     const int tiles = p.num_m_blocks * p.num_n_blocks;
@@ -152,8 +153,8 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
 }
 
 // ---- 512 x 256 tiling (sf_gemm_wide.cuh)
-template <int AM, int BM>
-static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
+template <int AM, int BM, int EPISET>
+static int launch_wide_impl(const GemmDesc& g, cudaStream_t stream) {
     using Cfg = GemmWideCfg<AM, BM>;
     CUtensorMap ta, tb;
     int rc;
@@ -183,7 +184,7 @@ static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int clusters = num_sms() / 2;
     if (tiles < clusters) clusters = tiles;
-    auto kern = gemm_wide_kernel<AM, BM>;
+    auto kern = gemm_wide_kernel<AM, BM, EPISET>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -222,6 +223,10 @@ static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
     count_launch();
     return 0;
 }
+template <int AM, int BM>
+static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
+    return heavy_epilogue(g.epi) ? launch_wide_impl<AM, BM, 2>(g, stream) : launch_wide_impl<AM, BM, 1>(g, stream);
+}
 // Which tiling.  The wide one moves 25 % fewer operand bytes per FLOP but cannot hide its epilogue behind the next tile's main loop
 // (all 512 TMEM columns hold one tile), so the accumulator drain is paid once per tile — and TMEM reads run at 64 B/clk per SM
 // (tools/gemm_trace.py: ~5 k cycles per 128 x 256 half next to the other half's MMAs, ~11 k exposed per tile of 65 k at K = 4096).
@@ -232,7 +237,7 @@ static int launch_wide(const GemmDesc& g, cudaStream_t stream) {
 // In-step rates by shape (bench.py roofline.gemm_by_shape) show why: with its drain exposed the wide tiling runs the SwiGLU
 // epilogues at 780-1065 TFLOP/s at K = 4096 (1350 in the 256 x 256 tiling, where the epilogue hides behind the next tile).
 // gemm_wide: -1 never; 0 (default) M >= 512 and K > 4096, K > 8192 for the heavy epilogues (SwiGLU fwd/bwd, RoPE, row statistics);
-// 1 every GEMM except the row-statistics epilogues at K <= 4096; 2 always; 3 only K > 8192.
+// 1 every GEMM except the row-statistics epilogues at K <= 4096; 2 always; 3 only K > 8192; 4 every plain epilogue, fused ones for K > 8192.
 static bool use_wide(const GemmDesc& g) {
     const int o = opt(OPT_GEMM_WIDE);
     if (o < 0 || g.M < 512) return false;
@@ -241,6 +246,7 @@ static bool use_wide(const GemmDesc& g) {
     const bool stats = g.epi == EPI_TEACHER || g.epi == EPI_BF16_STATS;
     if (o == 1) return g.K > 4096 || !stats;
     const bool heavy = heavy_epilogue(g.epi);
+    if (o == 4) return !heavy || g.K > 8192;
     return g.K > (heavy ? 8192 : 4096);
 }
 

@@ -191,7 +191,7 @@ __device__ __forceinline__ void gemm_epilogue_prefetch(const GemmParams& p, cons
 // The epilogue of one thread: its row of the [128 x kBlockN] accumulator block at TMEM address t_row (lane = row), processed in
 // 32-column chunks; shared by the 256 x 256 (gemm_kernel) and 512 x 256 (gemm_wide_kernel) tilings.  wbuf: this warp's 2 KB
 // staging block (bf16 outputs / inputs then move as described above) or nullptr (direct per-thread accesses).
-template <int kBlockN>
+template <int kBlockN, int kEpiSet = 0>
 __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const int row, const bool row_ok, const int n_blk,
                                                    const int n0, const uint32_t t_row, uint8_t* wbuf, const int lane,
                                                    const int part = 0, const int nparts = 1) {
@@ -199,7 +199,11 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
             // each accumulator half with two warpgroups side by side); the row-statistics partials are then per (n-block, part)
             const int row0 = row - lane;                                   // first row of this warp's 32-row block
             const int rows_valid = min(32, max(0, p.M - row0));
-            if (p.epi == EPI_SWIGLU) {
+            // kEpiSet: 0 = every epilogue, 1 = the plain ones only (bf16 / residual / fp32 / accumulate), 2 = the fused ones only
+            // (heavy_epilogue() in sf_gemm.cu) — the 384-thread kernels are capped at 168 registers, and one function body for all
+            // variants made both groups spill.
+            constexpr bool kLight = kEpiSet == 1;
+            if (!kLight && p.epi == EPI_SWIGLU) {
                 // columns [0,128) of the accumulator = gate(j0 + .), [128,256) = up(j0 + .)
                 const int j0 = n_blk * (kBlockN / 2);
                 __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
@@ -239,7 +243,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         reinterpret_cast<uint4*>(act + col)[q] = make_uint4(oa[q * 4], oa[q * 4 + 1], oa[q * 4 + 2], oa[q * 4 + 3]);
                     }
                 }
-            } else if (p.epi == EPI_SWIGLU_BWD) {
+            } else if (!kLight && p.epi == EPI_SWIGLU_BWD) {
                 const __nv_bfloat16* gu = p.R + (size_t)row * p.ldr;
                 const __nv_bfloat16* gu0 = p.R + (size_t)row0 * p.ldr;
                 __nv_bfloat16* dgu = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd;
@@ -307,7 +311,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         warp_store_32x32(wbuf, lane, duw, dgu0 + p.n_half + col, p.ldd, rows_valid);
                     }
                 }
-            } else if (p.epi == EPI_BF16_STATS || p.epi == EPI_TEACHER) {
+            } else if (!kLight && (p.epi == EPI_BF16_STATS || p.epi == EPI_TEACHER)) {
                 const bool gather = p.epi == EPI_TEACHER;
                 float m = -INFINITY, d = 0.f, md = -INFINITY, dd = 0.f;
                 int idx = 0x7fffffff;
@@ -386,7 +390,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                     sp[0] = m; sp[plane] = d; sp[2 * plane] = __int_as_float(idx);
                     if (gather) { sp[3 * plane] = md; sp[4 * plane] = dd; }
                 }
-            } else if (p.epi == EPI_BF16_ROPE) {
+            } else if (!kLight && p.epi == EPI_BF16_ROPE) {
                 // chunk pairs (c, c + half/32) of one head: x1 = columns [hc, hc+32), x2 = columns [hc + half, hc + half + 32)
                 const int hchunks = p.head_dim / 32, pairs = hchunks / 2;              // 4 / 2 (d = 128) or 2 / 1 (d = 64)
                 const int pos = (row_ok ? row % p.S : 0) + p.rope_pos0;
@@ -451,7 +455,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         }
                     }
                 }
-            } else {
+            } else if (kEpiSet != 2) {
             const int c_begin = part * (kBlockN / 32 / nparts), c_end = (part + 1) * (kBlockN / 32 / nparts);
             const bool resid = p.epi == EPI_BF16_RESID;
             uint4 rn[4];                                             // the NEXT chunk's residual, already in flight
@@ -462,17 +466,14 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                 else row_load_issue(rn, p.R + (size_t)row * p.ldr + col, row_ok);
             };
             issue_resid(c_begin);
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(t_row + c * 32, v);
+            // One 32-column chunk: v holds this thread's row of the accumulator (already waited for).
+            auto chunk = [&](const uint32_t (&v)[32], const int c) {
                 uint4 rc[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) rc[q] = rn[q];
                 issue_resid(c + 1);
-                tmem_ld_wait();
                 const int col = n0 + c * 32;
-                if (col >= p.N) continue;
+                if (col >= p.N) return;
                 const bool full = (col + 32 <= p.N);
                 if (wbuf && full && (p.epi == EPI_BF16 || p.epi == EPI_BF16_RESID)) {   // warp-staged: every lane takes part
                     uint32_t o[16];
@@ -492,9 +493,9 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         for (int e = 0; e < 16; ++e) o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
                     }
                     warp_store_32x32(wbuf, lane, o, reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row0 * p.ldd + col, p.ldd, rows_valid);
-                    continue;
+                    return;
                 }
-                if (!row_ok) continue;
+                if (!row_ok) return;
                 if (p.epi == EPI_BF16 || p.epi == EPI_BF16_RESID) {
                     __nv_bfloat16* dst =
                         reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col;
@@ -555,6 +556,23 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
                         }
                     }
                 }
+            };
+            // The TMEM read of chunk c+1 is in flight while chunk c is converted, staged and stored: a chunk is otherwise a serial
+            // chain (tcgen05.ld ~0.5 k cycles with 8 warps on the 64 B/clk port, then ~0.7 k of conversion / staging / stores),
+            // which made the 512 x 256 tiling's two accumulator halves take ~5 k cycles each to drain (profiles/r02_gemm_wide_trace_*).
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(t_row + c_begin * 32, va);
+            tmem_ld_wait();
+#pragma unroll 1
+            for (int c = c_begin; c < c_end; c += 2) {
+                if (c + 1 < c_end) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, vb);
+                chunk(va, c);
+                if (c + 1 < c_end) {
+                    tmem_ld_wait();
+                    if (c + 2 < c_end) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, va);
+                    chunk(vb, c + 1);
+                    if (c + 2 < c_end) tmem_ld_wait();
+                }
             }
             }
 }
@@ -563,7 +581,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const in
 // SM sub-partition hosts ONE epilogue warp, so nothing hides the latency of its dependent ALU / MUFU chain: the exp-heavy epilogues
 // (SwiGLU backward ~35 instructions per element) then take as long as the K = 4096 main loop and pace the GEMM (1.02 PFLOP/s in the
 // step).  Eight warps double the epilogue's issue rate at the price of a 168-register cap.
-template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN, int kEpiWarps = 4>
+template <int kCtaGroup, int kAMajor, int kBMajor, int kBlockN, int kEpiWarps = 4>   // 8 warps: used for the fused epilogues only
 __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmParams p) {
@@ -730,7 +748,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 tile_coords(tile + num_clusters, nm, nn);
                 gemm_epilogue_prefetch<Cfg::BLOCK_N>(p, nm * Cfg::TILE_M + (int)cta_rank * Cfg::BLOCK_M + wq * 32 + lane, nn * Cfg::BLOCK_N);
             }
-            gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row_ok, n_blk, n0, t_row, wbuf, lane, (warp - 4) >> 2, kEpiWarps / 4);
+            gemm_epilogue_rows<Cfg::BLOCK_N, kEpiWarps == 8 ? 2 : 0>(p, row, row_ok, n_blk, n0, t_row, wbuf, lane, (warp - 4) >> 2, kEpiWarps / 4);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

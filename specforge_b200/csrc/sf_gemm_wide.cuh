@@ -35,7 +35,7 @@ struct GemmWideCfg {
     static constexpr int kThreads = 384;
 };
 
-template <int kAMajor, int kBMajor>
+template <int kAMajor, int kBMajor, int kEpiSet>
 __global__ void __launch_bounds__(384, 1)
 gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
     using Cfg = GemmWideCfg<kAMajor, kBMajor>;
@@ -212,7 +212,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (tr && tcount < 32) tr[tcount * 16 + 9 + h * 3] = clock64();
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + h * Cfg::BLOCK_N;
-                gemm_epilogue_rows<Cfg::BLOCK_N>(p, row, row < p.M, n_blk, n0, t_row, wbuf, lane, part, 2);
+                gemm_epilogue_rows<Cfg::BLOCK_N, kEpiSet>(p, row, row < p.M, n_blk, n0, t_row, wbuf, lane, part, 2);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_bar(h), 0);

@@ -12,7 +12,7 @@ void count_launch(int n = 1);
 
 // Tuning / A-B switches.  Each starts from its environment variable (SF_<NAME>, upper case) and can be changed at run time
 // through sf_debug_option() so that two settings can be alternated inside ONE process (boxes of the pool differ by +-8 %).
-enum Opt { OPT_NO_PDL, OPT_LOSS_SIDE, OPT_NO_OVERLAP, OPT_NO_SWIGLU_FUSION, OPT_GEMM_GROUP_M, OPT_GEMM_GROUP_M_MIDK, OPT_GEMM_GROUP_M_WGRAD, OPT_DFLASH_ATTN_TC, OPT_GEMM_STAGES, OPT_NO_TEACHER_FUSION, OPT_NO_LOSS_STATS_FUSION, OPT_GEMM_WIDE, OPT_GEMM_EPI_STAGED, OPT_NO_ROPE_FUSION, OPT_GEMM_EPI8, OPT_COUNT };
+enum Opt { OPT_NO_PDL, OPT_LOSS_SIDE, OPT_NO_OVERLAP, OPT_NO_SWIGLU_FUSION, OPT_GEMM_GROUP_M, OPT_GEMM_GROUP_M_MIDK, OPT_GEMM_GROUP_M_WGRAD, OPT_DFLASH_ATTN_TC, OPT_GEMM_STAGES, OPT_NO_TEACHER_FUSION, OPT_NO_LOSS_STATS_FUSION, OPT_GEMM_WIDE, OPT_GEMM_EPI_STAGED, OPT_NO_ROPE_FUSION, OPT_GEMM_EPI8, OPT_DFLASH_ATTN_WINDOW, OPT_COUNT };
 int opt(Opt o);
 
 struct GemmDesc {

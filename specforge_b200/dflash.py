@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import dataclasses
-from ctypes import POINTER, Structure, c_float, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, Structure, c_float, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -26,7 +26,8 @@ class SfDflashConfig(Structure):
                                        "intermediate", "num_heads", "num_kv_heads", "head_dim", "num_layers", "vocab",
                                        "mask_token_id", "rope_rows")] + [("rms_eps", c_float), ("loss_decay_gamma", c_float),
                                                                           ("grad_of_numerator", c_int32), ("loss_type", c_int32),
-                                                                          ("dpace_alpha", c_float)]
+                                                                          ("dpace_alpha", c_float), ("sliding_window", c_int32),
+                                                                          ("sliding_layers", c_uint32)]
 
 
 class SfDflashFrozen(Structure):
@@ -56,6 +57,24 @@ class DFlashDims:
     loss_decay_gamma: Optional[float] = None
     loss_type: str = "dflash"         # "dflash" | "dpace" | "dpace-cumulative-confidence-only" | "dpace-continuation-value-only"
     dpace_alpha: float = 0.5          # (dflash_family_model.py:29-31,245-279)
+    layer_types: Optional[Tuple[str, ...]] = None   # per layer "full_attention" | "sliding_attention" (modeling/draft/dflash.py:24-68)
+    sliding_window: Optional[int] = None            # window of the sliding layers (dflash_family_model.py:73-84)
+
+    def sliding_layout(self) -> Tuple[int, int]:
+        """(window, bit mask of the sliding layers) — the validation of `resolve_dflash_attention_layout` (dflash.py:38-68)."""
+        if self.layer_types is None:
+            return 0, 0
+        types = tuple(self.layer_types)
+        if len(types) != self.num_layers:
+            raise ValueError(f"DFlash config.layer_types must contain exactly num_hidden_layers={self.num_layers} entries, got {len(types)}")
+        invalid = set(types) - {"full_attention", "sliding_attention"}
+        if invalid:
+            raise ValueError(f"DFlash config.layer_types supports only full_attention and sliding_attention, got {sorted(invalid)}")
+        if "sliding_attention" not in types:
+            return 0, 0
+        if self.sliding_window is None or self.sliding_window <= 0:
+            raise ValueError("DFlash sliding_attention layers require use_sliding_window=true and a positive config.sliding_window")
+        return int(self.sliding_window), sum(1 << i for i, t in enumerate(types) if t == "sliding_attention")
 
 
 LOSS_TYPES = {"dflash": 0, "dpace": 1, "dpace-cumulative-confidence-only": 2, "dpace-continuation-value-only": 3}
@@ -163,7 +182,7 @@ class DFlashEngine:
         return SfDflashConfig(B, S, N, d.block_size, d.hidden_size, d.num_target_feats, d.intermediate_size, d.num_heads,
                               d.num_kv_heads, d.head_dim, d.num_layers, d.vocab_size, d.mask_token_id, rope_rows, d.rms_norm_eps,
                               float(d.loss_decay_gamma) if d.loss_decay_gamma else 0.0, int(getattr(self, "grad_of_numerator", 0)),
-                              LOSS_TYPES[d.loss_type], float(d.dpace_alpha))
+                              LOSS_TYPES[d.loss_type], float(d.dpace_alpha), *d.sliding_layout())
 
     def shape_of(self, name: str) -> Tuple[int, ...]:
         d = self.dims
@@ -285,8 +304,6 @@ def dims_from_config(config) -> DFlashDims:
         nt = get("num_target_layers")
         layer_ids = [nt // 2] if L == 1 else [int(round(1 + i * (nt - 4) / (L - 1))) for i in range(L)]
     types = get("layer_types")
-    if types and any(t != "full_attention" for t in types):
-        raise NotImplementedError("sliding_attention DFlash layers are not implemented on the CUDA path")
     rope_params = get("rope_parameters")
     theta = rope_params["rope_theta"] if rope_params else get("rope_theta", 1000000.0)
     for rp in (get("rope_scaling"), rope_params):       # transformers 5 mirrors rope_parameters into rope_scaling
@@ -296,7 +313,8 @@ def dims_from_config(config) -> DFlashDims:
                       head_dim=get("head_dim") or H // nh, num_layers=L, num_target_feats=len(layer_ids), vocab_size=get("vocab_size"),
                       block_size=get("block_size", 16), mask_token_id=int(dcfg.get("mask_token_id") or 0),
                       rms_norm_eps=get("rms_norm_eps", 1e-6), rope_theta=float(theta),
-                      max_position_embeddings=get("max_position_embeddings", 40960))
+                      max_position_embeddings=get("max_position_embeddings", 40960),
+                      layer_types=tuple(types) if types else None, sliding_window=get("sliding_window"))
 
 
 try:  # the reference's registry needs `config_class` (registry.py:38-41); its DFlash draft uses Qwen3Config

@@ -22,7 +22,8 @@ def test_dflash_step_matches_reference_and_oracle(path):
     dims = DFlashDims(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size, num_heads=c.num_heads, num_kv_heads=c.num_kv_heads,
                       head_dim=c.head_dim, num_layers=c.num_layers, num_target_feats=c.num_target_feats, vocab_size=c.vocab_size,
                       block_size=c.block_size, mask_token_id=c.mask_token_id, rms_norm_eps=c.rms_norm_eps, rope_theta=c.rope_theta,
-                      max_position_embeddings=1024, loss_decay_gamma=c.loss_decay_gamma, loss_type=c.loss_type, dpace_alpha=c.dpace_alpha)
+                      max_position_embeddings=1024, loss_decay_gamma=c.loss_decay_gamma, loss_type=c.loss_type, dpace_alpha=c.dpace_alpha,
+                      layer_types=c.layer_types, sliding_window=c.sliding_window)
     B, S = g["batch"]["input_ids"].shape
     N = g["anchors"].shape[1]
     eng = DFlashEngine(dims, batch=B, seq_len=S, num_blocks=N)

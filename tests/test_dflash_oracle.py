@@ -223,3 +223,62 @@ def test_tensor_core_tiling_reproduces_the_dflash_mask(g, bs):
                     n_lo = n + 1
             attends = [n for n in range(N) if keep[b, n] and bool(want[b, n * bs, k0:min(k0 + 128, S)].any())]
             assert attends == list(range(n_lo, n_hi))
+
+
+# ------------------------------------------------------------------------------------------------ sliding-window layers
+def test_sliding_mask_semantics():
+    """dflash_family_model.py:73-84 — slot o of a block anchored at a sees context keys [a + o - (W - 1), a) and own slots <= o."""
+    anchors = torch.tensor([[5, 9]])
+    keep = torch.tensor([[True, True]])
+    S, bs, W = 12, 4, 3
+    m = D.dflash_mask(anchors, keep, S, bs, W)[0]                   # [N*bs, S + N*bs]
+    for n, a in enumerate((5, 9)):
+        for o in range(bs):
+            row = m[n * bs + o]
+            ctx = [k for k in range(S) if row[k]]
+            assert ctx == [k for k in range(max(0, a + o - (W - 1)), a)], (n, o, ctx)
+            own = [k for k in range(bs) if row[S + n * bs + k]]
+            assert own == list(range(o + 1)), (n, o, own)
+            other = (1 - n) * bs
+            assert not row[S + other:S + other + bs].any()
+    full = D.dflash_mask(anchors, keep, S, bs)[0]
+    assert (m & ~full).sum() == 0 and m.sum() < full.sum()          # a sliding mask only removes keys
+    assert torch.equal(D.dflash_mask(anchors, keep, S, bs, S + bs + 1)[0][:, :S], full[:, :S])   # a window wider than the context: same context keys
+
+
+def test_sliding_mask_equals_the_reference_builder():
+    import os
+    import sys
+    if not os.path.isdir("/root/reference/specforge"):
+        pytest.skip("reference checkout not present")
+    sys.path.insert(0, "/root/reference")
+    os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+    from specforge.algorithms.common.dflash_family_model import create_dflash_sdpa_mask
+    gen = torch.Generator().manual_seed(3)
+    lm = (torch.rand(3, 70, generator=gen) > 0.2).float()
+    lm[2, 6:] = 0
+    anchors, keep = D.sample_anchor_positions(lm, 9, generator=gen)
+    for W in (None, 1, 5, 33, 200):
+        want = create_dflash_sdpa_mask(anchors, keep, 70, 8, torch.device("cpu"), sliding_window=W)[:, 0]
+        assert torch.equal(D.dflash_mask(anchors, keep, 70, 8, W), want), W
+
+
+def test_sliding_layout_validation_and_the_checked_in_hybrid_config():
+    """modeling/draft/dflash.py:38-68 and configs/qwen3.6-27b-dflash.json (4 sliding + 1 full layer, window 2048)."""
+    from specforge_b200.dflash import DFlashDims, dims_from_config
+    cfg = {"hidden_size": 5120, "intermediate_size": 17408, "num_attention_heads": 32, "num_key_value_heads": 8, "head_dim": 128,
+           "num_hidden_layers": 5, "num_target_layers": 64, "vocab_size": 248320, "block_size": 16, "rope_theta": 10000000,
+           "dflash_config": {"mask_token_id": 248070, "target_layer_ids": [1, 16, 31, 46, 61]}, "sliding_window": 2048,
+           "layer_types": ["sliding_attention"] * 4 + ["full_attention"], "use_sliding_window": True, "rope_scaling": None}
+    dims = dims_from_config(cfg)
+    assert dims.sliding_layout() == (2048, 0b01111)
+    base = dict(hidden_size=64, intermediate_size=128, num_heads=4, num_kv_heads=2, head_dim=16, num_layers=2, num_target_feats=2, vocab_size=256)
+    assert DFlashDims(**base).sliding_layout() == (0, 0)
+    assert DFlashDims(**base, layer_types=("full_attention", "full_attention"), sliding_window=7).sliding_layout() == (0, 0)
+    assert DFlashDims(**base, layer_types=("full_attention", "sliding_attention"), sliding_window=7).sliding_layout() == (7, 0b10)
+    for types, w in ((("full_attention",), None), (("full_attention", "unknown"), None), (("sliding_attention", "full_attention"), None),
+                     (("sliding_attention", "full_attention"), 0), (("sliding_attention", "full_attention"), -1)):
+        with pytest.raises(ValueError):
+            DFlashDims(**base, layer_types=types, sliding_window=w).sliding_layout()
+        with pytest.raises(ValueError):
+            D.layer_windows(D.DFlashConfig(num_layers=2, layer_types=types, sliding_window=w))

@@ -14,13 +14,13 @@ from oracle import dflash_oracle as D                        # noqa: E402   (che
 from specforge_b200._lib import check, lib                   # noqa: E402
 
 
-def dense_reference(q, kn, vn, kc, vc, anchors, keep, B, S, N, bs, nh, nkv, d, dout):
+def dense_reference(q, kn, vn, kc, vc, anchors, keep, B, S, N, bs, nh, nkv, d, dout, window=None):
     """fp32 autograd reference on the GPU: scores over [context ; noise] keys with the oracle's boolean mask."""
     g = nh // nkv
     leaves = [t.float().detach().clone().requires_grad_(True) for t in (q, kn, vn, kc, vc)]
     qf, knf, vnf, kcf, vcf = leaves
     Q = N * bs
-    mask = D.dflash_mask(anchors.cpu().long(), keep.cpu().bool(), S, bs).to(q.device)                     # [B, Q, S+Q]
+    mask = D.dflash_mask(anchors.cpu().long(), keep.cpu().bool(), S, bs, window).to(q.device)                     # [B, Q, S+Q]
     qh = qf.view(B, Q, nh, d).transpose(1, 2)
     k = torch.cat([kcf.view(B, S, nkv, d), knf.view(B, Q, nkv, d)], dim=1).transpose(1, 2).repeat_interleave(g, dim=1)
     v = torch.cat([vcf.view(B, S, nkv, d), vnf.view(B, Q, nkv, d)], dim=1).transpose(1, 2).repeat_interleave(g, dim=1)
@@ -57,8 +57,11 @@ def main():
     ap.add_argument("--d", type=int, default=128); ap.add_argument("--g", type=int, default=4); ap.add_argument("--nkv", type=int, default=2)
     ap.add_argument("--bs", type=int, default=16); ap.add_argument("--S", type=int, default=300); ap.add_argument("--N", type=int, default=9)
     ap.add_argument("--B", type=int, default=2); ap.add_argument("--impl", type=int, nargs="+", default=[0, 1])
+    ap.add_argument("--window", type=int, default=0, help="sliding-window layer: keys [a + o - (W - 1), a) + own slots <= o (0 = full)")
     a = ap.parse_args()
     L = lib()
+    L.sf_debug_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    check(L.sf_debug_option(b"dflash_attn_window", a.window), "sf_debug_option")
     for f in (L.sf_dflash_attention_fwd, L.sf_dflash_attention_bwd):
         f.restype = ctypes.c_int
     dev = torch.device("cuda", 0)
@@ -73,7 +76,7 @@ def main():
     mk = lambda rows, cols: (torch.randn(rows, cols, generator=gen) * 0.7).bfloat16().to(dev)
     q, kn, vn, kc, vc, dout = mk(Mq, nh * d), mk(Mq, nkv * d), mk(Mq, nkv * d), mk(Mc, nkv * d), mk(Mc, nkv * d), mk(Mq, nh * d)
     anc, kp = anchors.to(dev, torch.int32).contiguous(), keep.to(dev).to(torch.uint8).contiguous()
-    ref_o, ref_lse, ref_g = dense_reference(q, kn, vn, kc, vc, anc, kp, B, S, N, bs, nh, nkv, d, dout)
+    ref_o, ref_lse, ref_g = dense_reference(q, kn, vn, kc, vc, anc, kp, B, S, N, bs, nh, nkv, d, dout, a.window or None)
     kept_rows = keep.repeat_interleave(bs, dim=1).reshape(-1).to(dev)
     names = ["dq", "dkn", "dvn", "dkc", "dvc"]
     for impl in a.impl:
@@ -83,7 +86,7 @@ def main():
             print(f"impl {impl}: {exc}")
             continue
         cos = lambda x, y: torch.nn.functional.cosine_similarity(x.float().flatten(), y.float().flatten(), dim=0).item()
-        print(f"impl {impl}: out max|err| {float((out.float() - ref_o).abs().max()):.3e} cos {cos(out, ref_o):.6f}   "
+        print(f"window {a.window} impl {impl}: out max|err| {float((out.float() - ref_o).abs().max()):.3e} cos {cos(out, ref_o):.6f}   "
               f"lse max|err| (kept rows) {float((lse - ref_lse)[kept_rows].abs().max()):.3e}")
         for n, g_, r_ in zip(names, grads, ref_g):
             print(f"          {n:4s} max|err| {float((g_.float() - r_).abs().max()):.3e} (ref max {float(r_.abs().max()):.3e}) cos {cos(g_, r_):.6f}")
