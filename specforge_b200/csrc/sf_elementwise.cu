@@ -92,6 +92,13 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
 // gather mode (ids != null): x rows come from the frozen embedding table, only dw is produced.
 // One block per row (looping), kChunks 16-byte chunks per thread, ONE block reduction per row
 // (sum x^2 and sum g*x together), so several blocks stay resident per SM and hide the HBM latency.
+constexpr int kRmsStages = 3;
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int kChunks, int kThreads>
 __global__ void __launch_bounds__(kThreads, kChunks == 1 ? 1024 / kThreads : 1)   // 64 registers: two 512-thread blocks per SM
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64_t* __restrict__ ids, int S, int shift,
@@ -113,31 +120,46 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
         }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Software pipeline over the rows of this block: the 16-byte loads of row r + gridDim.x (x and dy) and row r's own residual-
-    // gradient addends are issued before row r's block reduction, so a block always has a row of loads in flight — with one row at
-    // a time the two dependent round trips per row (x/dy, then the addends) left the kernel at ~0.45 of HBM bandwidth.
-    uint4 xn[kChunks], dn[kChunks];
+    // Row pipeline: every thread streams ITS OWN 16-byte chunks of the next kRmsStages - 1 rows (x, dy and the residual-gradient
+    // addends) into private shared-memory slots with cp.async — no registers held for loads in flight, no cross-thread
+    // synchronisation (a thread only reads back what it copied).  One row at a time left two dependent round trips per row and
+    // ~0.45 of HBM bandwidth; register prefetch of one row reached 0.50 (profiles/r02_ncu_step_nongemm.csv).
+    extern __shared__ uint4 rms_stage[];                 // [kRmsStages][4 streams][kChunks][kThreads]
     const bool has_add1 = dx && add1, has_add2 = dx && add2;
-    auto issue = [&](int64_t r) {
-        const __nv_bfloat16* xr;
-        if (ids) {
-            const int64_t b = r / S, s = r % S;
-            const int64_t tok = (s + shift < S) ? ids[b * S + s + shift] : 0;
-            xr = x + tok * ldx;
-        } else {
-            xr = x + r * ldx;
-        }
+    auto slot = [&](int stage, int stream, int c) { return rms_stage + ((stage * 4 + stream) * kChunks + c) * kThreads + threadIdx.x; };
+    auto issue = [&](int64_t r, int stage) {
+        if (r < M) {
+            const __nv_bfloat16* xr;
+            if (ids) {
+                const int64_t b = r / S, s = r % S;
+                const int64_t tok = (s + shift < S) ? ids[b * S + s + shift] : 0;
+                xr = x + tok * ldx;
+            } else {
+                xr = x + r * ldx;
+            }
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-            const int ch = threadIdx.x + c * kThreads;
-            if (ch < nchunks) {
-                xn[c] = __ldg(reinterpret_cast<const uint4*>(xr) + ch);
-                dn[c] = __ldg(reinterpret_cast<const uint4*>(dy + r * lddy) + ch);
+            for (int c = 0; c < kChunks; ++c) {
+                const int ch = threadIdx.x + c * kThreads;
+                if (ch < nchunks) {
+                    cp_async_16(slot(stage, 0, c), reinterpret_cast<const uint4*>(xr) + ch);
+                    cp_async_16(slot(stage, 1, c), reinterpret_cast<const uint4*>(dy + r * lddy) + ch);
+                    if (has_add1) cp_async_16(slot(stage, 2, c), reinterpret_cast<const uint4*>(add1 + r * (int64_t)H) + ch);
+                    if (has_add2) cp_async_16(slot(stage, 3, c), reinterpret_cast<const uint4*>(add2 + r * (int64_t)H) + ch);
+                }
             }
         }
+        cp_async_commit();                               // one group per row, empty past the end: the wait below stays uniform
     };
-    if ((int64_t)blockIdx.x < M) issue(blockIdx.x);
+#pragma unroll
+    for (int s = 0; s < kRmsStages - 1; ++s) issue(blockIdx.x + (int64_t)s * gridDim.x, s);
+    int stage = 0;
     for (int64_t r = blockIdx.x; r < M; r += gridDim.x) {
+        {
+            int nstage = stage + kRmsStages - 1;
+            if (nstage >= kRmsStages) nstage -= kRmsStages;
+            issue(r + (int64_t)(kRmsStages - 1) * gridDim.x, nstage);     // the slot row r - gridDim.x used: consumed last iteration
+        }
+        cp_async_wait<kRmsStages - 1>();                 // row r's group has landed
         float xv[kChunks][8], gv[kChunks][8];
         uint4 a1c[kChunks], a2c[kChunks];
         float ss = 0.f, gx = 0.f;
@@ -145,17 +167,17 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int64
         for (int c = 0; c < kChunks; ++c) {
             const int ch = threadIdx.x + c * kThreads;
             if (ch < nchunks) {
-                if (has_add1) a1c[c] = __ldg(reinterpret_cast<const uint4*>(add1 + r * (int64_t)H) + ch);   // consumed after the reduction
-                if (has_add2) a2c[c] = __ldg(reinterpret_cast<const uint4*>(add2 + r * (int64_t)H) + ch);
-                bf16x8 t; t.u = xn[c];
+                bf16x8 t; t.u = *slot(stage, 0, c);
                 t.unpack(xv[c]);
-                bf16x8 d; d.u = dn[c];
+                bf16x8 d; d.u = *slot(stage, 1, c);
                 d.unpack(gv[c]);
+                if (has_add1) a1c[c] = *slot(stage, 2, c);
+                if (has_add2) a2c[c] = *slot(stage, 3, c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { ss += xv[c][i] * xv[c][i]; gx += gv[c][i] * wf[c][i] * xv[c][i]; }
             }
         }
-        if (r + gridDim.x < M) issue(r + gridDim.x);
+        if (++stage == kRmsStages) stage = 0;
         ss = warp_sum(ss); gx = warp_sum(gx);
         __syncthreads();
         if (lane == 0) red[warp] = make_float2(ss, gx);
@@ -400,17 +422,24 @@ int rmsnorm_bwd(const void* x, int64_t ldx, const int64_t* ids, int S, int shift
     const int nch = H / 8;
 #define SF_RMS_BWD(CH, TH, BPS)                                                                                        \
     do {                                                                                                               \
-        int blocks = 148 * BPS;                                                                                        \
+        int blocks = 148 * BPS;                  /* one resident wave: BPS blocks per SM fit (registers and staging) */  \
         if (blocks > M) blocks = (int)M;                                                                               \
         launched_blocks = blocks;                                                                                      \
-        rmsnorm_bwd_kernel<CH, TH><<<blocks, TH, 0, st>>>((const __nv_bfloat16*)x, ldx, ids, S, shift,                 \
+        const int smem = kRmsStages * 4 * CH * TH * 16;                                                                \
+        static bool attr_set = false;                                                                                  \
+        if (!attr_set) {                                                                                               \
+            cudaError_t e = cudaFuncSetAttribute(rmsnorm_bwd_kernel<CH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+            if (e != cudaSuccess) return set_error(-22, "rmsnorm_bwd smem attr: %s", cudaGetErrorString(e));           \
+            attr_set = true;                                                                                           \
+        }                                                                                                              \
+        rmsnorm_bwd_kernel<CH, TH><<<blocks, TH, smem, st>>>((const __nv_bfloat16*)x, ldx, ids, S, shift,              \
             (const __nv_bfloat16*)w, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)add1,                        \
             (const __nv_bfloat16*)add2, (__nv_bfloat16*)dx, partial_ws, M, H, eps);                                    \
     } while (0)
-    if (nch <= 128) SF_RMS_BWD(1, 128, 12);
-    else if (nch <= 256) SF_RMS_BWD(1, 256, 8);
-    else if (nch <= 512) SF_RMS_BWD(1, 512, 4);
-    else SF_RMS_BWD(2, 512, 3);
+    if (nch <= 128) SF_RMS_BWD(1, 128, 8);
+    else if (nch <= 256) SF_RMS_BWD(1, 256, 4);
+    else if (nch <= 512) SF_RMS_BWD(1, 512, 2);
+    else SF_RMS_BWD(2, 512, 1);
 #undef SF_RMS_BWD
     SF_CUDA_CHECK_LAUNCH("rmsnorm_bwd");
     colsum_partials_kernel<<<(H + 31) / 32, 256, 0, st>>>(partial_ws, launched_blocks, H, dw);

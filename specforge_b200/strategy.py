@@ -116,9 +116,10 @@ class B200Eagle3TrainStrategy:
         loss = _Eagle3StepFn.apply(flat, self, batch.tensors, need_grad)
         m = eng.metrics.clone()  # [T, 8] on device; slicing below creates views, no host sync
         T = eng.T
+        acc = m[:, 1] / m[:, 2]    # one launch for all T positions
         metrics = {
             "plosses": [m[j, 0] for j in range(T)],
-            "acces": [m[j, 1] / m[j, 2] for j in range(T)],
+            "acces": [acc[j] for j in range(T)],
             "acceptance_rates": [m[j, 3] for j in range(T)],
             "acc_corrects": [m[j, 1] for j in range(T)],
             "acc_denoms": [m[j, 2] for j in range(T)],
