@@ -257,22 +257,15 @@ __global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
     MaxIdx mi{-INFINITY, 0x7fffffff};
     float d = 0.f;
     if (p.stats) {
-        if (warp == 0) {
+        // every thread takes (at most) one of the row's partial blocks; the block reduction below merges them — a single warp
+        // walking the 125-250 partials serially cost ~1.5 k cycles per row before the other 15 warps could start pass B
+        for (int nb = threadIdx.x; nb < p.stats_nb; nb += 512) {
             const size_t plane = (size_t)p.stats_nb * p.M;
-            for (int nb = lane; nb < p.stats_nb; nb += 32) {          // ascending n-blocks per lane; a row's partials are contiguous
-                const float* sp = p.stats + (size_t)r * p.stats_nb + nb;
-                const float pm = __ldg(sp), pd = __ldg(sp + plane);
-                if (pm > mi.v) { d = d * __expf(mi.v - pm) + pd; mi.v = pm; mi.i = __float_as_int(__ldg(sp + 2 * plane)); }
-                else if (pm > -INFINITY) d += pd * __expf(pm - mi.v);
-            }
-            const float my_m = mi.v;
-            mi = warp_argmax(mi);                                     // equal maxima: the smaller index wins
-            d = warp_sum(my_m == -INFINITY ? 0.f : d * __expf(my_m - mi.v));
-            if (lane == 0) { redv[0] = mi.v; redi[0] = mi.i; redd[0] = d; }
+            const float* sp = p.stats + (size_t)r * p.stats_nb + nb;                // a row's partials are contiguous
+            const float pm = __ldg(sp), pd = __ldg(sp + plane);
+            if (pm > mi.v) { d = d * __expf(mi.v - pm) + pd; mi.v = pm; mi.i = __float_as_int(__ldg(sp + 2 * plane)); }
+            else if (pm > -INFINITY) d += pd * __expf(pm - mi.v);
         }
-        __syncthreads();
-        mi.v = redv[0]; mi.i = redi[0]; d = redd[0];
-        __syncthreads();   // red* are reused below
     } else {
 #pragma unroll 4
     for (int c = threadIdx.x; c < nch; c += 512) {
@@ -286,7 +279,8 @@ __global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) d += __expf(f[e] - mi.v);
     }
-    {   // one combined block reduction of (max, argmax, sum-exp)
+    }
+    {   // one combined block reduction of (max, argmax, sum-exp); equal maxima: the smaller column index wins
         const float my_m = mi.v;
         MaxIdx wm = warp_argmax(mi);
         float wd = warp_sum(my_m == -INFINITY ? 0.f : d * __expf(my_m - wm.v));
@@ -297,7 +291,6 @@ __global__ void __launch_bounds__(512, 3) loss_kernel(LossParams p) {
         mi = warp_argmax(t);
         d = warp_sum(t.v == -INFINITY ? 0.f : td * __expf(t.v - mi.v));
         __syncthreads();   // red* are reused below
-    }
     }
     const float m = mi.v;
     const float inv_d = 1.f / d;
