@@ -460,6 +460,19 @@ def run_ours(args):
 
     ms_e2e, last_loss = timed_e2e(args.steps)
     e2e = world * B / (ms_e2e / args.steps / 1e3)
+    if args.e2e_variants and rank == 0:
+        # diagnostic: which part of the end-to-end loop costs what (device batch + loss read; host feed without the read)
+        ms_b, _ = timed(dev_batch, True, args.steps)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for batch in DevicePrefetcher((host_batch for _ in range(args.steps)), device=dev):
+            step(batch, False)
+        e1.record()
+        barrier()
+        print(json.dumps({"e2e_variants_ms_per_step": {"resident_no_read": ms_total / args.steps, "resident_loss_read": ms_b / args.steps,
+                                                       "host_feed_no_read": e0.elapsed_time(e1) / args.steps, "host_feed_loss_read": ms_e2e / args.steps}}),
+              file=sys.stderr, flush=True)
 
     e2e_shards = None
     if args.feed_shards:
@@ -692,6 +705,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--ab", action="append", default=None, help="diagnostic: NAME=V0,V1[,..] alternates sf_debug_option(NAME) step by step, prints ms/step per value to stderr")
     ap.add_argument("--ab-rounds", type=int, default=10)
+    ap.add_argument("--e2e-variants", action="store_true", help="diagnostic: time the end-to-end loop with / without the host feed and the loss read")
     ap.add_argument("--feed-shards", action="store_true", help="also measure e2e fed from an SFPK shard on local disk")
     ap.add_argument("--timeline", default=None, help="also write a CUPTI kernel-timeline summary of 2 steps to this path")
     ap.add_argument("--steps", type=int, default=10)
