@@ -26,12 +26,26 @@ def wait_until_copied(host_tensor: torch.Tensor) -> None:
         host_tensor._sf_copy_event = None
 
 
+_FEED_STREAMS = {}
+
+
+def feed_stream(device: torch.device) -> "torch.cuda.Stream":
+    """ONE copy stream per device for every prefetcher of the process.  The caching allocator keeps a pool per stream: a prefetcher
+    that made its own stream (one per epoch, say) had to cudaMalloc its staging tensors again — half a gigabyte per batch at the
+    BASELINE shapes — and the freed blocks of the previous stream's pool could not serve it."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _FEED_STREAMS.get(idx)
+    if st is None:
+        st = _FEED_STREAMS[idx] = torch.cuda.Stream(device=device)
+    return st
+
+
 class DevicePrefetcher:
     def __init__(self, batches: Iterable, device: Optional[torch.device] = None, depth: int = 2):
         self.batches = batches
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.depth = max(1, depth)
-        self.stream = torch.cuda.Stream(device=self.device)
+        self.stream = feed_stream(self.device)
 
     def _stage(self, batch):
         with torch.cuda.stream(self.stream):
