@@ -671,6 +671,8 @@ def run_dflash(args):
     for b in DevicePrefetcher((mk(host_t) for _ in range(3)), device=dev):
         step(b, True)
     ms_e2e, last_loss = timed(DevicePrefetcher((mk(host_t) for _ in range(args.steps)), device=dev), True)
+    if args.timeline and rank == 0:
+        kernel_timeline(lambda: step(mk(dev_t), False), args.timeline)
     sustained, burst, peak_src = peaks()
     A, KV, I, Lr, Mq, Mc = 4096, 1024, 12288, 5, Bd * Nd * bs, Bd * Sd
     fwd = 2 * Mc * F * H * H + Lr * (2 * Mq * H * (A + 2 * KV) + 2 * Mc * H * 2 * KV + 2 * Mq * A * H + 6 * Mq * H * I) + 2 * Mq * H * V

@@ -545,11 +545,14 @@ __global__ void __launch_bounds__(256) df_delta_kernel(const __nv_bfloat16* __re
 }
 
 // dK / dV of a block's own bs noise keys: CTA = (block, kv head, sequence), R = g*bs query rows; P and dS of the own tile are
-// recomputed from lse / delta (fp32, CUDA cores: R x bs x d work).
+// recomputed from lse / delta (fp32, CUDA cores: R x bs x d work).  16-byte global loads, fp32 shared-memory tiles with a row
+// stride of d + 4 floats (float4-aligned, conflict-free for the access patterns below), float4 inner products: the first version
+// (element-wise 2-byte loads, scalar shared-memory reads, two LDS per FMA) took 3.1 ms per launch at the BASELINE shape — 5 % of
+// the DFlash step for 16 GFLOP of work.
 __global__ void __launch_bounds__(256) df_bwd_own_kernel(AttnArgs a) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int n = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
-    const int d = a.d, bs = a.bs, g = a.nh / a.nkv, R = g * bs, ds = d + 1, ts = bs + 1;
+    const int d = a.d, bs = a.bs, g = a.nh / a.nkv, R = g * bs, ds = d + 4, ts = bs + 1, d8 = d / 8, d4 = d / 4;
     float* Qs = sm;                 // [R][ds]
     float* Gs = Qs + R * ds;        // [R][ds]
     float* Ks = Gs + R * ds;        // [bs][ds]
@@ -559,44 +562,97 @@ __global__ void __launch_bounds__(256) df_bwd_own_kernel(AttnArgs a) {
     const int t = threadIdx.x;
     const int64_t qrow0 = ((int64_t)b * a.N + n) * bs;
     if (!a.keep[b * a.N + n]) {
-        for (int i = t; i < bs * d; i += 256) {
-            const int k = i / d, c = i % d;
-            a.dkn[(qrow0 + k) * a.lddkn + kvh * d + c] = __float2bfloat16_rn(0.f);
-            a.dvn[(qrow0 + k) * a.lddvn + kvh * d + c] = __float2bfloat16_rn(0.f);
+        for (int i = t; i < bs * d8; i += 256) {
+            const int k = i / d8, c8 = i % d8;
+            reinterpret_cast<uint4*>(a.dkn + (qrow0 + k) * a.lddkn + kvh * d)[c8] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4*>(a.dvn + (qrow0 + k) * a.lddvn + kvh * d)[c8] = make_uint4(0, 0, 0, 0);
         }
         return;
     }
-    for (int i = t; i < R * d; i += 256) {
-        const int rr = i / d, c = i % d;
+    auto put8 = [](float* dst, uint4 raw) {
+        const __nv_bfloat162* e = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const float2 f0 = __bfloat1622float2(e[0]), f1 = __bfloat1622float2(e[1]), f2 = __bfloat1622float2(e[2]), f3 = __bfloat1622float2(e[3]);
+        reinterpret_cast<float4*>(dst)[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+    };
+    for (int i = t; i < R * d8; i += 256) {
+        const int rr = i / d8, c8 = i % d8;
         const int64_t row = qrow0 + rr % bs;
         const int hh = kvh * g + rr / bs;
-        Qs[rr * ds + c] = __bfloat162float(a.q[row * a.ldq + hh * d + c]);
-        Gs[rr * ds + c] = __bfloat162float(a.dout[row * a.lddo + hh * d + c]);
+        put8(Qs + rr * ds + c8 * 8, __ldg(reinterpret_cast<const uint4*>(a.q + row * a.ldq + hh * d) + c8));
+        put8(Gs + rr * ds + c8 * 8, __ldg(reinterpret_cast<const uint4*>(a.dout + row * a.lddo + hh * d) + c8));
     }
-    for (int i = t; i < bs * d; i += 256) {
-        const int k = i / d, c = i % d;
-        Ks[k * ds + c] = __bfloat162float(a.kn[(qrow0 + k) * a.ldkn + kvh * d + c]);
-        Vs[k * ds + c] = __bfloat162float(a.vn[(qrow0 + k) * a.ldvn + kvh * d + c]);
-    }
-    __syncthreads();
-    for (int i = t; i < R * bs; i += 256) {
-        const int rr = i / bs, k = i % bs;
-        const int64_t orow = qrow0 + rr % bs;
-        const int head = kvh * g + rr / bs;
-        float s = 0.f, dp = 0.f;
-        for (int c = 0; c < d; ++c) { s += Qs[rr * ds + c] * Ks[k * ds + c]; dp += Gs[rr * ds + c] * Vs[k * ds + c]; }
-        const bool allowed = a.window == 0 || k <= rr % bs;          // sliding-window layer: own slots <= the query's slot
-        const float pr = allowed ? __expf(s * a.scale - a.lse[orow * a.nh + head]) : 0.f;
-        Ps[rr * ts + k] = pr;
-        Ds[rr * ts + k] = pr * (dp - a.delta[orow * a.nh + head]) * a.scale;
+    for (int i = t; i < bs * d8; i += 256) {
+        const int k = i / d8, c8 = i % d8;
+        put8(Ks + k * ds + c8 * 8, __ldg(reinterpret_cast<const uint4*>(a.kn + (qrow0 + k) * a.ldkn + kvh * d) + c8));
+        put8(Vs + k * ds + c8 * 8, __ldg(reinterpret_cast<const uint4*>(a.vn + (qrow0 + k) * a.ldvn + kvh * d) + c8));
     }
     __syncthreads();
-    for (int i = t; i < bs * d; i += 256) {
-        const int k = i / d, c = i % d;
-        float dk = 0.f, dv = 0.f;
-        for (int rr = 0; rr < R; ++rr) { dk += Ds[rr * ts + k] * Qs[rr * ds + c]; dv += Ps[rr * ts + k] * Gs[rr * ds + c]; }
-        a.dkn[(qrow0 + k) * a.lddkn + kvh * d + c] = __float2bfloat16_rn(dk);
-        a.dvn[(qrow0 + k) * a.lddvn + kvh * d + c] = __float2bfloat16_rn(dv);
+    // P and dS of the own tile.  The kernel is shared-memory-bandwidth bound (2 MB of tile reads per CTA with one pair per thread),
+    // so every thread computes a 2 x 2 block of (query row, key) pairs from 8 float4 loads per 4 columns.  Tile order: the 4 lanes
+    // of a quad take 4 key pairs of the same row pair (rows broadcast, keys 8 banks apart), the quads walk the row pairs.
+    const int nrt = R / 2;
+    for (int tile = t; tile < nrt * (bs / 2); tile += 256) {
+        const int kt = (tile & 3) + 4 * (tile / (4 * nrt)), rt = (tile >> 2) % nrt;
+        const int rr0 = rt * 2, k0 = kt * 2;
+        float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, dp[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        for (int c = 0; c < d4; ++c) {
+            float4 qa[2], ga[2], ka[2], va[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                qa[u] = reinterpret_cast<const float4*>(Qs + (rr0 + u) * ds)[c];
+                ga[u] = reinterpret_cast<const float4*>(Gs + (rr0 + u) * ds)[c];
+                ka[u] = reinterpret_cast<const float4*>(Ks + (k0 + u) * ds)[c];
+                va[u] = reinterpret_cast<const float4*>(Vs + (k0 + u) * ds)[c];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    s[u][v] += qa[u].x * ka[v].x + qa[u].y * ka[v].y + qa[u].z * ka[v].z + qa[u].w * ka[v].w;
+                    dp[u][v] += ga[u].x * va[v].x + ga[u].y * va[v].y + ga[u].z * va[v].z + ga[u].w * va[v].w;
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rr = rr0 + u;
+            const int64_t orow = qrow0 + rr % bs;
+            const int head = kvh * g + rr / bs;
+            const float lse = a.lse[orow * a.nh + head], del = a.delta[orow * a.nh + head];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int k = k0 + v;
+                const bool allowed = a.window == 0 || k <= rr % bs;      // sliding-window layer: own slots <= the query's slot
+                const float pr = allowed ? __expf(s[u][v] * a.scale - lse) : 0.f;
+                Ps[rr * ts + k] = pr;
+                Ds[rr * ts + k] = pr * (dp[u][v] - del) * a.scale;
+            }
+        }
+    }
+    __syncthreads();
+    // dK[k, c..c+3] = sum_rr dS[rr, k] Q[rr, c..c+3], dV likewise from P and dO: two keys and four columns per thread and pass
+    for (int i = t; i < (bs / 2) * d4; i += 256) {
+        const int k0 = (i / d4) * 2, c4 = i % d4;
+        float4 dk[2], dv[2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) { dk[v] = make_float4(0.f, 0.f, 0.f, 0.f); dv[v] = dk[v]; }
+        for (int rr = 0; rr < R; ++rr) {
+            const float4 qa = reinterpret_cast<const float4*>(Qs + rr * ds)[c4], ga = reinterpret_cast<const float4*>(Gs + rr * ds)[c4];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const float dsv = Ds[rr * ts + k0 + v], pv = Ps[rr * ts + k0 + v];
+                dk[v].x += dsv * qa.x; dk[v].y += dsv * qa.y; dk[v].z += dsv * qa.z; dk[v].w += dsv * qa.w;
+                dv[v].x += pv * ga.x; dv[v].y += pv * ga.y; dv[v].z += pv * ga.z; dv[v].w += pv * ga.w;
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            uint2 ok, ov;
+            ok.x = pack_bf16x2(dk[v].x, dk[v].y); ok.y = pack_bf16x2(dk[v].z, dk[v].w);
+            ov.x = pack_bf16x2(dv[v].x, dv[v].y); ov.y = pack_bf16x2(dv[v].z, dv[v].w);
+            reinterpret_cast<uint2*>(a.dkn + (qrow0 + k0 + v) * a.lddkn + kvh * d)[c4] = ok;
+            reinterpret_cast<uint2*>(a.dvn + (qrow0 + k0 + v) * a.lddvn + kvh * d)[c4] = ov;
+        }
     }
 }
 
@@ -636,7 +692,7 @@ static int bwd_tc_t(const AttnArgs& a, cudaStream_t st) {
         SF_CUDA_CHECK_LAUNCH("dflash bwd_dq_tc");
     }
     {
-        const int smem = (int)((2 * R * (D + 1) + 2 * a.bs * (D + 1) + 2 * R * (a.bs + 1)) * 4);
+        const int smem = (int)((2 * R * (D + 4) + 2 * a.bs * (D + 4) + 2 * R * (a.bs + 1)) * 4);
         // one high-water mark for both head dims: the kernel is not a template, so a per-instantiation mark let the d = 64 call
         // lower the limit a d = 128 call had raised ("invalid argument" on the next d = 128 launch)
         if (smem > g_own_smem_set) {

@@ -156,6 +156,127 @@ headnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int n
         partial[(int64_t)blockIdx.x * d + i] = t;
     }
 }
+// ---- the same two kernels for head dims that are a multiple of 32 (every real config: d = 64 / 128): lane l owns the EPL = d / 32
+// contiguous elements [EPL*l, EPL*l + EPL) — one vector load per tensor per item instead of EPL two-byte loads, values stay in
+// registers across the passes, and the rotate_half partner (i +- d/2) is always lane ^ 16.  Same formulas and rounding points.
+template <int EPL> struct BfVec;
+template <> struct BfVec<1> { using T = uint16_t; };
+template <> struct BfVec<2> { using T = uint32_t; };
+template <> struct BfVec<4> { using T = uint2; };
+template <> struct BfVec<8> { using T = uint4; };
+template <int EPL>
+__device__ __forceinline__ void ld_bf(const __nv_bfloat16* p, float (&o)[EPL]) {
+    typename BfVec<EPL>::T raw = __ldg(reinterpret_cast<const typename BfVec<EPL>::T*>(p));
+    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) o[i] = __bfloat162float(e[i]);
+}
+template <int EPL>
+__device__ __forceinline__ void st_bf(__nv_bfloat16* p, const float (&v)[EPL]) {
+    typename BfVec<EPL>::T raw;
+    __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&raw);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) e[i] = __float2bfloat16_rn(v[i]);
+    *reinterpret_cast<typename BfVec<EPL>::T*>(p) = raw;
+}
+
+template <int EPL>
+__global__ void __launch_bounds__(256)
+headnorm_rope_fwd_vec_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int n_heads, const __nv_bfloat16* __restrict__ w,
+                             const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
+                             const int32_t* __restrict__ pos, int S, float eps, __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t M) {
+    constexpr int d = EPL * 32;
+    const int64_t item = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (item >= M * n_heads) return;
+    const int h = (int)(item % n_heads);
+    const int64_t r = item / n_heads;
+    const int p = pos ? pos[r] : (int)(r % S);
+    float xv[EPL], wv[EPL], cv[EPL], sv[EPL], y[EPL], o[EPL];
+    ld_bf<EPL>(x + r * ldx + h * d + lane * EPL, xv);
+    ld_bf<EPL>(w + lane * EPL, wv);
+    ld_bf<EPL>(cos_t + (int64_t)p * d + lane * EPL, cv);
+    ld_bf<EPL>(sin_t + (int64_t)p * d + lane * EPL, sv);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) ss += xv[i] * xv[i];
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)d + eps);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        y[i] = rbf(wv[i] * rbf(xv[i] * rstd));
+        const float yj = __shfl_xor_sync(0xffffffffu, y[i], 16);
+        const float rot = (lane < 16) ? -yj : yj;
+        o[i] = rbf(y[i] * cv[i]) + rbf(rot * sv[i]);
+    }
+    st_bf<EPL>(out + r * ldo + h * d + lane * EPL, o);
+}
+
+template <int EPL>
+__global__ void __launch_bounds__(256)
+headnorm_rope_bwd_vec_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int n_heads, const __nv_bfloat16* __restrict__ w,
+                             const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
+                             const int32_t* __restrict__ pos, int S, float eps, const __nv_bfloat16* __restrict__ g, int64_t ldg,
+                             __nv_bfloat16* __restrict__ dx, int64_t lddx, float* __restrict__ partial, int64_t M) {
+    constexpr int d = EPL * 32;
+    extern __shared__ float dw_s[];   // [8 warps][d]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float dw[EPL], wv[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) dw[i] = 0.f;
+    ld_bf<EPL>(w + lane * EPL, wv);
+    const int64_t items = M * n_heads;
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    int64_t item = (int64_t)blockIdx.x * 8 + wid;
+    // the next item's four vectors are requested before the current item's reductions (two items in flight per warp)
+    float xn[EPL], gn[EPL], cn[EPL], sn[EPL];
+    auto fetch = [&](int64_t it) {
+        const int h = (int)(it % n_heads);
+        const int64_t r = it / n_heads;
+        const int p = pos ? pos[r] : (int)(r % S);
+        ld_bf<EPL>(x + r * ldx + h * d + lane * EPL, xn);
+        ld_bf<EPL>(g + r * ldg + h * d + lane * EPL, gn);
+        ld_bf<EPL>(cos_t + (int64_t)p * d + lane * EPL, cn);
+        ld_bf<EPL>(sin_t + (int64_t)p * d + lane * EPL, sn);
+    };
+    if (item < items) fetch(item);
+    for (; item < items; item += stride) {
+        float xv[EPL], gv[EPL], cv[EPL], sv[EPL], dy[EPL], xh[EPL], o[EPL];
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) { xv[i] = xn[i]; gv[i] = gn[i]; cv[i] = cn[i]; sv[i] = sn[i]; }
+        if (item + stride < items) fetch(item + stride);
+        const int h = (int)(item % n_heads);
+        const int64_t r = item / n_heads;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) ss += xv[i] * xv[i];
+        ss = warp_sum(ss);
+        const float rstd = rsqrtf(ss / (float)d + eps);
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const float gs = __shfl_xor_sync(0xffffffffu, gv[i] * sv[i], 16);      // g_j * sin_j of the rotate_half partner
+            dy[i] = gv[i] * cv[i] + ((lane < 16) ? gs : -gs);
+            xh[i] = xv[i] * rstd;
+            dot += dy[i] * wv[i] * xh[i];
+            dw[i] += dy[i] * rbf(xh[i]);
+        }
+        dot = warp_sum(dot) / (float)d;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) o[i] = rstd * (dy[i] * wv[i] - xh[i] * dot);
+        st_bf<EPL>(dx + r * lddx + h * d + lane * EPL, o);
+    }
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) dw_s[wid * d + lane * EPL + i] = dw[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += dw_s[k * d + i];
+        partial[(int64_t)blockIdx.x * d + i] = t;
+    }
+}
+
 // dst[c] (+)= sum_b partial[b][c], fixed order
 __global__ void colsum_kernel(const float* __restrict__ partial, int nblocks, int d, float* __restrict__ dst, int accumulate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -589,7 +710,18 @@ int gather_rows(const void* table, const int32_t* ids, void* out, int64_t M, int
 int headnorm_rope_fwd(const void* x, int64_t ldx, int n_heads, int d, const void* w, const void* cos_t, const void* sin_t,
                       const int32_t* pos, int S, float eps, void* out, int64_t ldo, int64_t M, cudaStream_t st) {
     const int64_t warps = M * n_heads;
-    headnorm_rope_fwd_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+    const unsigned nblk = (unsigned)((warps * 32 + 255) / 256);
+    const bool vec = (ldx % 8 == 0) && (ldo % 8 == 0);       // vector loads need the rows aligned to the widest vector (16 B)
+#define SF_HN_FWD(EPL)                                                                                                       \
+    headnorm_rope_fwd_vec_kernel<EPL><<<nblk, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, n_heads, (const __nv_bfloat16*)w,  \
+        (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, pos, S, eps, (__nv_bfloat16*)out, ldo, M)
+    if (vec && (d == 32 || d == 64 || d == 128 || d == 256)) {
+        if (d == 32) SF_HN_FWD(1); else if (d == 64) SF_HN_FWD(2); else if (d == 128) SF_HN_FWD(4); else SF_HN_FWD(8);
+        SF_CUDA_CHECK_LAUNCH("dflash headnorm_rope_fwd");
+        return 0;
+    }
+#undef SF_HN_FWD
+    headnorm_rope_fwd_kernel<<<nblk, 256, 0, st>>>(
         (const __nv_bfloat16*)x, ldx, n_heads, d, (const __nv_bfloat16*)w, (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, pos, S,
         eps, (__nv_bfloat16*)out, ldo, M);
     SF_CUDA_CHECK_LAUNCH("dflash headnorm_rope_fwd");
@@ -598,9 +730,19 @@ int headnorm_rope_fwd(const void* x, int64_t ldx, int n_heads, int d, const void
 int headnorm_rope_bwd(const void* x, int64_t ldx, int n_heads, int d, const void* w, const void* cos_t, const void* sin_t,
                       const int32_t* pos, int S, float eps, const void* g, int64_t ldg, void* dx, int64_t lddx, float* dw,
                       int accumulate, float* partial_ws, int64_t M, cudaStream_t st) {
-    headnorm_rope_bwd_kernel<<<kNormBlocks, 256, 8 * d * 4, st>>>(
-        (const __nv_bfloat16*)x, ldx, n_heads, d, (const __nv_bfloat16*)w, (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, pos, S,
-        eps, (const __nv_bfloat16*)g, ldg, (__nv_bfloat16*)dx, lddx, partial_ws, M);
+    const bool vec = (ldx % 8 == 0) && (ldg % 8 == 0) && (lddx % 8 == 0);
+#define SF_HN_BWD(EPL)                                                                                                       \
+    headnorm_rope_bwd_vec_kernel<EPL><<<kNormBlocks, 256, 8 * d * 4, st>>>((const __nv_bfloat16*)x, ldx, n_heads,           \
+        (const __nv_bfloat16*)w, (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, pos, S, eps, (const __nv_bfloat16*)g, ldg, \
+        (__nv_bfloat16*)dx, lddx, partial_ws, M)
+    if (vec && (d == 32 || d == 64 || d == 128 || d == 256)) {
+        if (d == 32) SF_HN_BWD(1); else if (d == 64) SF_HN_BWD(2); else if (d == 128) SF_HN_BWD(4); else SF_HN_BWD(8);
+    } else {
+        headnorm_rope_bwd_kernel<<<kNormBlocks, 256, 8 * d * 4, st>>>(
+            (const __nv_bfloat16*)x, ldx, n_heads, d, (const __nv_bfloat16*)w, (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, pos, S,
+            eps, (const __nv_bfloat16*)g, ldg, (__nv_bfloat16*)dx, lddx, partial_ws, M);
+    }
+#undef SF_HN_BWD
     SF_CUDA_CHECK_LAUNCH("dflash headnorm_rope_bwd");
     colsum_kernel<<<(d + 127) / 128, 128, 0, st>>>(partial_ws, kNormBlocks, d, dw, accumulate);
     SF_CUDA_CHECK_LAUNCH("dflash colsum");
