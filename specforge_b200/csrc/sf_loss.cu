@@ -225,9 +225,10 @@ teacher_merge_kernel(const float* __restrict__ stats, int nb, int64_t M, const u
 // ------------------------------------------------------------------ fused loss / metrics / gradient
 // Reference: core/loss.py:15-21,49-170 (soft-label CE, mean over ALL rows, in-place backward),
 // core/lk_loss.py:43-80 (acceptance = sum_v min(p_on_draft, softmax)), eagle3/model.py:161-173 (top-1).
-// One block per row, two passes:
-//   A  logits row from HBM: online max / sum-exp / first-index argmax, ONE block reduction
-//   B  logits row again (L2-hot) + the gathered bf16 teacher logits: target_p re-evaluated (see teacher_kernel),
+// One block per row:
+//   A  (max, sum-exp, first-index argmax) of the row — normally merged from the partials the lm_head GEMM epilogue left
+//      (EPI_BF16_STATS: one partial per thread, one block reduction, the row is not read); without them an online pass over the row
+//   B  logits row + the gathered bf16 teacher logits: target_p re-evaluated (see teacher_kernel),
 //      soft-label CE sum, acceptance sum, and the gradient written over the logits row
 //          d loss / d x_v = coef * (softmax(x)_v * sum_v(target_p) - target_p_v),   sum_v(target_p) = 1
 // 192 KB of HBM traffic per 32000-wide row (64 read + 64 read + 64 written); no dynamic smem, <= 40 registers so three
