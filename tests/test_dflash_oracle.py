@@ -272,6 +272,13 @@ def test_sliding_layout_validation_and_the_checked_in_hybrid_config():
            "layer_types": ["sliding_attention"] * 4 + ["full_attention"], "use_sliding_window": True, "rope_scaling": None}
     dims = dims_from_config(cfg)
     assert dims.sliding_layout() == (2048, 0b01111)
+    ref_json = "/root/reference/configs/qwen3.6-27b-dflash.json"
+    if os.path.exists(ref_json):                       # the checked-in file itself, where the reference checkout is present
+        import json
+        with open(ref_json) as f:
+            real = dims_from_config(json.load(f))
+        assert real.sliding_layout() == (2048, 0b01111) and real.num_layers == 5 and real.hidden_size == 5120
+        assert real.num_target_feats == 5 and real.mask_token_id == 248070 and real.block_size == 16
     base = dict(hidden_size=64, intermediate_size=128, num_heads=4, num_kv_heads=2, head_dim=16, num_layers=2, num_target_feats=2, vocab_size=256)
     assert DFlashDims(**base).sliding_layout() == (0, 0)
     assert DFlashDims(**base, layer_types=("full_attention", "full_attention"), sliding_window=7).sliding_layout() == (0, 0)
