@@ -81,11 +81,19 @@ def test_dflash_param_layout_and_workspace(L):
     assert 20e9 < ws < 80e9, ws
     bad = SfDflashConfig(4, 2048, 512, 16, 4096, 5, 12288, 32, 8, 100, 5, 151936, 151669, 41000, 1e-6, 0.0)
     assert L.sf_dflash_workspace_bytes(bad) == 0 and b"multiples of 8" in L.sf_last_error()
+    # sliding-window layers (configs/qwen3.6-27b-dflash.json: 4 sliding + 1 full, W = 2048): the layout fields validate like
+    # resolve_dflash_attention_layout (modeling/draft/dflash.py:38-68)
+    base = (4, 2048, 512, 16, 4096, 5, 12288, 32, 8, 128, 5, 151936, 151669, 41000, 1e-6, 0.0, 0, 0, 0.5)
+    assert L.sf_dflash_num_params(SfDflashConfig(*base, 2048, 0b01111)) == n
+    assert L.sf_dflash_num_params(SfDflashConfig(*base, 0, 0b00001)) < 0 and b"positive sliding_window" in L.sf_last_error()
+    assert L.sf_dflash_num_params(SfDflashConfig(*base, 2048, 0b100000)) < 0 and b"num_layers" in L.sf_last_error()
 
 
 def test_debug_option_names(L):
     L.sf_debug_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
-    for name in (b"no_pdl", b"loss_side", b"no_overlap", b"no_swiglu_fusion", b"gemm_group_m", b"gemm_group_m_midk", b"gemm_group_m_wgrad"):
+    for name in (b"no_pdl", b"loss_side", b"no_overlap", b"no_swiglu_fusion", b"gemm_group_m", b"gemm_group_m_midk", b"gemm_group_m_wgrad",
+                 b"dflash_attn_tc", b"gemm_stages", b"no_teacher_fusion", b"no_loss_stats_fusion", b"gemm_wide", b"gemm_epi_staged",
+                 b"no_rope_fusion", b"gemm_epi8", b"dflash_attn_window"):
         assert L.sf_debug_option(name, 0) == 0, name
     assert L.sf_debug_option(b"no_such_switch", 1) != 0
     assert b"unknown option" in L.sf_last_error()
